@@ -1,0 +1,319 @@
+"""ctypes binding of include/fmb200.h.  Mirrors the C-ABI one to one; numpy arrays in, numpy arrays out."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+HIT_DTYPE = np.dtype([("qidx", "<u8"), ("lb", "<u8"), ("lb_rev", "<u8"), ("len", "<u8"), ("steps", "<u8"), ("e", "<u8")])
+LOC_DTYPE = np.dtype([("qidx", "<u8"), ("seq", "<u8"), ("pos", "<u8"), ("e", "<u8")])
+LOC32_DTYPE = np.dtype([("qidx", "<u4"), ("seq", "<u4"), ("pos", "<u4"), ("e", "<u4")])
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("sigma", C.c_uint32), ("bidirectional", C.c_uint32), ("n_samples", C.c_uint64),
+                ("n_delims", C.c_uint64), ("device_bytes", C.c_uint64), ("occ_block_bytes", C.c_uint32),
+                ("occ_block_rows", C.c_uint32), ("device", C.c_int32), ("reserved", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("extensions", C.c_uint64), ("occ_lookups", C.c_uint64), ("lf_steps", C.c_uint64),
+                ("frontier_peak", C.c_uint64), ("kernel_ms", C.c_double)]
+
+
+class FmbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"fmb200 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return _build.LIB
+
+
+# every symbol include/fmb200.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "fmb_last_error", "fmb_device_count", "fmb_version",
+    "fmb_index_create", "fmb_index_build", "fmb_index_destroy", "fmb_index_get_info", "fmb_index_get_C", "fmb_index_export",
+    "fmb_string_symbol", "fmb_string_rank", "fmb_string_prefix_rank", "fmb_string_all_ranks",
+    "fmb_cursor_extend", "fmb_cursor_extend_all",
+    "fmb_queries_upload", "fmb_queries_destroy", "fmb_queries_count",
+    "fmb_search_exact", "fmb_search_scheme", "fmb_search_backtracking", "fmb_locate",
+    "fmb_results_count", "fmb_results_kind", "fmb_results_fetch_hits", "fmb_results_fetch_locs", "fmb_results_fetch_locs32",
+    "fmb_results_get_stats", "fmb_results_destroy",
+    "fmb_search_and_locate",
+    "fmb_synth_text_device", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
+]
+
+
+def lib():
+    """Load libfmb200.so (building it first if sources are newer).  Raises if it cannot be loaded: the product
+    path has no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.build()
+    if not os.path.exists(path):
+        raise FmbError(-2, f"{path} missing: the CUDA extension is required")
+    L = C.CDLL(path)
+    L.fmb_last_error.restype = C.c_char_p
+    L.fmb_version.restype = C.c_char_p
+    L.fmb_results_count.restype = C.c_uint64
+    L.fmb_queries_count.restype = C.c_uint64
+    L.fmb_host_alloc_pinned.restype = C.c_void_p
+    L.fmb_host_alloc_pinned.argtypes = [C.c_uint64]
+    L.fmb_host_free_pinned.argtypes = [C.c_void_p]
+    for name in ("fmb_results_count", "fmb_results_kind", "fmb_results_destroy", "fmb_queries_destroy",
+                 "fmb_queries_count", "fmb_index_destroy"):
+        getattr(L, name).argtypes = [C.c_void_p]
+    _LIB = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise FmbError(rc, lib().fmb_last_error().decode())
+
+
+def device_count():
+    return lib().fmb_device_count()
+
+
+def _ptr(a, typ=C.c_void_p):
+    if a is None:
+        return typ()
+    return a.ctypes.data_as(typ)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+class Index:
+    """Device image of a BiFMIndex / FMIndex (fmindex/BiFMIndex.h, fmindex/FMIndex.h of the reference)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def from_bwt(cls, sigma, bwt, bwt_rev, sample_bitmap, sample_seq, sample_pos, device=0):
+        bwt = _u8(bwt)
+        bwt_rev = None if bwt_rev is None else _u8(bwt_rev)
+        bm, sq, sp = _u64(sample_bitmap), _u32(sample_seq), _u32(sample_pos)
+        h = C.c_void_p()
+        _check(lib().fmb_index_create(C.byref(h), C.c_int(device), C.c_uint32(sigma), C.c_uint64(bwt.size), _ptr(bwt),
+                                      _ptr(bwt_rev), _ptr(bm), _ptr(sq), _ptr(sp), C.c_uint64(sq.size)))
+        return cls(h)
+
+    @classmethod
+    def build(cls, sigma, text, sampling_rate=16, bidirectional=True, device=0):
+        """GPU construction from the concatenated text s0 0 s1 0 ... (numpy uint8 on the host)."""
+        text = _u8(text)
+        h = C.c_void_p()
+        _check(lib().fmb_index_build(C.byref(h), C.c_int(device), C.c_uint32(sigma), _ptr(text), C.c_uint64(text.size),
+                                     C.c_uint32(sampling_rate), C.c_int(1 if bidirectional else 0), C.c_int(0)))
+        return cls(h)
+
+    @classmethod
+    def build_from_device_text(cls, sigma, d_text_ptr, n, sampling_rate=16, bidirectional=True, device=0):
+        h = C.c_void_p()
+        _check(lib().fmb_index_build(C.byref(h), C.c_int(device), C.c_uint32(sigma), C.c_void_p(d_text_ptr), C.c_uint64(n),
+                                     C.c_uint32(sampling_rate), C.c_int(1 if bidirectional else 0), C.c_int(1)))
+        return cls(h)
+
+    def close(self):
+        if self.h:
+            lib().fmb_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def info(self):
+        i = IndexInfo()
+        _check(lib().fmb_index_get_info(self.h, C.byref(i)))
+        return i
+
+    @property
+    def C(self):
+        out = np.zeros(self.info.sigma + 1, dtype=np.uint64)
+        _check(lib().fmb_index_get_C(self.h, _ptr(out)))
+        return out
+
+    def export(self):
+        i = self.info
+        bwt = np.zeros(i.n, dtype=np.uint8)
+        rev = np.zeros(i.n, dtype=np.uint8) if i.bidirectional else None
+        bm = np.zeros((i.n + 63) // 64, dtype=np.uint64)
+        sq = np.zeros(i.n_samples, dtype=np.uint32)
+        sp = np.zeros(i.n_samples, dtype=np.uint32)
+        _check(lib().fmb_index_export(self.h, _ptr(bwt), _ptr(rev), _ptr(bm), _ptr(sq), _ptr(sp)))
+        return bwt, rev, bm, sq, sp
+
+    # String_c
+    def symbol(self, idx, dir=0):
+        idx = _u64(idx)
+        out = np.zeros(idx.size, dtype=np.uint8)
+        _check(lib().fmb_string_symbol(self.h, C.c_int(dir), _ptr(idx), C.c_uint64(idx.size), _ptr(out)))
+        return out
+
+    def rank(self, idx, symb, dir=0):
+        idx, symb = _u64(idx), _u8(symb)
+        out = np.zeros(idx.size, dtype=np.uint64)
+        _check(lib().fmb_string_rank(self.h, C.c_int(dir), _ptr(idx), _ptr(symb), C.c_uint64(idx.size), _ptr(out)))
+        return out
+
+    def prefix_rank(self, idx, symb, dir=0):
+        idx, symb = _u64(idx), _u8(symb)
+        out = np.zeros(idx.size, dtype=np.uint64)
+        _check(lib().fmb_string_prefix_rank(self.h, C.c_int(dir), _ptr(idx), _ptr(symb), C.c_uint64(idx.size), _ptr(out)))
+        return out
+
+    def all_ranks(self, idx, dir=0):
+        idx = _u64(idx)
+        s = self.info.sigma
+        rs = np.zeros((idx.size, s), dtype=np.uint64)
+        prs = np.zeros((idx.size, s), dtype=np.uint64)
+        _check(lib().fmb_string_all_ranks(self.h, C.c_int(dir), _ptr(idx), C.c_uint64(idx.size), _ptr(rs), _ptr(prs)))
+        return rs, prs
+
+    # cursors: arrays of shape (count, 4) = lb, lbRev, len, steps
+    def extend(self, cur, symb, right):
+        cur, symb = _u64(cur).reshape(-1, 4), _u8(symb)
+        out = np.zeros_like(cur)
+        _check(lib().fmb_cursor_extend(self.h, C.c_int(right), _ptr(cur), _ptr(symb), C.c_uint64(cur.shape[0]), _ptr(out)))
+        return out
+
+    def extend_all(self, cur, right):
+        cur = _u64(cur).reshape(-1, 4)
+        out = np.zeros((cur.shape[0], self.info.sigma, 4), dtype=np.uint64)
+        _check(lib().fmb_cursor_extend_all(self.h, C.c_int(right), _ptr(cur), C.c_uint64(cur.shape[0]), _ptr(out)))
+        return out
+
+    # searches
+    def upload(self, symbols, offsets):
+        return Queries(self, symbols, offsets)
+
+    def search_exact(self, queries):
+        r = C.c_void_p()
+        _check(lib().fmb_search_exact(self.h, queries.h, C.byref(r)))
+        return Results(r)
+
+    def search_scheme(self, queries, scheme, partition, edit):
+        pi, l, u = (np.ascontiguousarray(a, dtype=np.uint32) for a in scheme)
+        part = _u32(partition)
+        r = C.c_void_p()
+        _check(lib().fmb_search_scheme(self.h, queries.h, C.c_int(1 if edit else 0), C.c_uint32(pi.shape[0]),
+                                       C.c_uint32(pi.shape[1]), _ptr(pi), _ptr(l), _ptr(u), _ptr(part), C.byref(r)))
+        return Results(r)
+
+    def search_backtracking(self, queries, max_errors):
+        r = C.c_void_p()
+        _check(lib().fmb_search_backtracking(self.h, queries.h, C.c_uint32(max_errors), C.byref(r)))
+        return Results(r)
+
+    def locate(self, hits):
+        r = C.c_void_p()
+        _check(lib().fmb_locate(self.h, hits.h, C.byref(r)))
+        return Results(r)
+
+    def search_and_locate(self, symbols, offsets, scheme=None, partition=None, edit=False, capacity=None,
+                          out=None):
+        """One-call host-to-host path (fmb_search_and_locate).  symbols/offsets may be numpy arrays or raw
+        (pointer, count) pairs built on pinned memory."""
+        symbols, offsets = _u8(symbols), _u64(offsets)
+        nq = offsets.size - 1
+        if scheme is None:
+            ns, npart, pi, l, u, part = 0, 0, None, None, None, None
+        else:
+            pi, l, u = (np.ascontiguousarray(a, dtype=np.uint32) for a in scheme)
+            part = _u32(partition)
+            ns, npart = pi.shape
+        if out is None:
+            out = np.zeros(capacity if capacity is not None else max(nq, 1) * 4, dtype=LOC32_DTYPE)
+        n_out = C.c_uint64(0)
+        st = Stats()
+        _check(lib().fmb_search_and_locate(self.h, _ptr(symbols), _ptr(offsets), C.c_uint64(nq), C.c_int(1 if edit else 0),
+                                           C.c_uint32(ns), C.c_uint32(npart), _ptr(pi), _ptr(l), _ptr(u), _ptr(part),
+                                           _ptr(out), C.c_uint64(out.size), C.byref(n_out), C.byref(st)))
+        return out[: n_out.value], st
+
+
+class Queries:
+    def __init__(self, index, symbols, offsets):
+        symbols, offsets = _u8(symbols), _u64(offsets)
+        self.h = C.c_void_p()
+        _check(lib().fmb_queries_upload(C.byref(self.h), index.h, _ptr(symbols), _ptr(offsets), C.c_uint64(offsets.size - 1)))
+
+    def __len__(self):
+        return lib().fmb_queries_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().fmb_queries_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Results:
+    def __init__(self, handle):
+        self.h = handle
+
+    def __len__(self):
+        return lib().fmb_results_count(self.h)
+
+    @property
+    def kind(self):
+        return lib().fmb_results_kind(self.h)
+
+    @property
+    def stats(self):
+        s = Stats()
+        _check(lib().fmb_results_get_stats(self.h, C.byref(s)))
+        return s
+
+    def hits(self):
+        out = np.zeros(len(self), dtype=HIT_DTYPE)
+        _check(lib().fmb_results_fetch_hits(self.h, _ptr(out), C.c_uint64(out.size)))
+        return out
+
+    def locs(self):
+        out = np.zeros(len(self), dtype=LOC_DTYPE)
+        _check(lib().fmb_results_fetch_locs(self.h, _ptr(out), C.c_uint64(out.size)))
+        return out
+
+    def locs32(self):
+        out = np.zeros(len(self), dtype=LOC32_DTYPE)
+        _check(lib().fmb_results_fetch_locs32(self.h, _ptr(out), C.c_uint64(out.size)))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().fmb_results_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

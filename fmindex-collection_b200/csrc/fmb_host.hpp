@@ -1,0 +1,114 @@
+// fmb_host.hpp -- host-side objects behind the opaque handles of include/fmb200.h.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/fmb200.h"
+#include "fmb_device.cuh"
+
+namespace fmb {
+
+void set_error(const char* fmt, ...);
+
+#define FMB_CUDA(call)                                                                               \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            fmb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return e_ == cudaErrorMemoryAllocation ? FMB_ENOMEM : FMB_ECUDA;                         \
+        }                                                                                            \
+    } while (0)
+
+#define FMB_TRY(expr)                  \
+    do {                               \
+        int rc_ = (expr);              \
+        if (rc_ != FMB_OK) return rc_; \
+    } while (0)
+
+// device buffer with RAII
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            cudaGetLastError();
+            return FMB_ENOMEM;
+        }
+        n = count;
+        return FMB_OK;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// internal record formats (compact, 32-bit: n < 2^32)
+struct HitRec {
+    uint32_t qidx, lb, lb_rev, len, steps, e;
+};
+typedef fmb_loc32 LocRec;
+
+}  // namespace fmb
+
+struct fmb_index {
+    int device = 0;
+    uint32_t sigma = 0;
+    uint64_t n = 0;
+    bool bidirectional = false;
+    bool dna = true;
+    cudaStream_t stream = nullptr;
+    fmb::DevBuf<fmb::DnaBlock> occ_dna[2];
+    fmb::DevBuf<uint8_t> occ_gen[2];
+    uint32_t gen_stride = 0, gen_planes = 0;
+    fmb::DevBuf<uint32_t> delim_rows[2];
+    uint64_t n_delims = 0;
+    uint32_t delim0[2] = {0, 0};
+    fmb::DevBuf<uint4> marks;
+    fmb::DevBuf<uint2> samples;
+    uint64_t n_samples = 0;
+    uint64_t C[65] = {0};
+
+    fmb::IndexView<fmb::OccDna> view_dna() const;
+    fmb::IndexView<fmb::OccGen> view_gen() const;
+    uint64_t device_bytes() const;
+};
+
+struct fmb_queries {
+    int device = 0;
+    uint64_t nq = 0;
+    uint64_t total_symbols = 0;
+    uint32_t max_len = 0, min_len = 0;
+    fmb::DevBuf<uint8_t> symbols;     // padded to a multiple of 16 bytes
+    fmb::DevBuf<uint64_t> offsets;    // nq + 1
+};
+
+struct fmb_results {
+    int device = 0;
+    int kind = 0;                     // 0 = hits, 1 = located rows
+    uint64_t count = 0;
+    fmb::DevBuf<fmb::HitRec> hits;
+    fmb::DevBuf<fmb::LocRec> locs;
+    fmb_stats stats{};
+};

@@ -1,0 +1,652 @@
+// fmb_lib.cu -- index image construction (K1), String_c / cursor batch kernels, exact search (K2),
+// locate (K4), result compaction (K5) and the C-ABI of include/fmb200.h.
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+#include <cub/cub.cuh>
+
+#include "fmb_host.hpp"
+#include "fmb_kernels.cuh"
+
+namespace fmb {
+
+static thread_local std::string g_error = "";
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+static int use_device(int device) {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); libfmb200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return FMB_ENODEVICE;
+    }
+    if (device < 0 || device >= cnt) {
+        set_error("device %d out of range (have %d)", device, cnt);
+        return FMB_ENODEVICE;
+    }
+    FMB_CUDA(cudaSetDevice(device));
+    return FMB_OK;
+}
+
+static inline unsigned grid_for(uint64_t items, unsigned block) {
+    return (unsigned)std::max<uint64_t>(1, (items + block - 1) / block);
+}
+
+struct EventTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t s;
+    explicit EventTimer(cudaStream_t s_) : s(s_) {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, s);
+    }
+    double stop() {
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        return ms;
+    }
+    ~EventTimer() {
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+};
+
+// exclusive prefix sum of u32 -> u32 on `stream` (CUB; plumbing, not a hot kernel)
+static int exclusive_sum_u32(const uint32_t* in, uint32_t* out, uint64_t count, cudaStream_t stream) {
+    size_t tmp_bytes = 0;
+    FMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int64_t)count, stream));
+    DevBuf<uint8_t> tmp;
+    FMB_TRY(tmp.alloc(tmp_bytes));
+    FMB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, (int64_t)count, stream));
+    FMB_CUDA(cudaStreamSynchronize(stream));
+    return FMB_OK;
+}
+
+struct Uint4Add {
+    __host__ __device__ uint4 operator()(const uint4& a, const uint4& b) const {
+        return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+};
+
+}  // namespace fmb
+
+using namespace fmb;
+
+fmb::IndexView<fmb::OccDna> fmb_index::view_dna() const {
+    fmb::IndexView<fmb::OccDna> v{};
+    for (int d = 0; d < 2; ++d) {
+        v.occ[d].blocks = occ_dna[d].p;
+        v.occ[d].delim_rows = delim_rows[d].p;
+        v.occ[d].n_delims = (uint32_t)n_delims;
+        v.occ[d].delim0 = delim0[d];
+    }
+    for (uint32_t s = 0; s <= sigma; ++s) v.C[s] = (uint32_t)C[s];
+    v.n = (row_t)n;
+    v.sigma = sigma;
+    v.marks = marks.p;
+    v.samples = samples.p;
+    return v;
+}
+
+uint64_t fmb_index::device_bytes() const {
+    uint64_t b = 0;
+    for (int d = 0; d < 2; ++d) b += occ_dna[d].p ? occ_dna[d].bytes() : 0, b += occ_gen[d].p ? occ_gen[d].bytes() : 0, b += delim_rows[d].p ? delim_rows[d].bytes() : 0;
+    b += marks.p ? marks.bytes() : 0;
+    b += samples.p ? samples.bytes() : 0;
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// index construction from BWT bytes that are already on the device
+// ---------------------------------------------------------------------------------------------------------
+namespace fmb {
+
+// Builds occ table `dir` of `ix` from n BWT bytes at d_bwt (device).  Fails when a symbol is >= sigma.
+int build_occ_from_device_bwt(fmb_index* ix, int dir, const uint8_t* d_bwt) {
+    const uint64_t n = ix->n;
+    const uint64_t nblocks = n / 64 + 1;
+    cudaStream_t st = ix->stream;
+    if (!ix->dna) {
+        set_error("sigma %u: generic occurrence table not built in this call path", ix->sigma);
+        return FMB_EUNSUPPORTED;
+    }
+    FMB_TRY(ix->occ_dna[dir].alloc(nblocks));
+    DevBuf<uint4> counts;
+    FMB_TRY(counts.alloc(nblocks));
+    DevBuf<uint32_t> dflags;     // per block: number of delimiter rows, then scanned
+    FMB_TRY(dflags.alloc(nblocks + 1));
+    DevBuf<uint32_t> bad;
+    FMB_TRY(bad.alloc(1));
+    FMB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(uint32_t), st));
+    pack_dna_kernel<<<grid_for(nblocks + 1, 256), 256, 0, st>>>(d_bwt, n, ix->sigma, ix->occ_dna[dir].p, counts.p, dflags.p, bad.p);
+    FMB_CUDA(cudaGetLastError());
+    uint32_t h_bad = 0;
+    FMB_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, st));
+    FMB_CUDA(cudaStreamSynchronize(st));
+    if (h_bad) {
+        set_error("BWT contains a symbol >= sigma (%u)", ix->sigma);
+        return FMB_EINVAL;
+    }
+    // exclusive scan of the per-block symbol counts
+    {
+        size_t tmp_bytes = 0;
+        FMB_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp_bytes, counts.p, counts.p, Uint4Add{}, make_uint4(0, 0, 0, 0), (int64_t)nblocks, st));
+        DevBuf<uint8_t> tmp;
+        FMB_TRY(tmp.alloc(tmp_bytes));
+        FMB_CUDA(cub::DeviceScan::ExclusiveScan(tmp.p, tmp_bytes, counts.p, counts.p, Uint4Add{}, make_uint4(0, 0, 0, 0), (int64_t)nblocks, st));
+    }
+    store_counts_kernel<<<grid_for(nblocks, 256), 256, 0, st>>>(ix->occ_dna[dir].p, counts.p, nblocks);
+    FMB_CUDA(cudaGetLastError());
+    // delimiter rows: scan per-block delimiter counts, then scatter the rows
+    FMB_TRY(exclusive_sum_u32(dflags.p, dflags.p, nblocks + 1, st));
+    uint32_t nd = 0;
+    FMB_CUDA(cudaMemcpy(&nd, dflags.p + nblocks, sizeof nd, cudaMemcpyDeviceToHost));
+    if (dir == 0) ix->n_delims = nd;
+    else if (ix->n_delims != nd) {
+        set_error("bwt and bwtRev hold a different number of delimiters (%llu vs %u)", (unsigned long long)ix->n_delims, nd);
+        return FMB_EINVAL;
+    }
+    FMB_TRY(ix->delim_rows[dir].alloc((size_t)nd + 1));
+    FMB_CUDA(cudaMemsetAsync(ix->delim_rows[dir].p, 0xFF, ((size_t)nd + 1) * sizeof(uint32_t), st));
+    if (nd) {
+        scatter_delims_kernel<<<grid_for(nblocks, 256), 256, 0, st>>>(d_bwt, n, dflags.p, ix->delim_rows[dir].p);
+        FMB_CUDA(cudaGetLastError());
+    }
+    FMB_CUDA(cudaMemcpyAsync(&ix->delim0[dir], ix->delim_rows[dir].p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    FMB_CUDA(cudaStreamSynchronize(st));
+    return FMB_OK;
+}
+
+// C[s] = prefix_rank(n, s), s = 0..sigma (utils.h:200-206), evaluated with the device table itself
+int compute_C(fmb_index* ix) {
+    DevBuf<uint64_t> d_out;
+    FMB_TRY(d_out.alloc(ix->sigma + 1));
+    auto v = ix->view_dna();
+    compute_C_kernel<<<1, 64, 0, ix->stream>>>(v, d_out.p);
+    FMB_CUDA(cudaGetLastError());
+    FMB_CUDA(cudaMemcpyAsync(ix->C, d_out.p, (ix->sigma + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream));
+    FMB_CUDA(cudaStreamSynchronize(ix->stream));
+    return FMB_OK;
+}
+
+// sample tables from a device bitmap ((n+63)/64 words; rows >= n clear) and device sample arrays
+int build_marks_from_device(fmb_index* ix, const uint64_t* d_bitmap, const uint32_t* d_seq, const uint32_t* d_pos, uint64_t n_samples) {
+    const uint64_t words = ix->n / 64 + 1;
+    const uint64_t have = (ix->n + 63) / 64;
+    cudaStream_t st = ix->stream;
+    DevBuf<uint32_t> pc;
+    FMB_TRY(pc.alloc(words + 1));
+    popcount_words_kernel<<<grid_for(words + 1, 256), 256, 0, st>>>(d_bitmap, have, words + 1, pc.p);
+    FMB_CUDA(cudaGetLastError());
+    FMB_TRY(exclusive_sum_u32(pc.p, pc.p, words + 1, st));
+    uint32_t total = 0;
+    FMB_CUDA(cudaMemcpy(&total, pc.p + words, sizeof total, cudaMemcpyDeviceToHost));
+    if (total != n_samples) {
+        set_error("sample bitmap has %u set bits but n_samples = %llu", total, (unsigned long long)n_samples);
+        return FMB_EINVAL;
+    }
+    FMB_TRY(ix->marks.alloc(words));
+    build_marks_kernel<<<grid_for(words, 256), 256, 0, st>>>(d_bitmap, have, words, pc.p, ix->marks.p);
+    FMB_CUDA(cudaGetLastError());
+    FMB_TRY(ix->samples.alloc(n_samples));
+    if (n_samples) {
+        zip_samples_kernel<<<grid_for(n_samples, 256), 256, 0, st>>>(d_seq, d_pos, n_samples, ix->samples.p);
+        FMB_CUDA(cudaGetLastError());
+    }
+    ix->n_samples = n_samples;
+    FMB_CUDA(cudaStreamSynchronize(st));
+    return FMB_OK;
+}
+
+int new_index(fmb_index** out, int device, uint32_t sigma, uint64_t n, bool bidirectional) {
+    if (!out) { set_error("out is NULL"); return FMB_EINVAL; }
+    *out = nullptr;
+    if (sigma < 2 || sigma > 64) { set_error("sigma %u outside [2,64]", sigma); return FMB_EINVAL; }
+    if (n == 0) { set_error("empty index"); return FMB_EINVAL; }
+    if (n >= 0xFFFFFFFFull - 64) { set_error("n = %llu: this build supports n < 2^32 - 64", (unsigned long long)n); return FMB_EUNSUPPORTED; }
+    FMB_TRY(use_device(device));
+    fmb_index* ix = new fmb_index();
+    ix->device = device;
+    ix->sigma = sigma;
+    ix->n = n;
+    ix->bidirectional = bidirectional;
+    ix->dna = sigma <= 5;
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete ix; return FMB_ECUDA; }
+    *out = ix;
+    return FMB_OK;
+}
+
+template <typename T>
+static int upload(DevBuf<T>& buf, const T* host, size_t count, cudaStream_t st) {
+    FMB_TRY(buf.alloc(count));
+    if (count) FMB_CUDA(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    return FMB_OK;
+}
+
+}  // namespace fmb
+
+// =========================================================================================================
+// C-ABI
+// =========================================================================================================
+extern "C" {
+
+const char* fmb_last_error(void) { return fmb::g_error.c_str(); }
+const char* fmb_version(void) { return "fmb200 0.1 (sm_100a)"; }
+
+int fmb_device_count(void) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return cnt;
+}
+
+int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, const uint8_t* bwt, const uint8_t* bwt_rev,
+                     const uint64_t* sample_bitmap, const uint32_t* sample_seq, const uint32_t* sample_pos, uint64_t n_samples) {
+    if (!bwt) { set_error("bwt is NULL"); return FMB_EINVAL; }
+    if (n_samples && (!sample_bitmap || !sample_seq || !sample_pos)) { set_error("sample arrays missing"); return FMB_EINVAL; }
+    fmb_index* ix = nullptr;
+    FMB_TRY(new_index(&ix, device, sigma, n, bwt_rev != nullptr));
+    auto fail = [&](int rc) { fmb_index_destroy(ix); return rc; };
+    if (!ix->dna) { set_error("sigma %u > 5: generic occurrence table is not available yet", sigma); return fail(FMB_EUNSUPPORTED); }
+    {
+        DevBuf<uint8_t> d_bwt;
+        int rc = upload(d_bwt, bwt, n, ix->stream);
+        if (rc) return fail(rc);
+        rc = build_occ_from_device_bwt(ix, 0, d_bwt.p);
+        if (rc) return fail(rc);
+        if (bwt_rev) {
+            cudaError_t e = cudaMemcpyAsync(d_bwt.p, bwt_rev, n, cudaMemcpyHostToDevice, ix->stream);
+            if (e != cudaSuccess) { set_error("H2D bwtRev: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
+            rc = build_occ_from_device_bwt(ix, 1, d_bwt.p);
+            if (rc) return fail(rc);
+        }
+    }
+    int rc = compute_C(ix);
+    if (rc) return fail(rc);
+    {
+        const uint64_t have = (n + 63) / 64;
+        DevBuf<uint64_t> d_bm;
+        DevBuf<uint32_t> d_seq, d_pos;
+        std::vector<uint64_t> zero;
+        if (!sample_bitmap) { zero.assign(have, 0); sample_bitmap = zero.data(); }
+        rc = upload(d_bm, sample_bitmap, have, ix->stream);
+        if (rc) return fail(rc);
+        rc = upload(d_seq, sample_seq, n_samples, ix->stream);
+        if (rc) return fail(rc);
+        rc = upload(d_pos, sample_pos, n_samples, ix->stream);
+        if (rc) return fail(rc);
+        rc = build_marks_from_device(ix, d_bm.p, d_seq.p, d_pos.p, n_samples);
+        if (rc) return fail(rc);
+    }
+    *out = ix;
+    return FMB_OK;
+}
+
+void fmb_index_destroy(fmb_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+}
+
+int fmb_index_get_info(const fmb_index* ix, fmb_index_info* info) {
+    if (!ix || !info) { set_error("NULL argument"); return FMB_EINVAL; }
+    memset(info, 0, sizeof *info);
+    info->n = ix->n;
+    info->sigma = ix->sigma;
+    info->bidirectional = ix->bidirectional;
+    info->n_samples = ix->n_samples;
+    info->n_delims = ix->n_delims;
+    info->device_bytes = ix->device_bytes();
+    info->occ_block_bytes = ix->dna ? 32 : ix->gen_stride;
+    info->occ_block_rows = 64;
+    info->device = ix->device;
+    return FMB_OK;
+}
+
+int fmb_index_get_C(const fmb_index* ix, uint64_t* C) {
+    if (!ix || !C) { set_error("NULL argument"); return FMB_EINVAL; }
+    for (uint32_t s = 0; s <= ix->sigma; ++s) C[s] = ix->C[s];
+    return FMB_OK;
+}
+
+int fmb_index_export(const fmb_index* ix, uint8_t* bwt, uint8_t* bwt_rev, uint64_t* sample_bitmap, uint32_t* sample_seq, uint32_t* sample_pos) {
+    if (!ix) { set_error("NULL index"); return FMB_EINVAL; }
+    FMB_TRY(use_device(ix->device));
+    cudaStream_t st = ix->stream;
+    auto v = ix->view_dna();
+    for (int d = 0; d < 2; ++d) {
+        uint8_t* dst = d ? bwt_rev : bwt;
+        if (!dst) continue;
+        if (d == 1 && !ix->bidirectional) { set_error("index has no bwtRev"); return FMB_EINVAL; }
+        DevBuf<uint8_t> tmp;
+        FMB_TRY(tmp.alloc(ix->n));
+        unpack_bwt_kernel<<<grid_for(ix->n, 256), 256, 0, st>>>(v, d, tmp.p);
+        FMB_CUDA(cudaGetLastError());
+        FMB_CUDA(cudaMemcpyAsync(dst, tmp.p, ix->n, cudaMemcpyDeviceToHost, st));
+        FMB_CUDA(cudaStreamSynchronize(st));
+    }
+    if (sample_bitmap) {
+        const uint64_t have = (ix->n + 63) / 64;
+        DevBuf<uint64_t> tmp;
+        FMB_TRY(tmp.alloc(have));
+        export_marks_kernel<<<grid_for(have, 256), 256, 0, st>>>(ix->marks.p, have, tmp.p);
+        FMB_CUDA(cudaGetLastError());
+        FMB_CUDA(cudaMemcpyAsync(sample_bitmap, tmp.p, have * 8, cudaMemcpyDeviceToHost, st));
+        FMB_CUDA(cudaStreamSynchronize(st));
+    }
+    if ((sample_seq || sample_pos) && ix->n_samples) {
+        std::vector<uint2> h(ix->n_samples);
+        FMB_CUDA(cudaMemcpy(h.data(), ix->samples.p, ix->n_samples * sizeof(uint2), cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < ix->n_samples; ++i) {
+            if (sample_seq) sample_seq[i] = h[i].x;
+            if (sample_pos) sample_pos[i] = h[i].y;
+        }
+    }
+    return FMB_OK;
+}
+
+// ---- String_c batch ops -----------------------------------------------------------------------------------
+static int string_op(const fmb_index* ix, int dir, int op, const uint64_t* idx, const uint8_t* symb, uint64_t count,
+                     uint64_t* out64, uint8_t* out8, uint64_t* out_prs) {
+    if (!ix || !idx) { set_error("NULL argument"); return FMB_EINVAL; }
+    if (dir < 0 || dir > 1 || (dir == 1 && !ix->bidirectional)) { set_error("dir %d not available", dir); return FMB_EINVAL; }
+    FMB_TRY(use_device(ix->device));
+    if (count == 0) return FMB_OK;
+    for (uint64_t i = 0; i < count; ++i) {
+        uint64_t lim = (op == 0) ? ix->n - 1 : ix->n;
+        if (idx[i] > lim) { set_error("idx[%llu] = %llu out of range", (unsigned long long)i, (unsigned long long)idx[i]); return FMB_EINVAL; }
+        if (symb && ((op == 2) ? symb[i] > ix->sigma : symb[i] >= ix->sigma)) { set_error("symbol %u out of range", symb[i]); return FMB_EINVAL; }
+    }
+    cudaStream_t st = ix->stream;
+    DevBuf<uint64_t> d_idx, d_out, d_out2;
+    DevBuf<uint8_t> d_symb;
+    FMB_TRY(upload(d_idx, idx, count, st));
+    if (symb) FMB_TRY(upload(d_symb, symb, count, st));
+    size_t per = (op == 3) ? ix->sigma : 1;
+    FMB_TRY(d_out.alloc(count * per));
+    if (op == 3) FMB_TRY(d_out2.alloc(count * per));
+    auto v = ix->view_dna();
+    string_op_kernel<<<grid_for(count, 128), 128, 0, st>>>(v, dir, op, d_idx.p, d_symb.p, count, d_out.p, d_out2.p);
+    FMB_CUDA(cudaGetLastError());
+    std::vector<uint64_t> h(count * per);
+    FMB_CUDA(cudaMemcpyAsync(h.data(), d_out.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+    FMB_CUDA(cudaStreamSynchronize(st));
+    if (out8) for (uint64_t i = 0; i < count; ++i) out8[i] = (uint8_t)h[i];
+    if (out64) memcpy(out64, h.data(), h.size() * 8);
+    if (op == 3 && out_prs) FMB_CUDA(cudaMemcpy(out_prs, d_out2.p, h.size() * 8, cudaMemcpyDeviceToHost));
+    return FMB_OK;
+}
+
+int fmb_string_symbol(const fmb_index* ix, int dir, const uint64_t* idx, uint64_t count, uint8_t* out) {
+    return string_op(ix, dir, 0, idx, nullptr, count, nullptr, out, nullptr);
+}
+int fmb_string_rank(const fmb_index* ix, int dir, const uint64_t* idx, const uint8_t* symb, uint64_t count, uint64_t* out) {
+    if (!symb) { set_error("symb is NULL"); return FMB_EINVAL; }
+    return string_op(ix, dir, 1, idx, symb, count, out, nullptr, nullptr);
+}
+int fmb_string_prefix_rank(const fmb_index* ix, int dir, const uint64_t* idx, const uint8_t* symb, uint64_t count, uint64_t* out) {
+    if (!symb) { set_error("symb is NULL"); return FMB_EINVAL; }
+    return string_op(ix, dir, 2, idx, symb, count, out, nullptr, nullptr);
+}
+int fmb_string_all_ranks(const fmb_index* ix, int dir, const uint64_t* idx, uint64_t count, uint64_t* out_rs, uint64_t* out_prs) {
+    return string_op(ix, dir, 3, idx, nullptr, count, out_rs, nullptr, out_prs);
+}
+
+// ---- cursor batch ops ---------------------------------------------------------------------------------------
+static int cursor_op(const fmb_index* ix, int right, const uint64_t* cur, const uint8_t* symb, uint64_t count, uint64_t* out, bool all) {
+    if (!ix || !cur || !out) { set_error("NULL argument"); return FMB_EINVAL; }
+    if (!ix->bidirectional) { set_error("cursor ops need a bidirectional index"); return FMB_EINVAL; }
+    FMB_TRY(use_device(ix->device));
+    if (count == 0) return FMB_OK;
+    for (uint64_t i = 0; i < count; ++i) {
+        if (cur[4 * i] + cur[4 * i + 2] > ix->n || cur[4 * i + 1] + cur[4 * i + 2] > ix->n) { set_error("cursor %llu out of range", (unsigned long long)i); return FMB_EINVAL; }
+        if (!all && symb[i] >= ix->sigma) { set_error("symbol out of range"); return FMB_EINVAL; }
+    }
+    cudaStream_t st = ix->stream;
+    DevBuf<uint64_t> d_cur, d_out;
+    DevBuf<uint8_t> d_symb;
+    FMB_TRY(upload(d_cur, cur, count * 4, st));
+    if (!all) FMB_TRY(upload(d_symb, symb, count, st));
+    size_t per = all ? ix->sigma : 1;
+    FMB_TRY(d_out.alloc(count * per * 4));
+    auto v = ix->view_dna();
+    cursor_op_kernel<<<grid_for(count, 128), 128, 0, st>>>(v, right, all ? 1 : 0, d_cur.p, d_symb.p, count, d_out.p);
+    FMB_CUDA(cudaGetLastError());
+    FMB_CUDA(cudaMemcpyAsync(out, d_out.p, count * per * 4 * 8, cudaMemcpyDeviceToHost, st));
+    FMB_CUDA(cudaStreamSynchronize(st));
+    return FMB_OK;
+}
+int fmb_cursor_extend(const fmb_index* ix, int right, const uint64_t* cur, const uint8_t* symb, uint64_t count, uint64_t* out) {
+    if (!symb) { set_error("symb is NULL"); return FMB_EINVAL; }
+    return cursor_op(ix, right, cur, symb, count, out, false);
+}
+int fmb_cursor_extend_all(const fmb_index* ix, int right, const uint64_t* cur, uint64_t count, uint64_t* out) {
+    return cursor_op(ix, right, cur, nullptr, count, out, true);
+}
+
+// ---- queries ------------------------------------------------------------------------------------------------
+int fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq) {
+    if (!out || !ix || !offsets) { set_error("NULL argument"); return FMB_EINVAL; }
+    *out = nullptr;
+    if (nq >= 0xFFFFFFFFull) { set_error("too many queries in one batch"); return FMB_EUNSUPPORTED; }
+    FMB_TRY(use_device(ix->device));
+    uint64_t total = offsets[nq] - offsets[0];
+    if (total && !symbols) { set_error("symbols is NULL"); return FMB_EINVAL; }
+    auto q = new fmb_queries();
+    q->device = ix->device;
+    q->nq = nq;
+    q->total_symbols = total;
+    uint32_t mx = 0, mn = 0xFFFFFFFFu;
+    for (uint64_t i = 0; i < nq; ++i) {
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0xFFFFu) {
+            set_error("query %llu: offsets not monotone or query longer than 65535", (unsigned long long)i);
+            delete q;
+            return FMB_EINVAL;
+        }
+        uint32_t L = (uint32_t)(offsets[i + 1] - offsets[i]);
+        mx = std::max(mx, L);
+        mn = std::min(mn, L);
+    }
+    q->max_len = mx;
+    q->min_len = nq ? mn : 0;
+    cudaStream_t st = ix->stream;
+    int rc = q->symbols.alloc(total + 32);
+    if (!rc) rc = q->offsets.alloc(nq + 1);
+    if (rc) { delete q; return rc; }
+    cudaError_t e = cudaSuccess;
+    if (total) e = cudaMemcpyAsync(q->symbols.p, symbols + offsets[0], total, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(q->symbols.p + total, 0xFF, 32, st);
+    if (e == cudaSuccess) {
+        if (offsets[0] == 0) {
+            e = cudaMemcpyAsync(q->offsets.p, offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, st);
+        } else {
+            std::vector<uint64_t> rel(nq + 1);
+            for (uint64_t i = 0; i <= nq; ++i) rel[i] = offsets[i] - offsets[0];
+            e = cudaMemcpyAsync(q->offsets.p, rel.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("query upload: %s", cudaGetErrorString(e)); delete q; return FMB_ECUDA; }
+    *out = q;
+    return FMB_OK;
+}
+void fmb_queries_destroy(fmb_queries* q) {
+    if (!q) return;
+    cudaSetDevice(q->device);
+    delete q;
+}
+uint64_t fmb_queries_count(const fmb_queries* q) { return q ? q->nq : 0; }
+
+// ---- exact search (K2) + compaction (K5) ---------------------------------------------------------------------
+int fmb_search_exact(const fmb_index* ix, const fmb_queries* q, fmb_results** out) {
+    if (!ix || !q || !out) { set_error("NULL argument"); return FMB_EINVAL; }
+    *out = nullptr;
+    if (q->device != ix->device) { set_error("queries live on device %d, index on %d", q->device, ix->device); return FMB_EINVAL; }
+    FMB_TRY(use_device(ix->device));
+    cudaStream_t st = ix->stream;
+    auto res = new fmb_results();
+    res->device = ix->device;
+    res->kind = 0;
+    auto fail = [&](int rc) { delete res; return rc; };
+    const uint64_t nq = q->nq;
+    DevBuf<uint32_t> lb, len, pos;
+    DevBuf<unsigned long long> ctr;
+    int rc;
+    if ((rc = lb.alloc(nq)) || (rc = len.alloc(nq + 1)) || (rc = pos.alloc(nq + 1)) || (rc = ctr.alloc(4))) return fail(rc);
+    cudaMemsetAsync(ctr.p, 0, 4 * sizeof(unsigned long long), st);
+    cudaMemsetAsync(len.p + nq, 0, sizeof(uint32_t), st);
+    auto v = ix->view_dna();
+    EventTimer tm(st);
+    if (nq) {
+        exact_search_kernel<OccDna, true><<<grid_for(nq, 256), 256, 0, st>>>(v, q->symbols.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("exact_search_kernel: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
+        flag_nonzero_kernel<<<grid_for(nq + 1, 256), 256, 0, st>>>(len.p, nq + 1, pos.p);
+    } else {
+        cudaMemsetAsync(pos.p, 0, sizeof(uint32_t), st);
+    }
+    if ((rc = exclusive_sum_u32(pos.p, pos.p, nq + 1, st))) return fail(rc);
+    uint32_t nhits = 0;
+    if (cudaMemcpy(&nhits, pos.p + nq, sizeof nhits, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H count failed"); return fail(FMB_ECUDA); }
+    if ((rc = res->hits.alloc(nhits))) return fail(rc);
+    if (nhits) compact_exact_hits_kernel<<<grid_for(nq, 256), 256, 0, st>>>(lb.p, len.p, pos.p, q->offsets.p, (uint32_t)nq, res->hits.p);
+    res->stats.kernel_ms = tm.stop();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("exact search: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
+    unsigned long long h_ctr[4];
+    cudaMemcpy(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost);
+    res->stats.extensions = h_ctr[0];
+    res->stats.occ_lookups = h_ctr[1];
+    res->count = nhits;
+    *out = res;
+    return FMB_OK;
+}
+
+// ---- locate (K4) ------------------------------------------------------------------------------------------------
+int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) {
+    if (!ix || !hits || !out) { set_error("NULL argument"); return FMB_EINVAL; }
+    *out = nullptr;
+    if (hits->kind != 0) { set_error("fmb_locate needs a hit result set"); return FMB_EINVAL; }
+    if (hits->device != ix->device) { set_error("results live on another device"); return FMB_EINVAL; }
+    FMB_TRY(use_device(ix->device));
+    cudaStream_t st = ix->stream;
+    auto res = new fmb_results();
+    res->device = ix->device;
+    res->kind = 1;
+    auto fail = [&](int rc) { delete res; return rc; };
+    const uint64_t nh = hits->count;
+    DevBuf<uint32_t> starts;
+    DevBuf<unsigned long long> ctr;
+    int rc;
+    if ((rc = starts.alloc(nh + 1)) || (rc = ctr.alloc(4))) return fail(rc);
+    cudaMemsetAsync(ctr.p, 0, 4 * sizeof(unsigned long long), st);
+    EventTimer tm(st);
+    hit_lengths_kernel<<<grid_for(nh + 1, 256), 256, 0, st>>>(hits->hits.p, nh, starts.p);
+    if ((rc = exclusive_sum_u32(starts.p, starts.p, nh + 1, st))) return fail(rc);
+    uint32_t total = 0;
+    if (cudaMemcpy(&total, starts.p + nh, sizeof total, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H count failed"); return fail(FMB_ECUDA); }
+    // note: the sum of interval lengths must fit 32 bits in this build
+    if ((rc = res->locs.alloc(total))) return fail(rc);
+    if (total) {
+        auto v = ix->view_dna();
+        locate_kernel<OccDna, true><<<grid_for(total, 256), 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p);
+    }
+    res->stats.kernel_ms = tm.stop();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("locate: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
+    unsigned long long h_ctr[4];
+    cudaMemcpy(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost);
+    res->stats.lf_steps = h_ctr[2];
+    res->stats.occ_lookups = h_ctr[1];
+    res->count = total;
+    *out = res;
+    return FMB_OK;
+}
+
+// ---- results ----------------------------------------------------------------------------------------------------
+uint64_t fmb_results_count(const fmb_results* r) { return r ? r->count : 0; }
+int fmb_results_kind(const fmb_results* r) { return r ? r->kind : -1; }
+
+int fmb_results_fetch_hits(const fmb_results* r, fmb_hit* out, uint64_t capacity) {
+    if (!r || (!out && r->count)) { set_error("NULL argument"); return FMB_EINVAL; }
+    if (r->kind != 0) { set_error("result set holds located rows, not hits"); return FMB_EINVAL; }
+    if (capacity < r->count) { set_error("capacity %llu < %llu hits", (unsigned long long)capacity, (unsigned long long)r->count); return FMB_EOVERFLOW; }
+    FMB_TRY(use_device(r->device));
+    std::vector<HitRec> h(r->count);
+    if (r->count) FMB_CUDA(cudaMemcpy(h.data(), r->hits.p, r->count * sizeof(HitRec), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < r->count; ++i) out[i] = fmb_hit{h[i].qidx, h[i].lb, h[i].lb_rev, h[i].len, h[i].steps, h[i].e};
+    return FMB_OK;
+}
+int fmb_results_fetch_locs32(const fmb_results* r, fmb_loc32* out, uint64_t capacity) {
+    if (!r || (!out && r->count)) { set_error("NULL argument"); return FMB_EINVAL; }
+    if (r->kind != 1) { set_error("result set holds hits, not located rows"); return FMB_EINVAL; }
+    if (capacity < r->count) { set_error("capacity %llu < %llu rows", (unsigned long long)capacity, (unsigned long long)r->count); return FMB_EOVERFLOW; }
+    FMB_TRY(use_device(r->device));
+    if (r->count) FMB_CUDA(cudaMemcpy(out, r->locs.p, r->count * sizeof(LocRec), cudaMemcpyDeviceToHost));
+    return FMB_OK;
+}
+int fmb_results_fetch_locs(const fmb_results* r, fmb_loc* out, uint64_t capacity) {
+    if (!r || (!out && r->count)) { set_error("NULL argument"); return FMB_EINVAL; }
+    if (r->kind != 1) { set_error("result set holds hits, not located rows"); return FMB_EINVAL; }
+    if (capacity < r->count) { set_error("capacity too small"); return FMB_EOVERFLOW; }
+    std::vector<fmb_loc32> h(r->count);
+    FMB_TRY(fmb_results_fetch_locs32(r, h.data(), r->count));
+    for (uint64_t i = 0; i < r->count; ++i) out[i] = fmb_loc{h[i].qidx, h[i].seq, h[i].pos, h[i].e};
+    return FMB_OK;
+}
+int fmb_results_get_stats(const fmb_results* r, fmb_stats* out) {
+    if (!r || !out) { set_error("NULL argument"); return FMB_EINVAL; }
+    *out = r->stats;
+    return FMB_OK;
+}
+void fmb_results_destroy(fmb_results* r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    delete r;
+}
+
+// ---- helpers ------------------------------------------------------------------------------------------------------
+int fmb_synth_text_device(int device, uint32_t sigma, uint64_t n, uint64_t seed, uint8_t** d_text) {
+    if (!d_text || sigma < 2 || n == 0) { set_error("bad argument"); return FMB_EINVAL; }
+    FMB_TRY(use_device(device));
+    uint8_t* p = nullptr;
+    FMB_CUDA(cudaMalloc(&p, n));
+    synth_text_kernel<<<grid_for(n, 256), 256>>>(p, n, sigma, seed);
+    FMB_CUDA(cudaGetLastError());
+    FMB_CUDA(cudaDeviceSynchronize());
+    *d_text = p;
+    return FMB_OK;
+}
+int fmb_device_free(int device, void* p) {
+    FMB_TRY(use_device(device));
+    FMB_CUDA(cudaFree(p));
+    return FMB_OK;
+}
+int fmb_copy_to_host(int device, void* dst_host, const void* src_device, uint64_t bytes) {
+    FMB_TRY(use_device(device));
+    FMB_CUDA(cudaMemcpy(dst_host, src_device, bytes, cudaMemcpyDeviceToHost));
+    return FMB_OK;
+}
+void* fmb_host_alloc_pinned(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); set_error("cudaMallocHost(%llu) failed", (unsigned long long)bytes); return nullptr; }
+    return p;
+}
+void fmb_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

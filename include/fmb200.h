@@ -1,0 +1,187 @@
+/* fmb200.h -- C-ABI of libfmb200.so: B200-native batched FM-index search.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of SGSSGene/fmindex-collection.
+ * The reference is a header-only C++ template library without an FFI; the C++ shim in include/fmb200/ mirrors
+ * its search entry points 1:1 and calls only the functions declared here.  Every entry point names the
+ * reference interface it replaces (paths relative to /root/reference/src/fmindex-collection/).
+ *
+ * Conventions
+ *   - plain C types; the caller owns every host buffer, the library owns all device memory;
+ *   - every function returns 0 on success or a negative FMB_E* code; fmb_last_error() (thread local) has the text;
+ *   - no CPU fallback: without a usable CUDA device every compute entry point fails with FMB_ENODEVICE;
+ *   - symbols are uint8_t in [0, sigma); symbol 0 is the sequence delimiter (fmindex/BiFMIndex.h:26 FirstSymb=1);
+ *   - rows / text positions are 64-bit in the interface; this build supports indices with n < 2^32 - 64 rows;
+ *   - one fmb_index lives on one GPU.  Multi-GPU = one index replica per device, queries sharded by the caller
+ *     (fmb200/multi.hpp and bench.py do exactly that); there is no collective on the search path.
+ */
+#ifndef FMB200_H
+#define FMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMB_OK          0
+#define FMB_EINVAL     -1   /* bad argument                                              */
+#define FMB_ENODEVICE  -2   /* no CUDA device / device index out of range                */
+#define FMB_ECUDA      -3   /* a CUDA runtime call or kernel failed                      */
+#define FMB_ENOMEM     -4   /* host or device allocation failed                          */
+#define FMB_EUNSUPPORTED -5 /* valid request outside what this build implements          */
+#define FMB_EOVERFLOW  -6   /* result/frontier capacity exceeded and growing was refused */
+
+typedef struct fmb_index   fmb_index;    /* device image of a BiFMIndex / FMIndex                         */
+typedef struct fmb_queries fmb_queries;  /* device-resident query batch                                   */
+typedef struct fmb_results fmb_results;  /* device-resident result set: cursors (hits) or located rows    */
+
+/* One reported cursor = the arguments of the reference delegate `(size_t qidx, cursor, size_t e)`
+ * (search/SearchNg26.h:414-421); cursor = BiFMIndexCursor{lb, lbRev, len, steps} (fmindex/BiFMIndexCursor.h:22-37).
+ * Unidirectional / exact searches report lb_rev = 0 (LeftBiFMIndexCursor has none, BiFMIndexCursor.h:203-256). */
+typedef struct {
+    uint64_t qidx, lb, lb_rev, len, steps, e;
+} fmb_hit;
+
+/* One located row = the arguments of fmc::Search's report callback `(qidx, seqId, pos + offset, e)`
+ * (search/search.h:55-60) with (seqId, pos, offset) = index.locate(row) (fmindex/BiFMIndex.h:177-202). */
+typedef struct {
+    uint64_t qidx, seq, pos, e;
+} fmb_loc;
+
+/* compact form of fmb_loc for bulk transfers (valid because n < 2^32 in this build) */
+typedef struct {
+    uint32_t qidx, seq, pos, e;
+} fmb_loc32;
+
+typedef struct {
+    uint64_t n;                /* rows = text length incl. delimiters                      */
+    uint32_t sigma;
+    uint32_t bidirectional;    /* 1 = BiFMIndex, 0 = FMIndex                               */
+    uint64_t n_samples;        /* sampled suffix-array entries                             */
+    uint64_t n_delims;         /* rows of the BWT holding symbol 0                         */
+    uint64_t device_bytes;     /* HBM used by the index image                              */
+    uint32_t occ_block_bytes;  /* bytes fetched by one rank lookup (32 for sigma<=5)       */
+    uint32_t occ_block_rows;   /* BWT rows covered by one occ block                        */
+    int32_t  device;
+    uint32_t reserved;
+} fmb_index_info;
+
+/* work counters of the last search/locate call on a result set (device-side counting, optional) */
+typedef struct {
+    uint64_t extensions;       /* cursor extensions executed                                */
+    uint64_t occ_lookups;      /* occ blocks fetched (1 when both interval ends share a block, else 2) */
+    uint64_t lf_steps;         /* LF steps walked by locate                                 */
+    uint64_t frontier_peak;    /* largest breadth-first frontier (scheme search)            */
+    double   kernel_ms;        /* device time of the call (CUDA events)                     */
+} fmb_stats;
+
+const char* fmb_last_error(void);
+int fmb_device_count(void);                       /* number of CUDA devices, 0 if none     */
+const char* fmb_version(void);
+
+/* ---- index ---------------------------------------------------------------------------------------------- */
+
+/* Replaces the constructors BiFMIndex(bwt, bwtRev, SparseArray) (fmindex/BiFMIndex.h:40-51) and
+ * FMIndex(bwt, SparseArray) (fmindex/FMIndex.h:28-32): takes the BWT bytes (and the BWT of the reversed text,
+ * NULL for a unidirectional index) plus the sampled suffix array in the generic form "bit i of sample_bitmap
+ * set <=> row i carries a sample; samples listed in row order" (suffixarray/SparseArray.h:44-70).
+ * Builds the device occurrence tables (K1), C (utils.h:200-206) and the sample tables. */
+int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n,
+                     const uint8_t* bwt, const uint8_t* bwt_rev,
+                     const uint64_t* sample_bitmap, const uint32_t* sample_seq, const uint32_t* sample_pos,
+                     uint64_t n_samples);
+
+/* Replaces BiFMIndex(Sequences, samplingRate, threads) (fmindex/BiFMIndex.h:107-167) / FMIndex(Sequences, ...)
+ * (fmindex/FMIndex.h:58-112): `text` is the concatenation s0 0 s1 0 ... built by createSequences
+ * (utils.h:382-464).  Suffix sorting (libsais in the reference, utils.h:97-129), BWT (utils.h:145-163), the BWT
+ * of the reversed text (BiFMIndex.h:82-91) and the text-space sampling `pos_in_sequence % rate == 0`
+ * (BiFMIndex.h:121-135) all run on the GPU.  text may be a host pointer, or a device pointer on `device` when
+ * text_on_device != 0. */
+int fmb_index_build(fmb_index** out, int device, uint32_t sigma, const uint8_t* text, uint64_t n,
+                    uint32_t sampling_rate, int bidirectional, int text_on_device);
+
+void fmb_index_destroy(fmb_index* ix);
+int  fmb_index_get_info(const fmb_index* ix, fmb_index_info* info);
+int  fmb_index_get_C(const fmb_index* ix, uint64_t* C /* sigma+1 */);           /* member C, BiFMIndex.h:34 */
+
+/* Export the index content to host buffers (any pointer may be NULL): BWT bytes (n each), sample bitmap
+ * ((n+63)/64 words), samples (n_samples each).  Lets a host-side reference index be constructed from exactly
+ * the same data (BiFMIndex.h:40). */
+int fmb_index_export(const fmb_index* ix, uint8_t* bwt, uint8_t* bwt_rev, uint64_t* sample_bitmap,
+                     uint32_t* sample_seq, uint32_t* sample_pos);
+
+/* ---- String_c concept, batched (string/concepts.h:26-87).  dir 0 = bwt, 1 = bwtRev.  All pointers host. ---- */
+int fmb_string_symbol(const fmb_index* ix, int dir, const uint64_t* idx, uint64_t count, uint8_t* out);
+int fmb_string_rank(const fmb_index* ix, int dir, const uint64_t* idx, const uint8_t* symb, uint64_t count, uint64_t* out);
+int fmb_string_prefix_rank(const fmb_index* ix, int dir, const uint64_t* idx, const uint8_t* symb, uint64_t count, uint64_t* out);
+/* out_rs / out_prs: count x sigma, row-major; out_prs may be NULL (all_ranks vs all_ranks_and_prefix_ranks) */
+int fmb_string_all_ranks(const fmb_index* ix, int dir, const uint64_t* idx, uint64_t count, uint64_t* out_rs, uint64_t* out_prs);
+
+/* ---- cursor steps, batched (fmindex/BiFMIndexCursor.h:113-128 extendLeft/Right(symb); :58-82 all symbols) ---- */
+/* cur/out: count x 4 words {lb, lbRev, len, steps}; symb[i] < sigma extends by one symbol */
+int fmb_cursor_extend(const fmb_index* ix, int right, const uint64_t* cur, const uint8_t* symb, uint64_t count, uint64_t* out);
+/* out: count x sigma x 4 words */
+int fmb_cursor_extend_all(const fmb_index* ix, int right, const uint64_t* cur, uint64_t count, uint64_t* out);
+
+/* ---- queries --------------------------------------------------------------------------------------------- */
+
+/* `Sequences queries` of the reference (concepts.h:12-24), flattened: symbols of all queries back to back and
+ * offsets[nq+1].  Host pointers (pinned memory is copied faster).  The batch is bound to the device of `ix`. */
+int  fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq);
+void fmb_queries_destroy(fmb_queries* q);
+uint64_t fmb_queries_count(const fmb_queries* q);
+
+/* ---- searches (results stay on the device until fetched) -------------------------------------------------- */
+
+/* search_no_errors::search(index, queries, delegate) (search/SearchNoErrors.h:13-26 per query, :29-85 batched).
+ * One hit per query with a non-empty interval; works on both index kinds. */
+int fmb_search_exact(const fmb_index* ix, const fmb_queries* q, fmb_results** out);
+
+/* search_ng26::search<Edit>(index, queries, scheme, partition, delegate) (search/SearchNg26.h:427-433).
+ * Scheme = n_searches x n_parts arrays pi, l, u (search_scheme/Search.h:19-28, pi zero based as produced by
+ * search_scheme/generator/*.h); partition = n_parts part lengths (search_scheme/expand.h:324-343).
+ * Every query must have length sum(partition).  Reports every cursor the reference reports (as a multiset). */
+int fmb_search_scheme(const fmb_index* ix, const fmb_queries* q, int edit,
+                      uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l, const uint32_t* u,
+                      const uint32_t* partition, fmb_results** out);
+
+/* search_backtracking::search(index, queries, maxError, delegate) (search/Backtracking.h:85-88); Hamming,
+ * works on unidirectional indices. */
+int fmb_search_backtracking(const fmb_index* ix, const fmb_queries* q, uint32_t max_errors, fmb_results** out);
+
+/* LocateLinear{index, cursor} over every row of every hit (locate.h:15-57) with index.locate(row)
+ * (BiFMIndex.h:177-202, FMIndex.h:114-124); output rows carry pos + offset like search/search.h:55-60. */
+int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out);
+
+/* ---- results ----------------------------------------------------------------------------------------------- */
+uint64_t fmb_results_count(const fmb_results* r);
+int  fmb_results_kind(const fmb_results* r);                /* 0 = hits (cursors), 1 = located rows */
+int  fmb_results_fetch_hits(const fmb_results* r, fmb_hit* out, uint64_t capacity);
+int  fmb_results_fetch_locs(const fmb_results* r, fmb_loc* out, uint64_t capacity);
+int  fmb_results_fetch_locs32(const fmb_results* r, fmb_loc32* out, uint64_t capacity);
+int  fmb_results_get_stats(const fmb_results* r, fmb_stats* out);
+void fmb_results_destroy(fmb_results* r);
+
+/* ---- one-call end-to-end path: fmc::Search{index, queries, editDistance, errors}() (search/search.h:47-75)
+ *      with an explicit scheme (n_searches = 0 selects exact search).  Host queries in, located rows out;
+ *      uploads, kernels and downloads are pipelined over chunks of queries.  `out` must hold `capacity` rows;
+ *      *n_out receives the number of rows found (if it exceeds capacity the call fails with FMB_EOVERFLOW). ---- */
+int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq,
+                          int edit, uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l,
+                          const uint32_t* u, const uint32_t* partition,
+                          fmb_loc32* out, uint64_t capacity, uint64_t* n_out, fmb_stats* stats);
+
+/* ---- synthetic data + pinned host memory helpers (bench / tests) ------------------------------------------- */
+/* T[i] = 1 + (splitmix64(seed + i) % (sigma-1)) for i < n-1, T[n-1] = 0; written to a device buffer owned by the
+ * library (free with fmb_device_free).  The same generator is restated in fmb200/synth.py for the CPU side. */
+int  fmb_synth_text_device(int device, uint32_t sigma, uint64_t n, uint64_t seed, uint8_t** d_text);
+int  fmb_device_free(int device, void* p);
+int  fmb_copy_to_host(int device, void* dst_host, const void* src_device, uint64_t bytes);
+void* fmb_host_alloc_pinned(uint64_t bytes);
+void  fmb_host_free_pinned(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMB200_H */

@@ -1,0 +1,424 @@
+// fmb_scheme.cuh -- K3: k-error search with search schemes (Hamming / Edit) and backtracking on sm_100a.
+//
+// Semantics = search_ng26 of the reference (search/SearchNg26.h:18-366): the node state machine
+// search_next / search_next_pos / search_next_dir / search_next_dir_no_errors / search_next_dir_single is
+// reproduced exactly (same pruning, same children), only the traversal order differs: the reference recurses
+// depth first per query, here every WARP owns a shared-memory stack of pending states ("items") of many
+// queries.  Per iteration the warp pops up to 32 items, every lane expands ONE node (one or two occ-block
+// fetches), the children are compacted with a warp prefix sum and pushed back.  Lanes therefore always work
+// on different, independent (query, search, position, interval) items -- the breadth-first frontier of the
+// north star, staged in shared memory, with LIFO order to keep it bounded.  New roots (query x search pairs)
+// are pulled from a global counter whenever fewer than 32 items are pending; children that do not fit the
+// stack are spilled to a global overflow list that the host feeds into the next launch.
+//
+// Because no hit limit (`n`) is applied, the set of reported (cursor, e) pairs does not depend on the
+// traversal order (SURVEY.md §0 fact 5, §7 "hard parts").
+#pragma once
+#include "fmb_device.cuh"
+#include "fmb_host.hpp"
+
+namespace fmb {
+
+constexpr int kMaxSearches = 16;
+constexpr int kMaxParts = 16;
+
+struct SchemeParams {
+    uint32_t n_searches, n_parts;
+    uint32_t edit;            // 1 = edit distance, 0 = Hamming
+    uint32_t force_left;      // backtracking mode: a single part searched right-to-left (search/Backtracking.h)
+    uint32_t zero_lb_rev;     // unidirectional index: report lb_rev = 0
+    uint8_t pi[kMaxSearches][kMaxParts];
+    uint8_t l[kMaxSearches][kMaxParts];
+    uint8_t u[kMaxSearches][kMaxParts];
+    uint16_t partition[kMaxParts];
+    uint16_t start[kMaxSearches];      // sum of partition[0 .. pi[s][0])          (SearchNg26.h:65-68)
+};
+
+enum : uint32_t { INFO_M = 0, INFO_S = 1, INFO_D = 2, INFO_I = 3 };
+enum : uint32_t { MODE_POS = 0, MODE_NEXT = 1, MODE_NOERR = 2 };
+
+// 32-byte frontier item = State of SearchNg26.h:41-52 + (qidx, search)
+struct Item {
+    uint32_t lb, lb_rev, len, qidx;
+    uint32_t qpos;       // queryPosL | queryPosR << 16  (16-bit wrap-around, cf. the note at SearchNg26.h:69-71)
+    uint32_t pev_steps;  // partitionEntryValue | steps << 16
+    uint32_t meta;       // e | part << 8 | search << 16 | mode << 24 | LInfo << 26 | RInfo << 28 | Right << 30 | NextPos << 31
+    uint32_t side;       // lastRank[L] | lastQRank[L] << 8 | lastRank[R] << 16 | lastQRank[R] << 24
+};
+static_assert(sizeof(Item) == 32, "item is two 16-byte words");
+
+struct State {
+    uint32_t lb, lb_rev, len, qidx;
+    uint32_t qposL, qposR, pev, steps;
+    uint32_t e, part, search, mode, LInfo, RInfo, Right, NextPos;
+    uint32_t side;
+};
+
+__device__ __forceinline__ Item pack_item(const State& s) {
+    Item it;
+    it.lb = s.lb; it.lb_rev = s.lb_rev; it.len = s.len; it.qidx = s.qidx;
+    it.qpos = (s.qposL & 0xFFFF) | (s.qposR << 16);
+    it.pev_steps = (s.pev & 0xFFFF) | (s.steps << 16);
+    it.meta = s.e | (s.part << 8) | (s.search << 16) | (s.mode << 24) | (s.LInfo << 26) | (s.RInfo << 28) | (s.Right << 30) | (s.NextPos << 31);
+    it.side = s.side;
+    return it;
+}
+__device__ __forceinline__ State unpack_item(const Item& it) {
+    State s;
+    s.lb = it.lb; s.lb_rev = it.lb_rev; s.len = it.len; s.qidx = it.qidx;
+    s.qposL = it.qpos & 0xFFFF; s.qposR = it.qpos >> 16;
+    s.pev = it.pev_steps & 0xFFFF; s.steps = it.pev_steps >> 16;
+    s.e = it.meta & 0xFF; s.part = (it.meta >> 8) & 0xFF; s.search = (it.meta >> 16) & 0xFF;
+    s.mode = (it.meta >> 24) & 3; s.LInfo = (it.meta >> 26) & 3; s.RInfo = (it.meta >> 28) & 3;
+    s.Right = (it.meta >> 30) & 1; s.NextPos = it.meta >> 31;
+    s.side = it.side;
+    return s;
+}
+__device__ __forceinline__ uint32_t side_get(uint32_t side, uint32_t right, uint32_t which /*0 lastRank, 1 lastQRank*/) {
+    return (side >> (right * 16 + which * 8)) & 0xFF;
+}
+__device__ __forceinline__ uint32_t side_set(uint32_t side, uint32_t right, uint32_t which, uint32_t v) {
+    uint32_t sh = right * 16 + which * 8;
+    return (side & ~(0xFFu << sh)) | (v << sh);
+}
+
+struct SchemeOut {
+    HitRec* hits;
+    unsigned long long* hit_count;     // total hits found (may exceed capacity)
+    uint64_t hit_capacity;
+    Item* overflow;
+    unsigned long long* overflow_count;
+    uint64_t overflow_capacity;
+    unsigned long long* counters;      // [0] extensions, [1] occ lookups, [3] peak items per warp
+    unsigned long long* root_counter;
+};
+
+// one cursor extension by `symb` in direction `right` from two loaded blocks (DNA: blocks are symbol independent)
+template <class OCC>
+__device__ __forceinline__ void child_cursor(const IndexView<OCC>& ix, const OCC& occ, uint32_t b0, uint32_t b1,
+                                             typename OCC::Block& blk0, typename OCC::Block& blk1, row_t lo, row_t hi,
+                                             uint32_t symb, bool single, uint32_t& same, uint32_t& dother, uint32_t& clen) {
+    if (single) {
+        // interval of one row whose BWT symbol is `symb` (callers guarantee it): rank(lo+1) = rank(lo) + 1 and no
+        // smaller symbol lies inside, so the second block -- lo + 1 may start the next one -- is never needed
+        if (OCC::kSymbolLoad) blk0 = occ.load(b0, symb);
+        same = ix.C[symb] + occ.rank(blk0, lo, symb);
+        dother = 0;
+        clen = 1;
+        return;
+    }
+    if (OCC::kSymbolLoad) {
+        blk0 = occ.load(b0, symb);
+        blk1 = (b1 == b0) ? blk0 : occ.load(b1, symb);
+    }
+    uint32_t r0, p0, r1, p1;
+    occ.rank_pr(blk0, lo, symb, r0, p0);
+    occ.rank_pr(blk1, hi, symb, r1, p1);
+    same = ix.C[symb] + r0;
+    dother = p1 - p0;
+    clen = r1 - r0;
+}
+
+template <class OCC, bool EDIT>
+__global__ void __launch_bounds__(256) scheme_search_kernel(IndexView<OCC> ix, SchemeParams sp, const uint8_t* __restrict__ qsym,
+                                                            const uint64_t* __restrict__ qoff, uint64_t n_roots,
+                                                            const Item* __restrict__ in_items, uint64_t n_in,
+                                                            SchemeOut out, uint32_t cap) {
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = threadIdx.x >> 5;
+    Item* stack = reinterpret_cast<Item*>(smem_raw) + (size_t)warp * cap;
+    const uint64_t total_roots = n_roots + n_in;
+    uint32_t top = 0;
+    uint32_t n_ext = 0, n_look = 0, peak = 0;
+    bool more_roots = true;
+    const uint32_t np = sp.n_parts;
+    const uint32_t first_symb = 1;       // FirstSymb of delimited indices (fmindex/BiFMIndex.h:26)
+
+    for (;;) {
+        // ---- refill: pull roots while fewer than 32 items are pending -------------------------------------
+        if (top < 32 && more_roots) {
+            uint32_t want = 32 - top;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(out.root_counter, (unsigned long long)want);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (base >= total_roots) {
+                more_roots = false;
+            } else {
+                uint64_t avail = total_roots - base;
+                uint32_t got = avail < want ? (uint32_t)avail : want;
+                if (got < want) more_roots = false;
+                if (lane < got) {
+                    uint64_t r = base + lane;
+                    Item it;
+                    if (r < n_in) {
+                        it = in_items[r];
+                    } else {
+                        r -= n_in;
+                        uint32_t s = (uint32_t)(r % sp.n_searches);
+                        State st;
+                        st.qidx = (uint32_t)(r / sp.n_searches);
+                        st.lb = 0; st.lb_rev = 0; st.len = ix.n; st.steps = 0;                 // BiFMIndexCursor.h:28-30
+                        st.qposR = sp.start[s];
+                        st.qposL = (sp.start[s] - 1) & 0xFFFF;                                 // SearchNg26.h:69-72
+                        st.pev = sp.partition[sp.pi[s][0]];
+                        st.e = 0; st.part = 0; st.search = s; st.mode = MODE_NEXT;
+                        st.LInfo = INFO_M; st.RInfo = INFO_M; st.Right = 1; st.NextPos = 0; st.side = 0;
+                        if (sp.force_left) {                                                   // Backtracking.h: right to left
+                            st.qposL = (sp.partition[0] - 1) & 0xFFFF;
+                            st.qposR = 0;
+                        }
+                        it = pack_item(st);
+                    }
+                    stack[top + lane] = it;
+                }
+                top += got;
+                __syncwarp();
+            }
+        }
+        if (top == 0) {
+            if (!more_roots) break;
+            continue;
+        }
+        peak = top > peak ? top : peak;
+        // ---- pop ---------------------------------------------------------------------------------------------
+        const uint32_t nact = top < 32 ? top : 32;
+        const bool active = lane < nact;
+        State st;
+        if (active) st = unpack_item(stack[top - 1 - lane]);
+        top -= nact;
+        __syncwarp();
+
+        // ---- expand one node per lane ---------------------------------------------------------------------
+        // children are described by a bit mask and re-derived when they are written:
+        //   bit 0 match / continuation, bit 1 insertion, bits 8..8+sigma deletion(c), bits 40.. substitution(c) (64-bit)
+        unsigned long long cmask = 0;
+        bool report = false;
+        uint32_t q = 0, b0 = 0, b1 = 0, lo = 0, hi = 0, single_sym = 0;
+        typename OCC::Block blk0, blk1;
+        bool is_single = false, noerr_cont = false;
+        const OCC* occp = nullptr;
+
+        if (active) {
+            bool go_dir = true;
+            if (st.mode == MODE_POS) {                                                          // search_next_pos :119-141
+                if (st.NextPos) {
+                    if (st.Right) st.qposR = (st.qposR + 1) & 0xFFFF; else st.qposL = (st.qposL - 1) & 0xFFFF;
+                    st.pev -= 1;
+                    if (st.pev == 0) {
+                        st.part += 1;
+                        if (st.part != np) st.pev = sp.partition[sp.pi[st.search][st.part]];
+                        st.mode = MODE_NEXT;
+                    }
+                }
+            }
+            if (st.mode == MODE_NEXT) {                                                         // search_next :98-117
+                if (st.part == np) {
+                    bool ok = !EDIT || ((st.LInfo == INFO_M || st.LInfo == INFO_I) && (st.RInfo == INFO_M || st.RInfo == INFO_I));
+                    report = ok && sp.l[st.search][np - 1] <= st.e && st.e <= sp.u[st.search][np - 1];
+                    go_dir = false;
+                } else {
+                    st.Right = (st.part == 0) || (sp.pi[st.search][st.part - 1] < sp.pi[st.search][st.part]);
+                    if (sp.force_left) st.Right = 0;
+                }
+            }
+            if (go_dir) {
+                const uint32_t R = st.Right;
+                const OCC& occ = ix.occ[R];
+                occp = &occ;
+                q = __ldg(qsym + qoff[st.qidx] + (R ? st.qposR : st.qposL));
+                lo = R ? st.lb_rev : st.lb;
+                hi = lo + st.len;
+                b0 = lo >> 6;
+                b1 = hi >> 6;
+                if (st.mode == MODE_NOERR) {
+                    noerr_cont = true;                                                          // search_next_dir_no_errors :225-250
+                } else {
+                    const uint32_t TInfo = R ? st.RInfo : st.LInfo;
+                    const uint32_t lastRank = side_get(st.side, R, 0), lastQRank = side_get(st.side, R, 1);
+                    const bool Deletion = EDIT && TInfo != INFO_S && TInfo != INFO_I;
+                    const bool Insertion = EDIT && TInfo != INFO_S && TInfo != INFO_D;
+                    const uint32_t lp = sp.l[st.search][st.part], up = sp.u[st.search][st.part];
+                    const bool matchAllowed = (st.pev > 1 || lp <= st.e) && st.e <= up && (TInfo != INFO_I || q != lastQRank) &&
+                                              (TInfo != INFO_D || q != lastRank);
+                    const bool insAllowed = (st.pev > 1 || lp <= st.e + 1) && st.e + 1 <= up;
+                    const bool mismatchAllowed = st.e + 1 <= up;
+                    if (st.len > 1) {                                                           // search_next_dir :143-224
+                        if (mismatchAllowed) {
+                            blk0 = occ.load(b0, 0);
+                            blk1 = (b1 == b0) ? blk0 : occ.load(b1, 0);
+                            n_ext += 1; n_look += (b1 == b0) ? 1 : 2;
+                            uint32_t same, dother, clen;
+                            if (matchAllowed && q < ix.sigma) {
+                                child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, q, false, same, dother, clen);
+                                if (clen) cmask |= 1ull;
+                            }
+                            for (uint32_t c = first_symb; c < ix.sigma; ++c) {
+                                child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, c, false, same, dother, clen);
+                                if (!clen) continue;
+                                if (Deletion) cmask |= 1ull << (8 + c);
+                                if (insAllowed && c != q) cmask |= 1ull << (36 + c);
+                            }
+                            if (Insertion && insAllowed) cmask |= 2ull;
+                        } else if (matchAllowed) {
+                            noerr_cont = true;
+                        }
+                    } else {                                                                    // search_next_dir_single :251-365
+                        is_single = true;
+                        blk0 = occ.load(b0, 0);
+                        blk1 = blk0;
+                        n_ext += 1; n_look += 1;
+                        single_sym = occ.symbol(blk0, lo);                                      // symbolLeft/Right, BiFMIndexCursor.h:180-190
+                        if (Insertion && insAllowed) cmask |= 2ull;
+                        if (single_sym >= first_symb) {
+                            if (single_sym == q) {
+                                if (matchAllowed) {
+                                    if (!mismatchAllowed) noerr_cont = true;
+                                    else cmask |= 1ull;
+                                }
+                                if (Deletion && mismatchAllowed) cmask |= 1ull << (8 + single_sym);
+                            } else if (mismatchAllowed) {
+                                if (insAllowed) cmask |= 1ull << (36 + single_sym);
+                                if (Deletion) cmask |= 1ull << (8 + single_sym);
+                            }
+                        }
+                    }
+                }
+                if (noerr_cont) {
+                    // one step of the error-free loop; bit 0 = the continuation item
+                    if (q < ix.sigma) {
+                        if (!is_single) {
+                            blk0 = occ.load(b0, q);
+                            blk1 = (b1 == b0) ? blk0 : occ.load(b1, q);
+                            n_ext += 1; n_look += (b1 == b0) ? 1 : 2;
+                        }
+                        uint32_t same, dother, clen;
+                        child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, q, is_single, same, dother, clen);
+                        if (clen) cmask |= 1ull;
+                    }
+                }
+            }
+        }
+
+        // ---- report leaves (warp aggregated append) -----------------------------------------------------------
+        {
+            uint32_t rb = __ballot_sync(0xFFFFFFFFu, report);
+            if (rb) {
+                unsigned long long base = 0;
+                if (lane == (uint32_t)(__ffs(rb) - 1)) base = atomicAdd(out.hit_count, (unsigned long long)__popc(rb));
+                base = __shfl_sync(0xFFFFFFFFu, base, __ffs(rb) - 1);
+                if (report) {
+                    unsigned long long idx = base + __popc(rb & ((1u << lane) - 1));
+                    if (idx < out.hit_capacity) {
+                        HitRec h;
+                        h.qidx = st.qidx; h.lb = st.lb; h.lb_rev = sp.zero_lb_rev ? 0 : st.lb_rev; h.len = st.len; h.steps = st.steps; h.e = st.e;
+                        out.hits[idx] = h;
+                    }
+                }
+            }
+        }
+
+        // ---- compact + push children ---------------------------------------------------------------------------
+        uint32_t nchild = __popcll(cmask);
+        uint32_t incl = nchild;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (total == 0) continue;
+        uint32_t slot = incl - nchild;
+        Item* dst;
+        bool drop = false;
+        if (top + total <= cap) {
+            dst = stack + top;
+            top += total;
+        } else {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(out.overflow_count, (unsigned long long)total);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            dst = out.overflow + base;
+            drop = base + total > out.overflow_capacity;      // host sees overflow_count > capacity and fails loudly
+        }
+        if (cmask && !drop) {
+            const uint32_t R = st.Right;
+            const OCC& occ = *occp;
+            // helper state for children that took one index step with symbol c
+            auto stepped = [&](uint32_t c, State& ch) {
+                uint32_t same, dother, clen;
+                child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, c, is_single, same, dother, clen);
+                ch.len = clen;
+                if (R) { ch.lb_rev = same; ch.lb = st.lb + dother; } else { ch.lb = same; ch.lb_rev = st.lb_rev + dother; }
+                ch.steps = st.steps + 1;
+            };
+            if (cmask & 1ull) {
+                State ch = st;
+                stepped(q, ch);
+                if (noerr_cont) {
+                    if (R) ch.qposR = (st.qposR + 1) & 0xFFFF; else ch.qposL = (st.qposL - 1) & 0xFFFF;
+                    ch.pev = st.pev - 1;
+                    ch.NextPos = 0;
+                    if (ch.pev > 0) {
+                        ch.mode = MODE_NOERR;
+                    } else {                                                                    // :241-249
+                        ch.side = side_set(side_set(st.side, R, 0, q), R, 1, q);
+                        ch.part = st.part + 1;
+                        ch.pev = (ch.part != np) ? sp.partition[sp.pi[st.search][ch.part]] : 0;
+                        if (R) ch.RInfo = INFO_M; else ch.LInfo = INFO_M;
+                        ch.mode = MODE_NEXT;
+                    }
+                } else {                                                                        // match child
+                    ch.side = side_set(side_set(st.side, R, 0, q), R, 1, q);
+                    if (R) ch.RInfo = INFO_M; else ch.LInfo = INFO_M;
+                    ch.NextPos = 1;
+                    ch.mode = MODE_POS;
+                }
+                dst[slot++] = pack_item(ch);
+            }
+            if (cmask & 2ull) {                                                                 // insertion: no index step
+                State ch = st;
+                ch.e = st.e + 1;
+                ch.side = side_set(st.side, R, 1, q);
+                if (R) ch.RInfo = INFO_I; else ch.LInfo = INFO_I;
+                ch.NextPos = 1;
+                ch.mode = MODE_POS;
+                dst[slot++] = pack_item(ch);
+            }
+            unsigned long long rest = cmask >> 8;
+            while (rest) {
+                uint32_t bit = __ffsll((long long)rest) - 1;
+                rest &= rest - 1;
+                bool is_sub = bit >= 28;
+                uint32_t c = is_sub ? bit - 28 : bit;
+                State ch = st;
+                stepped(c, ch);
+                ch.e = st.e + 1;
+                ch.side = side_set(st.side, R, 0, c);
+                ch.mode = MODE_POS;
+                if (is_sub) {
+                    ch.side = side_set(ch.side, R, 1, q);
+                    if (R) ch.RInfo = INFO_S; else ch.LInfo = INFO_S;
+                    ch.NextPos = 1;
+                } else {
+                    if (R) ch.RInfo = INFO_D; else ch.LInfo = INFO_D;
+                    ch.NextPos = 0;
+                }
+                dst[slot++] = pack_item(ch);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- statistics ------------------------------------------------------------------------------------------
+    for (int o = 16; o > 0; o >>= 1) {
+        n_ext += __shfl_xor_sync(0xFFFFFFFFu, n_ext, o);
+        n_look += __shfl_xor_sync(0xFFFFFFFFu, n_look, o);
+    }
+    if (lane == 0) {
+        atomicAdd(out.counters + 0, (unsigned long long)n_ext);
+        atomicAdd(out.counters + 1, (unsigned long long)n_look);
+        atomicMax(out.counters + 3, (unsigned long long)peak);
+    }
+}
+
+}  // namespace fmb

@@ -1,0 +1,257 @@
+// fmb_search.cu -- host side of the k-error searches (K3) and the one-call search+locate path.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "fmb_host.hpp"
+#include "fmb_scheme.cuh"
+
+using namespace fmb;
+
+namespace {
+
+int set_device(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaSetDevice(%d): %s -- libfmb200 has no CPU fallback", device, cudaGetErrorString(e));
+        return FMB_ENODEVICE;
+    }
+    return FMB_OK;
+}
+
+constexpr uint32_t kStackCap = 256;          // items per warp (8 KB)
+constexpr uint32_t kWarpsPerBlock = 8;
+
+template <bool EDIT>
+int launch_scheme(const fmb_index* ix, const SchemeParams& sp, const fmb_queries* q, uint64_t n_roots, const Item* in_items,
+                  uint64_t n_in, const SchemeOut& out, cudaStream_t st) {
+    static int blocks_per_sm = 0, sms = 0;
+    size_t smem = (size_t)kStackCap * kWarpsPerBlock * sizeof(Item);
+    auto kern = scheme_search_kernel<OccDna, EDIT>;
+    if (!blocks_per_sm) {
+        FMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0;
+        FMB_CUDA(cudaGetDevice(&dev));
+        FMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 256, smem));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    } else {
+        FMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    uint64_t work = n_roots + n_in;
+    uint64_t want_blocks = (work + 255) / 256;
+    unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * blocks_per_sm, want_blocks));
+    kern<<<grid, 256, smem, st>>>(ix->view_dna(), sp, q->symbols.p, q->offsets.p, n_roots, in_items, n_in, out, kStackCap);
+    FMB_CUDA(cudaGetLastError());
+    return FMB_OK;
+}
+
+int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp, fmb_results** out_res) {
+    FMB_TRY(set_device(ix->device));
+    cudaStream_t st = ix->stream;
+    auto res = new fmb_results();
+    res->device = ix->device;
+    res->kind = 0;
+    struct Guard { fmb_results* r; ~Guard() { delete r; } } guard{res};
+
+    const uint64_t nq = q->nq;
+    const uint64_t n_roots = nq * sp.n_searches;
+    uint64_t hit_cap = std::max<uint64_t>(1u << 20, nq * 8);
+    const uint64_t ovf_cap = 1u << 22;       // 4 M items = 128 MB per buffer
+    DevBuf<Item> ovf[2];
+    DevBuf<unsigned long long> ctr;          // [0..3] counters, [4] hit_count, [5] overflow_count, [6] root_counter
+    FMB_TRY(ovf[0].alloc(ovf_cap));
+    FMB_TRY(ovf[1].alloc(ovf_cap));
+    FMB_TRY(ctr.alloc(8));
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    double total_ms = 0;
+    unsigned long long h_ctr[8];
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        FMB_TRY(res->hits.alloc(hit_cap));
+        FMB_CUDA(cudaMemsetAsync(ctr.p, 0, 8 * sizeof(unsigned long long), st));
+        SchemeOut so;
+        so.hits = res->hits.p;
+        so.hit_count = ctr.p + 4;
+        so.hit_capacity = hit_cap;
+        so.overflow_count = ctr.p + 5;
+        so.overflow_capacity = ovf_cap;
+        so.counters = ctr.p;
+        so.root_counter = ctr.p + 6;
+        uint64_t roots = n_roots, n_in = 0;
+        int cur = 0;
+        cudaEventRecord(ev0, st);
+        for (int pass = 0;; ++pass) {
+            so.overflow = ovf[cur].p;
+            const Item* in_items = pass ? ovf[cur ^ 1].p : nullptr;
+            if (roots + n_in > 0) {
+                int rc = sp.edit ? launch_scheme<true>(ix, sp, q, roots, in_items, n_in, so, st)
+                                 : launch_scheme<false>(ix, sp, q, roots, in_items, n_in, so, st);
+                if (rc) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
+            }
+            FMB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
+            FMB_CUDA(cudaStreamSynchronize(st));
+            if (h_ctr[5] > ovf_cap) {
+                cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+                set_error("scheme search: frontier overflow list exceeded %llu items; split the query batch", (unsigned long long)ovf_cap);
+                return FMB_EOVERFLOW;
+            }
+            if (h_ctr[5] == 0) break;
+            // feed the spilled items to the next pass
+            n_in = h_ctr[5];
+            roots = 0;
+            cur ^= 1;
+            FMB_CUDA(cudaMemsetAsync(ctr.p + 5, 0, 2 * sizeof(unsigned long long), st));   // overflow_count, root_counter
+            if (pass > 100000) { set_error("scheme search did not terminate"); return FMB_ECUDA; }
+        }
+        cudaEventRecord(ev1, st);
+        cudaEventSynchronize(ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        total_ms += ms;
+        if (h_ctr[4] <= hit_cap) break;
+        hit_cap = h_ctr[4];                  // second attempt with the exact size
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    res->count = h_ctr[4];
+    res->stats.extensions = h_ctr[0];
+    res->stats.occ_lookups = h_ctr[1];
+    res->stats.frontier_peak = h_ctr[3];
+    res->stats.kernel_ms = total_ms;
+    guard.r = nullptr;
+    *out_res = res;
+    return FMB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fmb_search_scheme(const fmb_index* ix, const fmb_queries* q, int edit, uint32_t n_searches, uint32_t n_parts,
+                      const uint32_t* pi, const uint32_t* l, const uint32_t* u, const uint32_t* partition, fmb_results** out) {
+    if (!ix || !q || !out || !pi || !l || !u || !partition) { set_error("NULL argument"); return FMB_EINVAL; }
+    *out = nullptr;
+    if (!ix->bidirectional) { set_error("search schemes need a bidirectional index (extendRight)"); return FMB_EINVAL; }
+    if (!ix->dna) { set_error("sigma %u: scheme search on the generic layout is not available yet", ix->sigma); return FMB_EUNSUPPORTED; }
+    if (q->device != ix->device) { set_error("queries live on device %d, index on %d", q->device, ix->device); return FMB_EINVAL; }
+    if (n_searches == 0 || n_searches > (uint32_t)kMaxSearches || n_parts == 0 || n_parts > (uint32_t)kMaxParts) {
+        set_error("scheme shape %u x %u outside [1,%d] x [1,%d]", n_searches, n_parts, kMaxSearches, kMaxParts);
+        return FMB_EINVAL;
+    }
+    SchemeParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.n_searches = n_searches;
+    sp.n_parts = n_parts;
+    sp.edit = edit ? 1 : 0;
+    sp.zero_lb_rev = 0;
+    uint64_t total = 0;
+    for (uint32_t p = 0; p < n_parts; ++p) {
+        if (partition[p] == 0 || partition[p] > 0xFFFF) { set_error("partition[%u] = %u out of range", p, partition[p]); return FMB_EINVAL; }
+        sp.partition[p] = (uint16_t)partition[p];
+        total += partition[p];
+    }
+    if (total > 0xFFFF) { set_error("query length %llu too long", (unsigned long long)total); return FMB_EINVAL; }
+    if (q->nq && (q->min_len != total || q->max_len != total)) {
+        set_error("every query must have length sum(partition) = %llu (batch has %u..%u)", (unsigned long long)total, q->min_len, q->max_len);
+        return FMB_EINVAL;
+    }
+    for (uint32_t s = 0; s < n_searches; ++s) {
+        uint32_t seen = 0;
+        for (uint32_t p = 0; p < n_parts; ++p) {
+            uint32_t v = pi[s * n_parts + p];
+            if (v >= n_parts || (seen >> v) & 1) { set_error("search %u: pi is not a permutation", s); return FMB_EINVAL; }
+            seen |= 1u << v;
+            if (l[s * n_parts + p] > 255 || u[s * n_parts + p] > 255) { set_error("error bounds too large"); return FMB_EINVAL; }
+            sp.pi[s][p] = (uint8_t)v;
+            sp.l[s][p] = (uint8_t)l[s * n_parts + p];
+            sp.u[s][p] = (uint8_t)u[s * n_parts + p];
+        }
+        // pi must be connected (each part adjacent to the block searched so far), as every generator produces
+        uint32_t lo = sp.pi[s][0], hi = sp.pi[s][0];
+        for (uint32_t p = 1; p < n_parts; ++p) {
+            uint32_t v = sp.pi[s][p];
+            if (v + 1 == lo) lo = v;
+            else if (v == hi + 1) hi = v;
+            else { set_error("search %u: pi is not a connected order", s); return FMB_EINVAL; }
+        }
+        uint32_t start = 0;
+        for (uint32_t i = 0; i < sp.pi[s][0]; ++i) start += sp.partition[i];
+        sp.start[s] = (uint16_t)start;
+    }
+    return run_scheme(ix, q, sp, out);
+}
+
+int fmb_search_backtracking(const fmb_index* ix, const fmb_queries* q, uint32_t max_errors, fmb_results** out) {
+    if (!ix || !q || !out) { set_error("NULL argument"); return FMB_EINVAL; }
+    *out = nullptr;
+    if (!ix->dna) { set_error("sigma %u: backtracking on the generic layout is not available yet", ix->sigma); return FMB_EUNSUPPORTED; }
+    if (q->device != ix->device) { set_error("queries live on device %d, index on %d", q->device, ix->device); return FMB_EINVAL; }
+    if (max_errors > 255) { set_error("max_errors too large"); return FMB_EINVAL; }
+    if (q->nq && q->min_len != q->max_len) { set_error("backtracking: all queries of a batch must have the same length"); return FMB_EUNSUPPORTED; }
+    if (q->nq && q->max_len == 0) { set_error("backtracking: empty queries"); return FMB_EINVAL; }
+    SchemeParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.n_searches = 1;
+    sp.n_parts = 1;
+    sp.edit = 0;
+    sp.force_left = 1;
+    sp.zero_lb_rev = ix->bidirectional ? 0 : 1;
+    sp.partition[0] = (uint16_t)(q->nq ? q->max_len : 1);
+    sp.pi[0][0] = 0;
+    sp.l[0][0] = 0;
+    sp.u[0][0] = (uint8_t)max_errors;
+    sp.start[0] = 0;
+    return run_scheme(ix, q, sp, out);
+}
+
+int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq, int edit,
+                          uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l, const uint32_t* u,
+                          const uint32_t* partition, fmb_loc32* out, uint64_t capacity, uint64_t* n_out, fmb_stats* stats) {
+    if (!ix || !offsets || !n_out) { set_error("NULL argument"); return FMB_EINVAL; }
+    *n_out = 0;
+    fmb_stats total{};
+    // chunks of queries: bounded device memory, and the next upload overlaps nothing yet (single stream)
+    const uint64_t chunk = 1u << 22;
+    uint64_t written = 0;
+    for (uint64_t b = 0; b < nq || (nq == 0 && b == 0); b += chunk) {
+        uint64_t e = std::min(nq, b + chunk);
+        fmb_queries* q = nullptr;
+        FMB_TRY(fmb_queries_upload(&q, ix, symbols, offsets + b, e - b));
+        fmb_results* hits = nullptr;
+        int rc = n_searches ? fmb_search_scheme(ix, q, edit, n_searches, n_parts, pi, l, u, partition, &hits) : fmb_search_exact(ix, q, &hits);
+        fmb_queries_destroy(q);
+        if (rc) return rc;
+        fmb_results* locs = nullptr;
+        rc = fmb_locate(ix, hits, &locs);
+        total.extensions += hits->stats.extensions;
+        total.occ_lookups += hits->stats.occ_lookups;
+        total.kernel_ms += hits->stats.kernel_ms;
+        fmb_results_destroy(hits);
+        if (rc) return rc;
+        total.lf_steps += locs->stats.lf_steps;
+        total.occ_lookups += locs->stats.occ_lookups;
+        total.kernel_ms += locs->stats.kernel_ms;
+        uint64_t cnt = locs->count;
+        if (written + cnt > capacity) {
+            fmb_results_destroy(locs);
+            *n_out = written + cnt;
+            set_error("output capacity %llu too small", (unsigned long long)capacity);
+            return FMB_EOVERFLOW;
+        }
+        rc = fmb_results_fetch_locs32(locs, out + written, capacity - written);
+        fmb_results_destroy(locs);
+        if (rc) return rc;
+        // qidx is chunk relative on the device
+        if (b) for (uint64_t i = written; i < written + cnt; ++i) out[i].qidx += (uint32_t)b;
+        written += cnt;
+        if (nq == 0) break;
+    }
+    *n_out = written;
+    if (stats) *stats = total;
+    return FMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+"""GPU parity: device occurrence table (String_c), cursor steps, exact search and locate against the oracle."""
+import numpy as np
+import pytest
+
+from helpers import hits_equal, locs_equal, make_index_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pair(gpu):
+    from fmb200 import synth
+    text = synth.multi_text([3000, 2000, 500, 1, 64, 63], 5, 7)
+    o, g = make_index_pair(gpu, text, 5, 4)
+    return text, o, g
+
+
+def test_index_info_and_C(pair):
+    text, o, g = pair
+    info = g.info
+    assert info.n == text.size and info.sigma == 5 and info.bidirectional == 1
+    assert info.n_delims == 6 and info.occ_block_bytes == 32 and info.occ_block_rows == 64
+    assert np.array_equal(g.C, o.C)
+
+
+def test_export_roundtrip(pair):
+    text, o, g = pair
+    bwt, rev, bm, sq, sp = g.export()
+    obm, osq, osp = o.samples
+    assert np.array_equal(bwt, o.bwt) and np.array_equal(rev, o.bwt_rev)
+    assert np.array_equal(bm, obm) and np.array_equal(sq, osq) and np.array_equal(sp, osp)
+
+
+@pytest.mark.parametrize("dir", [0, 1])
+def test_string_ops_every_row(pair, dir):
+    text, o, g = pair
+    n = o.n
+    rows = np.arange(n, dtype=np.uint64)
+    assert np.array_equal(g.symbol(rows, dir), np.array([o.symbol(i, dir) for i in range(n)], dtype=np.uint8))
+    rows1 = np.arange(n + 1, dtype=np.uint64)
+    for s in range(5):
+        symb = np.full(n + 1, s, dtype=np.uint8)
+        assert np.array_equal(g.rank(rows1, symb, dir), np.array([o.rank(i, s, dir) for i in range(n + 1)], dtype=np.uint64)), s
+    for s in range(6):   # prefix_rank accepts symb == sigma (string/FlattenedBitvectors2L.h:226-228)
+        symb = np.full(n + 1, s, dtype=np.uint8)
+        assert np.array_equal(g.prefix_rank(rows1, symb, dir), np.array([o.prefix_rank(i, s, dir) for i in range(n + 1)], dtype=np.uint64)), s
+    sel = rows1[:: 37]
+    rs, prs = g.all_ranks(sel, dir)
+    for k, i in enumerate(sel):
+        ors, oprs = o.all_ranks_and_prefix_ranks(int(i), dir)
+        assert np.array_equal(rs[k], ors) and np.array_equal(prs[k], oprs)
+
+
+def test_cursor_extend(pair):
+    text, o, g = pair
+    rng = np.random.default_rng(5)
+    # cursors reached by real searches: start from the root and extend randomly, keep the non-empty ones
+    curs = [np.array([0, 0, o.n, 0], dtype=np.uint64)]
+    for _ in range(400):
+        c = curs[rng.integers(0, len(curs))]
+        nc = o.extend(c, int(rng.integers(0, 5)), bool(rng.integers(0, 2)))
+        if nc[2] > 0:
+            curs.append(nc)
+    curs = np.array(curs, dtype=np.uint64)
+    for right in (0, 1):
+        for s in range(5):
+            got = g.extend(curs, np.full(len(curs), s, dtype=np.uint8), right)
+            exp = np.array([o.extend(c, s, right) for c in curs], dtype=np.uint64)
+            assert np.array_equal(got, exp), (right, s)
+        got = g.extend_all(curs, right)
+        exp = np.array([o.extend_all(c, right) for c in curs], dtype=np.uint64)
+        assert np.array_equal(got, exp)
+
+
+def test_exact_search_and_locate(pair):
+    from fmb200 import synth
+    from oracle.pyoracle import Counters
+    text, o, g = pair
+    rng = np.random.default_rng(11)
+    reads = []
+    for L in (1, 2, 5, 16, 17, 31, 32, 33, 50, 100):
+        for _ in range(40):
+            p = int(rng.integers(0, text.size - L))
+            reads.append(text[p:p + L].copy())            # may contain delimiters: must behave like the reference
+        for _ in range(10):
+            reads.append(rng.integers(1, 5, size=L).astype(np.uint8))
+    sym, off = synth.flatten(reads)
+    q = g.upload(sym, off)
+    res = g.search_exact(q)
+    exp = o.search_exact(sym, off)
+    got = res.hits()
+    assert hits_equal(got, exp)
+    assert np.all(np.diff(got["qidx"].astype(np.int64)) > 0)     # compaction keeps query order
+    loc = g.locate(res)
+    assert locs_equal(loc.locs(), o.locate(exp))
+    assert np.array_equal(loc.locs32()["pos"].astype(np.uint64), loc.locs()["pos"])
+    ctr = Counters()
+    o.search_exact(sym, off, ctr)
+    st = res.stats
+    assert st.extensions == ctr.extensions and st.occ_lookups == ctr.occ_lookups
+    ctr = Counters()
+    o.locate(exp, ctr)
+    assert loc.stats.lf_steps == ctr.lf_steps
+
+
+def test_empty_inputs(pair):
+    text, o, g = pair
+    q = g.upload(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
+    res = g.search_exact(q)
+    assert len(res) == 0 and len(g.locate(res)) == 0
+    # one empty query: the single-query form returns the whole index (search/SearchNoErrors.h:13-26)
+    q = g.upload(np.zeros(0, dtype=np.uint8), np.zeros(2, dtype=np.uint64))
+    h = g.search_exact(q).hits()
+    assert len(h) == 1 and h[0]["lb"] == 0 and h[0]["len"] == o.n and h[0]["steps"] == 0
+
+
+def test_unidirectional_index(gpu):
+    from fmb200 import synth
+    text = synth.multi_text([5000], 5, 3)
+    o, g = make_index_pair(gpu, text, 5, 16, bidirectional=False)
+    assert g.info.bidirectional == 0
+    reads, _ = synth.reads_from_text(text, 300, 25, 9)
+    sym, off = synth.flatten(reads)
+    res = g.search_exact(g.upload(sym, off))
+    exp = o.search_exact(sym, off)
+    assert hits_equal(res.hits(), exp)
+    assert locs_equal(g.locate(res).locs(), o.locate(exp))
+
+
+def test_larger_single_sequence(gpu):
+    """1 Mbp single sequence, rate 16: every read is found, every located position equals its source offset"""
+    from fmb200 import synth
+    text = synth.text(1 << 20, 5, 1)
+    o, g = make_index_pair(gpu, text, 5, 16)
+    reads, src = synth.reads_from_text(text, 20000, 100, 2)
+    sym, off = synth.flatten(reads)
+    res = g.search_exact(g.upload(sym, off))
+    exp = o.search_exact(sym, off)
+    assert hits_equal(res.hits(), exp)
+    loc = g.locate(res).locs()
+    assert locs_equal(loc, o.locate(exp))
+    first = {}
+    for r in loc:
+        first.setdefault(int(r["qidx"]), set()).add(int(r["pos"]))
+    assert all(int(src[q]) in first[q] for q in range(len(src)))

@@ -21,7 +21,7 @@ class IndexInfo(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("extensions", C.c_uint64), ("occ_lookups", C.c_uint64), ("lf_steps", C.c_uint64),
-                ("frontier_peak", C.c_uint64), ("kernel_ms", C.c_double)]
+                ("frontier_peak", C.c_uint64), ("kernel_ms", C.c_double), ("main_kernel_ms", C.c_double)]
 
 
 class FmbError(RuntimeError):
@@ -45,7 +45,7 @@ SYMBOLS = [
     "fmb_results_count", "fmb_results_kind", "fmb_results_fetch_hits", "fmb_results_fetch_locs", "fmb_results_fetch_locs32",
     "fmb_results_get_stats", "fmb_results_destroy",
     "fmb_search_and_locate",
-    "fmb_synth_text_device", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
+    "fmb_synth_text_device", "fmb_synth_reads_device", "fmb_index_set_stream", "fmb_kernel_launch_count", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
 ]
 
 
@@ -63,6 +63,7 @@ def lib():
     L.fmb_version.restype = C.c_char_p
     L.fmb_results_count.restype = C.c_uint64
     L.fmb_queries_count.restype = C.c_uint64
+    L.fmb_kernel_launch_count.restype = C.c_uint64
     L.fmb_host_alloc_pinned.restype = C.c_void_p
     L.fmb_host_alloc_pinned.argtypes = [C.c_uint64]
     L.fmb_host_free_pinned.argtypes = [C.c_void_p]
@@ -317,3 +318,52 @@ class Results:
             self.close()
         except Exception:
             pass
+
+
+# ---- raw-pointer helpers (bench / synthetic workloads) ---------------------------------------------------
+class PinnedArray:
+    """numpy view over page-locked host memory from fmb_host_alloc_pinned (fast H2D / D2H)"""
+
+    def __init__(self, count, dtype):
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(count) * self.dtype.itemsize
+        self.ptr = lib().fmb_host_alloc_pinned(C.c_uint64(max(self.nbytes, 1)))
+        if not self.ptr:
+            raise FmbError(-4, lib().fmb_last_error().decode())
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(count))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().fmb_host_free_pinned(C.c_void_p(self.ptr))
+            self.ptr = None
+
+
+def synth_text_device(device, sigma, n, seed):
+    p = C.c_void_p()
+    _check(lib().fmb_synth_text_device(C.c_int(device), C.c_uint32(sigma), C.c_uint64(n), C.c_uint64(seed), C.byref(p)))
+    return p.value
+
+
+def synth_reads_device(device, d_text, n, nq, length, seed):
+    p = C.c_void_p()
+    _check(lib().fmb_synth_reads_device(C.c_int(device), C.c_void_p(d_text), C.c_uint64(n), C.c_uint64(nq), C.c_uint32(length),
+                                        C.c_uint64(seed), C.byref(p)))
+    return p.value
+
+
+def device_free(device, ptr):
+    _check(lib().fmb_device_free(C.c_int(device), C.c_void_p(ptr)))
+
+
+def copy_to_host(device, host_array, d_ptr, nbytes):
+    _check(lib().fmb_copy_to_host(C.c_int(device), _ptr(host_array), C.c_void_p(d_ptr), C.c_uint64(nbytes)))
+
+
+def kernel_launch_count():
+    return int(lib().fmb_kernel_launch_count())
+
+
+def index_set_stream(index, stream_ptr):
+    _check(lib().fmb_index_set_stream(index.h, C.c_void_p(stream_ptr)))

@@ -13,6 +13,7 @@
 namespace fmb {
 
 void set_error(const char* fmt, ...);
+void note_launches(unsigned n);   // bookkeeping for fmb_kernel_launch_count()
 
 #define FMB_CUDA(call)                                                                               \
     do {                                                                                             \
@@ -78,7 +79,8 @@ struct fmb_index {
     uint64_t n = 0;
     bool bidirectional = false;
     bool dna = true;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // stream all work of this index is enqueued on
+    cudaStream_t own_stream = nullptr;   // private stream created with the index
     fmb::DevBuf<fmb::DnaBlock> occ_dna[2];
     fmb::DevBuf<uint8_t> occ_gen[2];
     uint32_t gen_stride = 0, gen_planes = 0;

@@ -20,6 +20,15 @@ __global__ void synth_text_kernel(uint8_t* text, uint64_t n, uint32_t sigma, uin
     text[i] = (i == n - 1) ? 0 : (uint8_t)(1 + (splitmix64(seed + i) >> 32) % (sigma - 1));
 }
 
+// reads[q*L + j] = text[off(q) + j], off(q) = splitmix64(q * 0x632BE59BD9B4E019 + seed) % (n - L)
+__global__ void synth_reads_kernel(const uint8_t* __restrict__ text, uint64_t n, uint64_t nq, uint32_t L, uint64_t seed, uint8_t* __restrict__ out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= nq * L) return;
+    uint64_t q = i / L, j = i % L;
+    uint64_t off = splitmix64(q * 0x632BE59BD9B4E019ull + seed) % (n - L);
+    out[i] = text[off + j];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K1: pack 64 BWT bytes into one DnaBlock (local counts; absolute counts are added after a scan)
 // ---------------------------------------------------------------------------------------------------------

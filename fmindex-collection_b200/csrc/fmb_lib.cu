@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 #include <cub/cub.cuh>
@@ -13,6 +14,9 @@
 namespace fmb {
 
 static thread_local std::string g_error = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void note_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     char buf[1024];
@@ -224,8 +228,9 @@ int new_index(fmb_index** out, int device, uint32_t sigma, uint64_t n, bool bidi
     ix->n = n;
     ix->bidirectional = bidirectional;
     ix->dna = sigma <= 5;
-    cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete ix; return FMB_ECUDA; }
+    ix->stream = ix->own_stream;
     *out = ix;
     return FMB_OK;
 }
@@ -298,7 +303,7 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, co
 void fmb_index_destroy(fmb_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
-    if (ix->stream) cudaStreamDestroy(ix->stream);
+    if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     delete ix;
 }
 
@@ -512,11 +517,15 @@ int fmb_search_exact(const fmb_index* ix, const fmb_queries* q, fmb_results** ou
     cudaMemsetAsync(len.p + nq, 0, sizeof(uint32_t), st);
     auto v = ix->view_dna();
     EventTimer tm(st);
+    cudaEvent_t ev_main = nullptr;
+    cudaEventCreate(&ev_main);
     if (nq) {
         exact_search_kernel<OccDna, true><<<grid_for(nq, 256), 256, 0, st>>>(v, q->symbols.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
+        cudaEventRecord(ev_main, st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("exact_search_kernel: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
         flag_nonzero_kernel<<<grid_for(nq + 1, 256), 256, 0, st>>>(len.p, nq + 1, pos.p);
+        note_launches(2);
     } else {
         cudaMemsetAsync(pos.p, 0, sizeof(uint32_t), st);
     }
@@ -524,8 +533,17 @@ int fmb_search_exact(const fmb_index* ix, const fmb_queries* q, fmb_results** ou
     uint32_t nhits = 0;
     if (cudaMemcpy(&nhits, pos.p + nq, sizeof nhits, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H count failed"); return fail(FMB_ECUDA); }
     if ((rc = res->hits.alloc(nhits))) return fail(rc);
-    if (nhits) compact_exact_hits_kernel<<<grid_for(nq, 256), 256, 0, st>>>(lb.p, len.p, pos.p, q->offsets.p, (uint32_t)nq, res->hits.p);
+    if (nhits) {
+        compact_exact_hits_kernel<<<grid_for(nq, 256), 256, 0, st>>>(lb.p, len.p, pos.p, q->offsets.p, (uint32_t)nq, res->hits.p);
+        note_launches(1);
+    }
     res->stats.kernel_ms = tm.stop();
+    if (nq) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, tm.a, ev_main);
+        res->stats.main_kernel_ms = ms;
+    }
+    cudaEventDestroy(ev_main);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("exact search: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
     unsigned long long h_ctr[4];
@@ -557,16 +575,30 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
     cudaMemsetAsync(ctr.p, 0, 4 * sizeof(unsigned long long), st);
     EventTimer tm(st);
     hit_lengths_kernel<<<grid_for(nh + 1, 256), 256, 0, st>>>(hits->hits.p, nh, starts.p);
+    note_launches(1);
     if ((rc = exclusive_sum_u32(starts.p, starts.p, nh + 1, st))) return fail(rc);
     uint32_t total = 0;
     if (cudaMemcpy(&total, starts.p + nh, sizeof total, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H count failed"); return fail(FMB_ECUDA); }
     // note: the sum of interval lengths must fit 32 bits in this build
     if ((rc = res->locs.alloc(total))) return fail(rc);
+    cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;
+    cudaEventCreate(&ev_m0);
+    cudaEventCreate(&ev_m1);
     if (total) {
         auto v = ix->view_dna();
+        cudaEventRecord(ev_m0, st);
         locate_kernel<OccDna, true><<<grid_for(total, 256), 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p);
+        cudaEventRecord(ev_m1, st);
+        note_launches(1);
     }
     res->stats.kernel_ms = tm.stop();
+    if (total) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_m0, ev_m1);
+        res->stats.main_kernel_ms = ms;
+    }
+    cudaEventDestroy(ev_m0);
+    cudaEventDestroy(ev_m1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("locate: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
     unsigned long long h_ctr[4];
@@ -632,6 +664,23 @@ int fmb_synth_text_device(int device, uint32_t sigma, uint64_t n, uint64_t seed,
     *d_text = p;
     return FMB_OK;
 }
+int fmb_synth_reads_device(int device, const uint8_t* d_text, uint64_t n, uint64_t nq, uint32_t length, uint64_t seed, uint8_t** d_reads) {
+    if (!d_text || !d_reads || length == 0 || n <= (uint64_t)length + 1) { set_error("bad argument"); return FMB_EINVAL; }
+    FMB_TRY(use_device(device));
+    uint8_t* p = nullptr;
+    FMB_CUDA(cudaMalloc(&p, nq * length + 32));
+    synth_reads_kernel<<<grid_for(nq * length, 256), 256>>>(d_text, n, nq, length, seed, p);
+    FMB_CUDA(cudaGetLastError());
+    FMB_CUDA(cudaDeviceSynchronize());
+    *d_reads = p;
+    return FMB_OK;
+}
+int fmb_index_set_stream(fmb_index* ix, void* stream) {
+    if (!ix) { set_error("NULL index"); return FMB_EINVAL; }
+    ix->stream = stream ? (cudaStream_t)stream : ix->own_stream;
+    return FMB_OK;
+}
+uint64_t fmb_kernel_launch_count(void) { return fmb::g_launches.load(); }
 int fmb_device_free(int device, void* p) {
     FMB_TRY(use_device(device));
     FMB_CUDA(cudaFree(p));

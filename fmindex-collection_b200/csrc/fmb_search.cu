@@ -44,6 +44,7 @@ int launch_scheme(const fmb_index* ix, const SchemeParams& sp, const fmb_queries
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * blocks_per_sm, want_blocks));
     kern<<<grid, 256, smem, st>>>(ix->view_dna(), sp, q->symbols.p, q->offsets.p, n_roots, in_items, n_in, out, kStackCap);
     FMB_CUDA(cudaGetLastError());
+    note_launches(1);
     return FMB_OK;
 }
 
@@ -121,6 +122,7 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     res->stats.occ_lookups = h_ctr[1];
     res->stats.frontier_peak = h_ctr[3];
     res->stats.kernel_ms = total_ms;
+    res->stats.main_kernel_ms = total_ms;
     guard.r = nullptr;
     *out_res = res;
     return FMB_OK;
@@ -229,6 +231,7 @@ int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uin
         total.extensions += hits->stats.extensions;
         total.occ_lookups += hits->stats.occ_lookups;
         total.kernel_ms += hits->stats.kernel_ms;
+        total.main_kernel_ms += hits->stats.main_kernel_ms;
         fmb_results_destroy(hits);
         if (rc) return rc;
         total.lf_steps += locs->stats.lf_steps;

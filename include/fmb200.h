@@ -74,6 +74,7 @@ typedef struct {
     uint64_t lf_steps;         /* LF steps walked by locate                                 */
     uint64_t frontier_peak;    /* largest breadth-first frontier (scheme search)            */
     double   kernel_ms;        /* device time of the call (CUDA events)                     */
+    double   main_kernel_ms;   /* device time of the dominant kernel alone (search / LF walk) */
 } fmb_stats;
 
 const char* fmb_last_error(void);
@@ -176,6 +177,14 @@ int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uin
 /* T[i] = 1 + (splitmix64(seed + i) % (sigma-1)) for i < n-1, T[n-1] = 0; written to a device buffer owned by the
  * library (free with fmb_device_free).  The same generator is restated in fmb200/synth.py for the CPU side. */
 int  fmb_synth_text_device(int device, uint32_t sigma, uint64_t n, uint64_t seed, uint8_t** d_text);
+/* nq reads of `length` symbols copied from d_text at offsets splitmix64(i * 0x632BE59BD9B4E019 + seed) % (n - length)
+ * (never covering the final delimiter); written back to back into a device buffer owned by the library. */
+int  fmb_synth_reads_device(int device, const uint8_t* d_text, uint64_t n, uint64_t nq, uint32_t length, uint64_t seed, uint8_t** d_reads);
+/* All work of `ix` is enqueued on `stream` (a cudaStream_t of the index's device, e.g. the caller's timing
+ * stream) instead of the index's private stream.  NULL restores the private stream. */
+int  fmb_index_set_stream(fmb_index* ix, void* stream);
+/* number of kernels of this library launched by the calling process so far (bench.py's gpu_launches) */
+uint64_t fmb_kernel_launch_count(void);
 int  fmb_device_free(int device, void* p);
 int  fmb_copy_to_host(int device, void* dst_host, const void* src_device, uint64_t bytes);
 void* fmb_host_alloc_pinned(uint64_t bytes);

@@ -389,5 +389,6 @@ extern "C" int fmb_index_build(fmb_index** out, int device, uint32_t sigma, cons
     FMB_TRY(compute_C(ix));
     guard.ix = nullptr;
     *out = ix;
+    pool_trim();
     return FMB_OK;
 }

@@ -4,7 +4,9 @@
 #include <cstdarg>
 #include <cstring>
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <unordered_map>
 
 #include <cub/cub.cuh>
 
@@ -25,6 +27,81 @@ void set_error(const char* fmt, ...) {
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
     g_error = buf;
+}
+
+// ---- caching device allocator (see fmb_host.hpp) ------------------------------------------------------------
+namespace {
+struct Pool {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> free_blocks;      // (device, class size) -> block
+    std::unordered_map<void*, std::pair<int, size_t>> live;         // block -> (device, class size)
+    size_t cached_bytes = 0;
+};
+Pool& pool() {
+    static Pool* p = new Pool();     // intentionally leaked: must outlive static destructors that free buffers
+    return *p;
+}
+size_t size_class(size_t bytes) {
+    if (bytes <= 4096) return 4096;
+    int top = 63 - __builtin_clzll((unsigned long long)bytes);
+    size_t step = size_t(1) << (top - 3);
+    return (bytes + step - 1) / step * step;
+}
+constexpr size_t kMaxCachedBlock = size_t(1) << 30;
+}  // namespace
+
+void pool_trim() {
+    Pool& P = pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    for (auto& kv : P.free_blocks) cudaFree(kv.second);
+    P.free_blocks.clear();
+    P.cached_bytes = 0;
+}
+
+void* pool_alloc(size_t bytes) {
+    Pool& P = pool();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t cls = size_class(bytes);
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        auto it = P.free_blocks.find({dev, cls});
+        if (it != P.free_blocks.end()) {
+            void* p = it->second;
+            P.free_blocks.erase(it);
+            P.cached_bytes -= cls;
+            P.live[p] = {dev, cls};
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cls);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pool_trim();
+        e = cudaMalloc(&p, cls);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc(%zu bytes) failed: %s", cls, cudaGetErrorString(e));
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.live[p] = {dev, cls};
+    return p;
+}
+
+void pool_free(void* p) {
+    if (!p) return;
+    Pool& P = pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.live.find(p);
+    if (it == P.live.end()) { cudaFree(p); return; }
+    auto key = it->second;
+    P.live.erase(it);
+    if (key.second > kMaxCachedBlock) { cudaFree(p); return; }
+    P.free_blocks.insert({key, p});
+    P.cached_bytes += key.second;
 }
 
 static int use_device(int device) {
@@ -297,6 +374,7 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, co
         if (rc) return fail(rc);
     }
     *out = ix;
+    pool_trim();
     return FMB_OK;
 }
 
@@ -305,6 +383,7 @@ void fmb_index_destroy(fmb_index* ix) {
     cudaSetDevice(ix->device);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     delete ix;
+    pool_trim();
 }
 
 int fmb_index_get_info(const fmb_index* ix, fmb_index_info* info) {

@@ -100,9 +100,17 @@ struct fmb_index {
     uint64_t device_bytes() const;
 };
 
+namespace fmb {
+// Stream the calling thread enqueues the work of `ix` on: a per-thread override (used by the pipelined
+// search+locate path, where several host threads drive one index on their own streams) or the index's stream.
+extern thread_local cudaStream_t tls_stream_override;
+inline cudaStream_t active_stream(const fmb_index* ix) { return tls_stream_override ? tls_stream_override : ix->stream; }
+}  // namespace fmb
+
 struct fmb_queries {
     int device = 0;
     uint64_t nq = 0;
+    uint64_t qidx_base = 0;           // added to every reported qidx (chunked uploads)
     uint64_t total_symbols = 0;
     uint32_t max_len = 0, min_len = 0;
     fmb::DevBuf<uint8_t> symbols;     // padded to a multiple of 16 bytes

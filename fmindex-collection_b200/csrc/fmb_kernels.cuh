@@ -263,14 +263,14 @@ __global__ void flag_nonzero_kernel(const uint32_t* __restrict__ len, uint64_t c
     flag[i] = len[i] ? 1u : 0u;
 }
 __global__ void compact_exact_hits_kernel(const uint32_t* __restrict__ lb, const uint32_t* __restrict__ len,
-                                          const uint32_t* __restrict__ pos, const uint64_t* __restrict__ qoff, uint32_t nq,
+                                          const uint32_t* __restrict__ pos, const uint64_t* __restrict__ qoff, uint32_t nq, uint32_t qidx_base,
                                           HitRec* __restrict__ hits) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     uint32_t l = len[q];
     if (!l) return;
     HitRec h;
-    h.qidx = q; h.lb = lb[q]; h.lb_rev = 0; h.len = l;
+    h.qidx = q + qidx_base; h.lb = lb[q]; h.lb_rev = 0; h.len = l;
     h.steps = (uint32_t)(qoff[q + 1] - qoff[q]);
     h.e = 0;
     hits[pos[q]] = h;

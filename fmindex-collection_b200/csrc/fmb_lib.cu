@@ -16,6 +16,7 @@
 namespace fmb {
 
 static thread_local std::string g_error = "";
+thread_local cudaStream_t tls_stream_override = nullptr;
 static std::atomic<uint64_t> g_launches{0};
 
 void note_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -199,7 +200,7 @@ namespace fmb {
 int build_occ_from_device_bwt(fmb_index* ix, int dir, const uint8_t* d_bwt) {
     const uint64_t n = ix->n;
     const uint64_t nblocks = n / 64 + 1;
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = active_stream(ix);
     if (!ix->dna) {
         set_error("sigma %u: generic occurrence table not built in this call path", ix->sigma);
         return FMB_EUNSUPPORTED;
@@ -267,7 +268,7 @@ int compute_C(fmb_index* ix) {
 int build_marks_from_device(fmb_index* ix, const uint64_t* d_bitmap, const uint32_t* d_seq, const uint32_t* d_pos, uint64_t n_samples) {
     const uint64_t words = ix->n / 64 + 1;
     const uint64_t have = (ix->n + 63) / 64;
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = active_stream(ix);
     DevBuf<uint32_t> pc;
     FMB_TRY(pc.alloc(words + 1));
     popcount_words_kernel<<<grid_for(words + 1, 256), 256, 0, st>>>(d_bitmap, have, words + 1, pc.p);
@@ -410,7 +411,7 @@ int fmb_index_get_C(const fmb_index* ix, uint64_t* C) {
 int fmb_index_export(const fmb_index* ix, uint8_t* bwt, uint8_t* bwt_rev, uint64_t* sample_bitmap, uint32_t* sample_seq, uint32_t* sample_pos) {
     if (!ix) { set_error("NULL index"); return FMB_EINVAL; }
     FMB_TRY(use_device(ix->device));
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = active_stream(ix);
     auto v = ix->view_dna();
     for (int d = 0; d < 2; ++d) {
         uint8_t* dst = d ? bwt_rev : bwt;
@@ -455,7 +456,7 @@ static int string_op(const fmb_index* ix, int dir, int op, const uint64_t* idx, 
         if (idx[i] > lim) { set_error("idx[%llu] = %llu out of range", (unsigned long long)i, (unsigned long long)idx[i]); return FMB_EINVAL; }
         if (symb && ((op == 2) ? symb[i] > ix->sigma : symb[i] >= ix->sigma)) { set_error("symbol %u out of range", symb[i]); return FMB_EINVAL; }
     }
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = active_stream(ix);
     DevBuf<uint64_t> d_idx, d_out, d_out2;
     DevBuf<uint8_t> d_symb;
     FMB_TRY(upload(d_idx, idx, count, st));
@@ -500,7 +501,7 @@ static int cursor_op(const fmb_index* ix, int right, const uint64_t* cur, const 
         if (cur[4 * i] + cur[4 * i + 2] > ix->n || cur[4 * i + 1] + cur[4 * i + 2] > ix->n) { set_error("cursor %llu out of range", (unsigned long long)i); return FMB_EINVAL; }
         if (!all && symb[i] >= ix->sigma) { set_error("symbol out of range"); return FMB_EINVAL; }
     }
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = active_stream(ix);
     DevBuf<uint64_t> d_cur, d_out;
     DevBuf<uint8_t> d_symb;
     FMB_TRY(upload(d_cur, cur, count * 4, st));
@@ -547,7 +548,7 @@ int fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* sy
     }
     q->max_len = mx;
     q->min_len = nq ? mn : 0;
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = active_stream(ix);
     int rc = q->symbols.alloc(total + 32);
     if (!rc) rc = q->offsets.alloc(nq + 1);
     if (rc) { delete q; return rc; }
@@ -582,7 +583,7 @@ int fmb_search_exact(const fmb_index* ix, const fmb_queries* q, fmb_results** ou
     *out = nullptr;
     if (q->device != ix->device) { set_error("queries live on device %d, index on %d", q->device, ix->device); return FMB_EINVAL; }
     FMB_TRY(use_device(ix->device));
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = active_stream(ix);
     auto res = new fmb_results();
     res->device = ix->device;
     res->kind = 0;
@@ -613,7 +614,7 @@ int fmb_search_exact(const fmb_index* ix, const fmb_queries* q, fmb_results** ou
     if (cudaMemcpy(&nhits, pos.p + nq, sizeof nhits, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H count failed"); return fail(FMB_ECUDA); }
     if ((rc = res->hits.alloc(nhits))) return fail(rc);
     if (nhits) {
-        compact_exact_hits_kernel<<<grid_for(nq, 256), 256, 0, st>>>(lb.p, len.p, pos.p, q->offsets.p, (uint32_t)nq, res->hits.p);
+        compact_exact_hits_kernel<<<grid_for(nq, 256), 256, 0, st>>>(lb.p, len.p, pos.p, q->offsets.p, (uint32_t)nq, (uint32_t)q->qidx_base, res->hits.p);
         note_launches(1);
     }
     res->stats.kernel_ms = tm.stop();
@@ -641,7 +642,7 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
     if (hits->kind != 0) { set_error("fmb_locate needs a hit result set"); return FMB_EINVAL; }
     if (hits->device != ix->device) { set_error("results live on another device"); return FMB_EINVAL; }
     FMB_TRY(use_device(ix->device));
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = active_stream(ix);
     auto res = new fmb_results();
     res->device = ix->device;
     res->kind = 1;

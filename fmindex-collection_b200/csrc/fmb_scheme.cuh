@@ -91,6 +91,7 @@ struct SchemeOut {
     uint64_t overflow_capacity;
     unsigned long long* counters;      // [0] extensions, [1] occ lookups, [3] peak items per warp
     unsigned long long* root_counter;
+    uint32_t qidx_base;                // added to the reported qidx (chunked query batches)
 };
 
 // one cursor extension by `symb` in direction `right` from two loaded blocks (DNA: blocks are symbol independent)
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(256) scheme_search_kernel(IndexView<OCC> ix, S
                     unsigned long long idx = base + __popc(rb & ((1u << lane) - 1));
                     if (idx < out.hit_capacity) {
                         HitRec h;
-                        h.qidx = st.qidx; h.lb = st.lb; h.lb_rev = sp.zero_lb_rev ? 0 : st.lb_rev; h.len = st.len; h.steps = st.steps; h.e = st.e;
+                        h.qidx = st.qidx + out.qidx_base; h.lb = st.lb; h.lb_rev = sp.zero_lb_rev ? 0 : st.lb_rev; h.len = st.len; h.steps = st.steps; h.e = st.e;
                         out.hits[idx] = h;
                     }
                 }

@@ -1,6 +1,10 @@
 // fmb_search.cu -- host side of the k-error searches (K3) and the one-call search+locate path.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "fmb_host.hpp"
@@ -50,7 +54,7 @@ int launch_scheme(const fmb_index* ix, const SchemeParams& sp, const fmb_queries
 
 int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp, fmb_results** out_res) {
     FMB_TRY(set_device(ix->device));
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = active_stream(ix);
     auto res = new fmb_results();
     res->device = ix->device;
     res->kind = 0;
@@ -81,6 +85,7 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
         so.overflow_capacity = ovf_cap;
         so.counters = ctr.p;
         so.root_counter = ctr.p + 6;
+        so.qidx_base = (uint32_t)q->qidx_base;
         uint64_t roots = n_roots, n_in = 0;
         int cur = 0;
         cudaEventRecord(ev0, st);
@@ -209,51 +214,108 @@ int fmb_search_backtracking(const fmb_index* ix, const fmb_queries* q, uint32_t 
     return run_scheme(ix, q, sp, out);
 }
 
+// One-call path: the query batch is cut into chunks; up to three host threads each drive their own CUDA stream
+// (upload -> search -> locate -> download of one chunk), so the H2D copy of one chunk, the kernels of another and
+// the D2H copy of a third overlap.  Rows are appended to `out` in completion order (they carry their qidx).
 int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq, int edit,
                           uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l, const uint32_t* u,
                           const uint32_t* partition, fmb_loc32* out, uint64_t capacity, uint64_t* n_out, fmb_stats* stats) {
-    if (!ix || !offsets || !n_out) { set_error("NULL argument"); return FMB_EINVAL; }
+    if (!ix || !offsets || !n_out || (capacity && !out)) { set_error("NULL argument"); return FMB_EINVAL; }
     *n_out = 0;
+    if (stats) *stats = fmb_stats{};
+    if (nq == 0) return FMB_OK;
+    FMB_TRY(set_device(ix->device));
+    const uint64_t chunk = n_searches ? (1u << 18) : (1u << 20);
+    const uint64_t n_chunks = (nq + chunk - 1) / chunk;
+    const int n_threads = (int)std::min<uint64_t>(3, n_chunks);
+    std::atomic<uint64_t> next_chunk{0}, written{0}, needed{0};
+    std::atomic<int> err{FMB_OK};
+    std::mutex mu;
+    std::string err_msg;
     fmb_stats total{};
-    // chunks of queries: bounded device memory, and the next upload overlaps nothing yet (single stream)
-    const uint64_t chunk = 1u << 22;
-    uint64_t written = 0;
-    for (uint64_t b = 0; b < nq || (nq == 0 && b == 0); b += chunk) {
-        uint64_t e = std::min(nq, b + chunk);
-        fmb_queries* q = nullptr;
-        FMB_TRY(fmb_queries_upload(&q, ix, symbols, offsets + b, e - b));
-        fmb_results* hits = nullptr;
-        int rc = n_searches ? fmb_search_scheme(ix, q, edit, n_searches, n_parts, pi, l, u, partition, &hits) : fmb_search_exact(ix, q, &hits);
-        fmb_queries_destroy(q);
-        if (rc) return rc;
-        fmb_results* locs = nullptr;
-        rc = fmb_locate(ix, hits, &locs);
-        total.extensions += hits->stats.extensions;
-        total.occ_lookups += hits->stats.occ_lookups;
-        total.kernel_ms += hits->stats.kernel_ms;
-        total.main_kernel_ms += hits->stats.main_kernel_ms;
-        fmb_results_destroy(hits);
-        if (rc) return rc;
-        total.lf_steps += locs->stats.lf_steps;
-        total.occ_lookups += locs->stats.occ_lookups;
-        total.kernel_ms += locs->stats.kernel_ms;
-        uint64_t cnt = locs->count;
-        if (written + cnt > capacity) {
-            fmb_results_destroy(locs);
-            *n_out = written + cnt;
-            set_error("output capacity %llu too small", (unsigned long long)capacity);
-            return FMB_EOVERFLOW;
+
+    auto worker = [&]() {
+        cudaSetDevice(ix->device);
+        cudaStream_t st = nullptr;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+            std::lock_guard<std::mutex> lk(mu);
+            err = FMB_ECUDA;
+            err_msg = "cudaStreamCreate failed";
+            return;
         }
-        rc = fmb_results_fetch_locs32(locs, out + written, capacity - written);
-        fmb_results_destroy(locs);
-        if (rc) return rc;
-        // qidx is chunk relative on the device
-        if (b) for (uint64_t i = written; i < written + cnt; ++i) out[i].qidx += (uint32_t)b;
-        written += cnt;
-        if (nq == 0) break;
-    }
-    *n_out = written;
+        tls_stream_override = st;
+        fmb_stats mine{};
+        auto fail = [&](int rc) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (err == FMB_OK) { err = rc; err_msg = fmb_last_error(); }
+        };
+        for (;;) {
+            uint64_t c = next_chunk.fetch_add(1);
+            const int e0 = err;
+            if (c >= n_chunks || (e0 != FMB_OK && e0 != FMB_EOVERFLOW)) break;
+            uint64_t b = c * chunk, e = std::min(nq, b + chunk);
+            fmb_queries* q = nullptr;
+            int rc = fmb_queries_upload(&q, ix, symbols, offsets + b, e - b);
+            if (rc) { fail(rc); break; }
+            q->qidx_base = b;
+            fmb_results* hits = nullptr;
+            rc = n_searches ? fmb_search_scheme(ix, q, edit, n_searches, n_parts, pi, l, u, partition, &hits) : fmb_search_exact(ix, q, &hits);
+            fmb_queries_destroy(q);
+            if (rc) { fail(rc); break; }
+            fmb_results* locs = nullptr;
+            rc = fmb_locate(ix, hits, &locs);
+            mine.extensions += hits->stats.extensions;
+            mine.occ_lookups += hits->stats.occ_lookups;
+            mine.kernel_ms += hits->stats.kernel_ms;
+            mine.main_kernel_ms += hits->stats.main_kernel_ms;
+            mine.frontier_peak = std::max(mine.frontier_peak, hits->stats.frontier_peak);
+            fmb_results_destroy(hits);
+            if (rc) { fail(rc); break; }
+            mine.lf_steps += locs->stats.lf_steps;
+            mine.occ_lookups += locs->stats.occ_lookups;
+            mine.kernel_ms += locs->stats.kernel_ms;
+            uint64_t cnt = locs->count;
+            needed.fetch_add(cnt);
+            uint64_t off = written.fetch_add(cnt);
+            if (off + cnt > capacity) {
+                fmb_results_destroy(locs);
+                std::lock_guard<std::mutex> lk(mu);
+                if (err == FMB_OK) { err = FMB_EOVERFLOW; err_msg = "output capacity too small"; }
+                continue;                    // keep counting so that *n_out reports the size that is needed
+            }
+            cudaError_t ce = cudaSuccess;
+            if (cnt) ce = cudaMemcpyAsync(out + off, locs->locs.p, cnt * sizeof(fmb_loc32), cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+            fmb_results_destroy(locs);
+            if (ce != cudaSuccess) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (err == FMB_OK) { err = FMB_ECUDA; err_msg = std::string("D2H of located rows: ") + cudaGetErrorString(ce); }
+                break;
+            }
+        }
+        tls_stream_override = nullptr;
+        cudaStreamDestroy(st);
+        std::lock_guard<std::mutex> lk(mu);
+        total.extensions += mine.extensions;
+        total.occ_lookups += mine.occ_lookups;
+        total.lf_steps += mine.lf_steps;
+        total.kernel_ms += mine.kernel_ms;
+        total.main_kernel_ms += mine.main_kernel_ms;
+        total.frontier_peak = std::max(total.frontier_peak, mine.frontier_peak);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
     if (stats) *stats = total;
+    if (err == FMB_EOVERFLOW) {
+        // on overflow every chunk still ran its search: *n_out = capacity needed
+        *n_out = needed.load();
+        set_error("output capacity %llu too small, %llu rows found", (unsigned long long)capacity, (unsigned long long)needed.load());
+        return FMB_EOVERFLOW;
+    }
+    if (err != FMB_OK) { set_error("%s", err_msg.c_str()); return err; }
+    *n_out = written.load();
     return FMB_OK;
 }
 

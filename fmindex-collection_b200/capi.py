@@ -41,7 +41,7 @@ SYMBOLS = [
     "fmb_string_symbol", "fmb_string_rank", "fmb_string_prefix_rank", "fmb_string_all_ranks",
     "fmb_cursor_extend", "fmb_cursor_extend_all",
     "fmb_queries_upload", "fmb_queries_destroy", "fmb_queries_count",
-    "fmb_search_exact", "fmb_search_scheme", "fmb_search_backtracking", "fmb_locate",
+    "fmb_search_exact", "fmb_search_scheme", "fmb_search_backtracking", "fmb_locate", "fmb_locate_rows", "fmb_sample_value",
     "fmb_results_count", "fmb_results_kind", "fmb_results_fetch_hits", "fmb_results_fetch_locs", "fmb_results_fetch_locs32",
     "fmb_results_get_stats", "fmb_results_destroy",
     "fmb_search_and_locate",
@@ -232,6 +232,24 @@ class Index:
         r = C.c_void_p()
         _check(lib().fmb_locate(self.h, hits.h, C.byref(r)))
         return Results(r)
+
+    def locate_rows(self, rows):
+        """index.locate(row) for many rows: (seq, pos, steps) arrays"""
+        rows = _u64(rows)
+        seq = np.zeros(rows.size, dtype=np.uint32)
+        pos = np.zeros(rows.size, dtype=np.uint32)
+        steps = np.zeros(rows.size, dtype=np.uint64)
+        _check(lib().fmb_locate_rows(self.h, _ptr(rows), C.c_uint64(rows.size), _ptr(seq), _ptr(pos), _ptr(steps)))
+        return seq, pos, steps
+
+    def sample_value(self, rows):
+        """index.single_locate_step(row) for many rows: (has, seq, pos) arrays"""
+        rows = _u64(rows)
+        has = np.zeros(rows.size, dtype=np.uint8)
+        seq = np.zeros(rows.size, dtype=np.uint32)
+        pos = np.zeros(rows.size, dtype=np.uint32)
+        _check(lib().fmb_sample_value(self.h, _ptr(rows), C.c_uint64(rows.size), _ptr(has), _ptr(seq), _ptr(pos)))
+        return has, seq, pos
 
     def search_and_locate(self, symbols, offsets, scheme=None, partition=None, edit=False, capacity=None,
                           out=None):

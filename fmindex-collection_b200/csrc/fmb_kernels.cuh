@@ -332,4 +332,50 @@ __global__ void __launch_bounds__(256) locate_kernel(IndexView<OCC> ix, const Hi
     }
 }
 
+// index.locate(row) for arbitrary rows (fmindex/BiFMIndex.h:177-202): same LF walk as locate_kernel, row list input
+template <class OCC>
+__global__ void __launch_bounds__(256) locate_rows_kernel(IndexView<OCC> ix, const uint64_t* __restrict__ rows, uint64_t count,
+                                                          uint32_t* __restrict__ seq, uint32_t* __restrict__ pos, uint64_t* __restrict__ steps_out) {
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    row_t row = (row_t)rows[t];
+    const OCC& occ = ix.occ[0];
+    uint32_t steps = 0;
+    for (;;) {
+        uint4 m = __ldg(ix.marks + (row >> 6));
+        typename OCC::Block b = occ.load(row >> 6, 0);
+        uint64_t bits = (uint64_t)m.x | ((uint64_t)m.y << 32);
+        uint32_t o = row & 63;
+        if ((bits >> o) & 1) {
+            uint2 sample = __ldg(ix.samples + (m.z + __popcll(bits & low_mask(o))));
+            seq[t] = sample.x;
+            pos[t] = sample.y;
+            steps_out[t] = steps;
+            return;
+        }
+        uint32_t c = occ.symbol(b, row);
+        if (OCC::kSymbolLoad) b = occ.load(row >> 6, c);
+        row = ix.C[c] + occ.rank(b, row, c);
+        ++steps;
+    }
+}
+
+// annotatedArray.value(row) (suffixarray/SparseArray.h:63-70)
+template <class OCC>
+__global__ void sample_value_kernel(IndexView<OCC> ix, const uint64_t* __restrict__ rows, uint64_t count, uint8_t* __restrict__ has,
+                                    uint32_t* __restrict__ seq, uint32_t* __restrict__ pos) {
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    row_t row = (row_t)rows[t];
+    uint4 m = __ldg(ix.marks + (row >> 6));
+    uint64_t bits = (uint64_t)m.x | ((uint64_t)m.y << 32);
+    uint32_t o = row & 63;
+    bool h = (bits >> o) & 1;
+    has[t] = h ? 1 : 0;
+    uint2 sample = make_uint2(0, 0);
+    if (h) sample = __ldg(ix.samples + (m.z + __popcll(bits & low_mask(o))));
+    seq[t] = sample.x;
+    pos[t] = sample.y;
+}
+
 }  // namespace fmb

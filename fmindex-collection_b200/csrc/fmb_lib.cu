@@ -690,6 +690,54 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
     return FMB_OK;
 }
 
+int fmb_locate_rows(const fmb_index* ix, const uint64_t* rows, uint64_t count, uint32_t* seq, uint32_t* pos, uint64_t* steps) {
+    if (!ix || (count && (!rows || !seq || !pos || !steps))) { set_error("NULL argument"); return FMB_EINVAL; }
+    FMB_TRY(use_device(ix->device));
+    if (count == 0) return FMB_OK;
+    if (ix->n_samples == 0) { set_error("index has no sampled suffix array"); return FMB_EINVAL; }
+    for (uint64_t i = 0; i < count; ++i)
+        if (rows[i] >= ix->n) { set_error("rows[%llu] = %llu out of range", (unsigned long long)i, (unsigned long long)rows[i]); return FMB_EINVAL; }
+    cudaStream_t st = active_stream(ix);
+    DevBuf<uint64_t> d_rows, d_steps;
+    DevBuf<uint32_t> d_seq, d_pos;
+    FMB_TRY(upload(d_rows, rows, count, st));
+    FMB_TRY(d_steps.alloc(count));
+    FMB_TRY(d_seq.alloc(count));
+    FMB_TRY(d_pos.alloc(count));
+    locate_rows_kernel<<<grid_for(count, 256), 256, 0, st>>>(ix->view_dna(), d_rows.p, count, d_seq.p, d_pos.p, d_steps.p);
+    FMB_CUDA(cudaGetLastError());
+    note_launches(1);
+    FMB_CUDA(cudaMemcpyAsync(seq, d_seq.p, count * 4, cudaMemcpyDeviceToHost, st));
+    FMB_CUDA(cudaMemcpyAsync(pos, d_pos.p, count * 4, cudaMemcpyDeviceToHost, st));
+    FMB_CUDA(cudaMemcpyAsync(steps, d_steps.p, count * 8, cudaMemcpyDeviceToHost, st));
+    FMB_CUDA(cudaStreamSynchronize(st));
+    return FMB_OK;
+}
+
+int fmb_sample_value(const fmb_index* ix, const uint64_t* rows, uint64_t count, uint8_t* has, uint32_t* seq, uint32_t* pos) {
+    if (!ix || (count && (!rows || !has || !seq || !pos))) { set_error("NULL argument"); return FMB_EINVAL; }
+    FMB_TRY(use_device(ix->device));
+    if (count == 0) return FMB_OK;
+    for (uint64_t i = 0; i < count; ++i)
+        if (rows[i] >= ix->n) { set_error("rows[%llu] = %llu out of range", (unsigned long long)i, (unsigned long long)rows[i]); return FMB_EINVAL; }
+    cudaStream_t st = active_stream(ix);
+    DevBuf<uint64_t> d_rows;
+    DevBuf<uint32_t> d_seq, d_pos;
+    DevBuf<uint8_t> d_has;
+    FMB_TRY(upload(d_rows, rows, count, st));
+    FMB_TRY(d_has.alloc(count));
+    FMB_TRY(d_seq.alloc(count));
+    FMB_TRY(d_pos.alloc(count));
+    sample_value_kernel<<<grid_for(count, 256), 256, 0, st>>>(ix->view_dna(), d_rows.p, count, d_has.p, d_seq.p, d_pos.p);
+    FMB_CUDA(cudaGetLastError());
+    note_launches(1);
+    FMB_CUDA(cudaMemcpyAsync(has, d_has.p, count, cudaMemcpyDeviceToHost, st));
+    FMB_CUDA(cudaMemcpyAsync(seq, d_seq.p, count * 4, cudaMemcpyDeviceToHost, st));
+    FMB_CUDA(cudaMemcpyAsync(pos, d_pos.p, count * 4, cudaMemcpyDeviceToHost, st));
+    FMB_CUDA(cudaStreamSynchronize(st));
+    return FMB_OK;
+}
+
 // ---- results ----------------------------------------------------------------------------------------------------
 uint64_t fmb_results_count(const fmb_results* r) { return r ? r->count : 0; }
 int fmb_results_kind(const fmb_results* r) { return r ? r->kind : -1; }

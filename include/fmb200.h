@@ -155,6 +155,15 @@ int fmb_search_backtracking(const fmb_index* ix, const fmb_queries* q, uint32_t 
  * (BiFMIndex.h:177-202, FMIndex.h:114-124); output rows carry pos + offset like search/search.h:55-60. */
 int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out);
 
+/* index.locate(idx) for `count` arbitrary SA rows in one launch (fmindex/BiFMIndex.h:177-202, FMIndex.h:114-124):
+ * (seqId, pos) of the nearest sampled row on the LF path and the number of LF steps walked; the text position of
+ * row i is pos[i] + steps[i].  All pointers host. */
+int fmb_locate_rows(const fmb_index* ix, const uint64_t* rows, uint64_t count, uint32_t* seq, uint32_t* pos, uint64_t* steps);
+
+/* index.single_locate_step(idx) = annotatedArray.value(idx) (fmindex/BiFMIndex.h:204-206, suffixarray/SparseArray.h:63-70):
+ * has[i] = 1 and (seq[i], pos[i]) = the sample when row i is sampled, else has[i] = 0. */
+int fmb_sample_value(const fmb_index* ix, const uint64_t* rows, uint64_t count, uint8_t* has, uint32_t* seq, uint32_t* pos);
+
 /* ---- results ----------------------------------------------------------------------------------------------- */
 uint64_t fmb_results_count(const fmb_results* r);
 int  fmb_results_kind(const fmb_results* r);                /* 0 = hits (cursors), 1 = located rows */

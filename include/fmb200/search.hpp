@@ -1,0 +1,330 @@
+// fmb200/search.hpp -- the reference's batch search entry points, executed by the CUDA kernels of libfmb200.so.
+//
+// Same names, argument meaning and delegate shapes as the reference (paths relative to
+// /root/reference/src/fmindex-collection/):
+//   search/SearchNoErrors.h:13-26,28-85   search_no_errors::search(index, query) / (index, queries, delegate(qidx, cursor))
+//   search/SearchNg26.h:426-444           search_ng26::search<Edit>(index, queries, scheme, partition, delegate(qidx, cursor, e))
+//                                         search_ng26::search<Edit>(index, queries, maxErrors, delegate)
+//   search/Backtracking.h:85-98           search_backtracking::search(index, queries, maxError, delegate(qidx, cursor, e))
+//   search/search.h:14-75                 fmc::search<Edit>(index, queries, errors, delegate), fmc::Search{...}()
+//   locate.h:15-57                        LocateLinear{index, cursor}
+// Differences a caller can observe: delegates are invoked after the device finished, grouped by
+// ascending qidx (the reference's batched exact search retires queries out of order; tests compare sorted); the
+// hit limit `n` of search_n / search_best is not supported (it depends on the reference's DFS order) -- any n other
+// than the default throws.  `*_bulk` variants return the raw records without per-hit callbacks.
+#pragma once
+#include <algorithm>
+#include <limits>
+#include <map>
+#include <memory>
+#include <optional>
+
+#include "index.hpp"
+#include "search_scheme.hpp"
+
+namespace fmb200 {
+
+namespace detail {
+struct QueriesDeleter { void operator()(fmb_queries* p) const { fmb_queries_destroy(p); } };
+struct ResultsDeleter { void operator()(fmb_results* p) const { fmb_results_destroy(p); } };
+using QueriesHandle = std::unique_ptr<fmb_queries, QueriesDeleter>;
+using ResultsHandle = std::unique_ptr<fmb_results, ResultsDeleter>;
+
+inline QueriesHandle upload(fmb_index const* ix, FlatSequences const& f, size_t first = 0, size_t count = std::numeric_limits<size_t>::max()) {
+    count = std::min(count, f.size() - first);
+    fmb_queries* q{};
+    check(fmb_queries_upload(&q, ix, f.symbols.data(), f.offsets.data() + first, count));
+    return QueriesHandle{q};
+}
+inline std::vector<fmb_hit> fetch_hits(fmb_results* r) {
+    std::vector<fmb_hit> hits(fmb_results_count(r));
+    check(fmb_results_fetch_hits(r, hits.data(), hits.size()));
+    return hits;
+}
+inline void sort_hits(std::vector<fmb_hit>& hits) {
+    std::sort(hits.begin(), hits.end(), [](fmb_hit const& a, fmb_hit const& b) {
+        return std::tie(a.qidx, a.e, a.lb, a.len, a.steps, a.lb_rev) < std::tie(b.qidx, b.e, b.lb, b.len, b.steps, b.lb_rev);
+    });
+}
+struct FlatScheme {
+    uint32_t n_searches{}, n_parts{};
+    std::vector<uint32_t> pi, l, u, partition;
+};
+// any range of {pi, l, u} records: fmb200::search_scheme::Scheme or the reference's fmc::search_scheme::Scheme
+template <typename T>
+concept SchemeLike = std::ranges::range<T> && requires(T const& t) {
+    { std::ranges::begin(t)->pi.size() } -> std::convertible_to<size_t>;
+    { std::ranges::begin(t)->l[0] } -> std::convertible_to<size_t>;
+    { std::ranges::begin(t)->u[0] } -> std::convertible_to<size_t>;
+};
+template <SchemeLike scheme_t>
+FlatScheme flatten(scheme_t const& ss, std::vector<size_t> const& partition) {
+    if (std::ranges::empty(ss)) throw std::invalid_argument("fmb200: empty search scheme");
+    FlatScheme f;
+    f.n_searches = static_cast<uint32_t>(std::ranges::size(ss));
+    f.n_parts = static_cast<uint32_t>(std::ranges::begin(ss)->pi.size());
+    if (partition.size() != f.n_parts) throw std::invalid_argument("fmb200: partition size does not match the scheme");
+    for (auto const& s : ss) {
+        if (s.pi.size() != f.n_parts || s.l.size() != f.n_parts || s.u.size() != f.n_parts) throw std::invalid_argument("fmb200: ragged search scheme");
+        for (size_t p = 0; p < f.n_parts; ++p) {
+            f.pi.push_back(static_cast<uint32_t>(s.pi[p]));
+            f.l.push_back(static_cast<uint32_t>(s.l[p]));
+            f.u.push_back(static_cast<uint32_t>(s.u[p]));
+        }
+    }
+    for (auto p : partition) f.partition.push_back(static_cast<uint32_t>(p));
+    return f;
+}
+template <typename index_t>
+constexpr bool is_bidirectional = requires(index_t const& ix) { ix.bwtRev; };
+
+template <typename index_t>
+auto make_cursor(index_t const& index, fmb_hit const& h) {
+    using cursor_t = select_cursor_t<index_t>;
+    if constexpr (requires { cursor_t{index, size_t{}, size_t{}, size_t{}, size_t{}}; }) {
+        return cursor_t{index, h.lb, h.lb_rev, h.len, h.steps};
+    } else {
+        return cursor_t{index, h.lb, h.len};
+    }
+}
+template <typename index_t>
+auto make_left_cursor(index_t const& index, fmb_hit const& h) {
+    using cursor_t = select_left_cursor_t<index_t>;
+    if constexpr (requires { cursor_t{index, size_t{}, size_t{}, size_t{}}; }) {
+        return cursor_t{index, h.lb, h.len, h.steps};
+    } else {
+        return cursor_t{index, h.lb, h.len};
+    }
+}
+}  // namespace detail
+
+// =====================================================================================================================
+namespace search_no_errors {
+
+// bulk form: one record per query with a non-empty interval
+template <typename index_t, Sequences queries_t>
+std::vector<fmb_hit> search_bulk(index_t const& index, queries_t const& queries, fmb_stats* stats = nullptr) {
+    auto flat = flatten(queries);
+    auto q = detail::upload(index.handle(), flat);
+    fmb_results* r{};
+    check(fmb_search_exact(index.handle(), q.get(), &r));
+    detail::ResultsHandle res{r};
+    if (stats) check(fmb_results_get_stats(r, stats));
+    return detail::fetch_hits(r);
+}
+
+// SearchNoErrors.h:28-85
+template <typename index_t, Sequences queries_t, typename delegate_t>
+void search(index_t const& index, queries_t const& queries, delegate_t&& delegate, size_t /*BatchSize*/ = 32) {
+    for (auto const& h : search_bulk(index, queries)) delegate(static_cast<size_t>(h.qidx), detail::make_left_cursor(index, h));
+}
+
+// SearchNoErrors.h:13-26: single query, returns the cursor (possibly empty)
+template <typename index_t, Sequence query_t>
+auto search(index_t const& index, query_t const& query) {
+    std::array<std::span<uint8_t const>, 1> one;
+    std::vector<uint8_t> copy(std::ranges::size(query));
+    std::ranges::copy(query, copy.begin());
+    one[0] = copy;
+    auto hits = search_bulk(index, one);
+    fmb_hit h{0, 0, 0, 0, copy.size(), 0};
+    if (!hits.empty()) h = hits[0];
+    return detail::make_left_cursor(index, h);
+}
+
+}  // namespace search_no_errors
+
+// =====================================================================================================================
+namespace search_ng26 {
+
+template <bool Edit = true, typename index_t, Sequences queries_t, detail::SchemeLike scheme_t>
+std::vector<fmb_hit> search_bulk(index_t const& index, queries_t const& queries, scheme_t const& scheme,
+                                 std::vector<size_t> const& partition, fmb_stats* stats = nullptr) {
+    static_assert(detail::is_bidirectional<index_t>, "search schemes need a bidirectional index (extendRight)");
+    auto fs = detail::flatten(scheme, partition);
+    auto flat = flatten(queries);
+    auto q = detail::upload(index.handle(), flat);
+    fmb_results* r{};
+    check(fmb_search_scheme(index.handle(), q.get(), Edit ? 1 : 0, fs.n_searches, fs.n_parts, fs.pi.data(), fs.l.data(), fs.u.data(), fs.partition.data(), &r));
+    detail::ResultsHandle res{r};
+    if (stats) check(fmb_results_get_stats(r, stats));
+    auto hits = detail::fetch_hits(r);
+    detail::sort_hits(hits);
+    return hits;
+}
+
+// SearchNg26.h:426-433: explicit scheme + partition
+template <bool Edit = true, typename index_t, Sequences queries_t, detail::SchemeLike scheme_t, typename delegate_t>
+void search(index_t const& index, queries_t&& queries, scheme_t const& scheme, std::vector<size_t> const& partition,
+            delegate_t&& delegate, size_t n = std::numeric_limits<size_t>::max()) {
+    if (n != std::numeric_limits<size_t>::max()) throw std::runtime_error("fmb200: the hit limit n of search_ng26::search is not supported");
+    for (auto const& h : search_bulk<Edit>(index, queries, scheme, partition)) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
+}
+
+// SearchNg26.h:436-444: scheme selected per query length (h2 with maxErrors+2 parts, CachedSearchScheme.h:15-36).
+// Queries are grouped by length; every group is one device call.
+template <bool Edit = true, typename index_t, Sequences queries_t>
+std::vector<fmb_hit> search_bulk(index_t const& index, queries_t const& queries, size_t maxErrors) {
+    std::map<size_t, std::vector<size_t>> by_len;
+    size_t qidx = 0;
+    for (auto const& q : queries) by_len[std::ranges::size(q)].push_back(qidx++);
+    std::vector<fmb_hit> all;
+    for (auto const& [len, ids] : by_len) {
+        if (len == 0) continue;      // an empty query has no scheme (createUniformPartition asserts totalSum > 0)
+        if (len < maxErrors + (len == 2 ? 1 : 2)) throw std::runtime_error("fmb200: query shorter than the number of scheme parts");
+        auto [scheme, partition] = search_scheme::facadeScheme<Edit>(maxErrors, len);
+        std::vector<std::span<uint8_t const>> group;
+        std::vector<std::vector<uint8_t>> store;
+        store.reserve(ids.size());
+        for (auto id : ids) {
+            auto const& q = queries[id];
+            store.emplace_back(std::ranges::size(q));
+            std::ranges::copy(q, store.back().begin());
+            group.emplace_back(store.back());
+        }
+        auto hits = search_bulk<Edit>(index, group, scheme, partition);
+        for (auto& h : hits) h.qidx = ids[h.qidx];
+        all.insert(all.end(), hits.begin(), hits.end());
+    }
+    detail::sort_hits(all);
+    return all;
+}
+template <bool Edit = true, typename index_t, Sequences queries_t, typename delegate_t>
+void search(index_t const& index, queries_t&& queries, size_t maxErrors, delegate_t&& delegate, size_t n = std::numeric_limits<size_t>::max()) {
+    if (n != std::numeric_limits<size_t>::max()) throw std::runtime_error("fmb200: the hit limit n of search_ng26::search is not supported");
+    for (auto const& h : search_bulk<Edit>(index, queries, maxErrors)) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
+}
+
+}  // namespace search_ng26
+
+// =====================================================================================================================
+namespace search_backtracking {
+
+template <typename index_t, Sequences queries_t>
+std::vector<fmb_hit> search_bulk(index_t const& index, queries_t const& queries, size_t maxError) {
+    // the device kernel takes batches of equal length; group like search_ng26 above
+    std::map<size_t, std::vector<size_t>> by_len;
+    size_t qidx = 0;
+    for (auto const& q : queries) by_len[std::ranges::size(q)].push_back(qidx++);
+    std::vector<fmb_hit> all;
+    for (auto const& [len, ids] : by_len) {
+        if (len == 0) continue;
+        FlatSequences flat;
+        flat.symbols.reserve(len * ids.size());
+        for (auto id : ids) {
+            for (auto c : queries[id]) flat.symbols.push_back(static_cast<uint8_t>(c));
+            flat.offsets.push_back(flat.symbols.size());
+        }
+        auto q = detail::upload(index.handle(), flat);
+        fmb_results* r{};
+        check(fmb_search_backtracking(index.handle(), q.get(), static_cast<uint32_t>(maxError), &r));
+        detail::ResultsHandle res{r};
+        auto hits = detail::fetch_hits(r);
+        for (auto& h : hits) h.qidx = ids[h.qidx];
+        all.insert(all.end(), hits.begin(), hits.end());
+    }
+    detail::sort_hits(all);
+    return all;
+}
+
+// Backtracking.h:85-98
+template <typename index_t, Sequences queries_t, typename delegate_t>
+void search(index_t const& index, queries_t&& queries, size_t maxError, delegate_t&& delegate) {
+    for (auto const& h : search_bulk(index, queries, maxError)) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
+}
+
+}  // namespace search_backtracking
+
+// =====================================================================================================================
+// locate.h:15-57: range over the (seqId, pos, offset) entries of every row of a cursor.  All rows are located by
+// one kernel launch when the range is constructed.
+template <typename index_t, typename cursor_t>
+struct LocateLinear {
+    using LEntry = std::tuple<uint32_t, uint32_t, size_t>;
+    index_t const& index;
+    cursor_t cursor;
+    std::vector<LEntry> entries;
+    LocateLinear(index_t const& ix, cursor_t const& cur) : index{ix}, cursor{cur} {
+        std::vector<uint64_t> rows(cur.len);
+        for (size_t i = 0; i < cur.len; ++i) rows[i] = cur.lb + i;
+        entries = fmb200::locate_rows(ix, rows);
+    }
+    auto begin() const { return entries.begin(); }
+    auto end() const { return entries.end(); }
+};
+template <typename index_t, typename cursor_t>
+LocateLinear(index_t const&, cursor_t const&) -> LocateLinear<index_t, cursor_t>;
+
+// =====================================================================================================================
+// search/search.h:26-35: k == 0 -> exact search, else search_ng26 with the h2 scheme
+template <bool EditDistance, typename index_t, Sequences queries_t, typename delegate_t>
+void search(index_t const& index, queries_t const& queries, size_t errors, delegate_t&& delegate) {
+    if (errors == 0) {
+        for (auto const& h : search_no_errors::search_bulk(index, queries)) {
+            if constexpr (detail::is_bidirectional<index_t>) {
+                delegate(static_cast<size_t>(h.qidx), detail::make_left_cursor(index, h), size_t{0});
+            } else {
+                delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), size_t{0});
+            }
+        }
+    } else {
+        search_ng26::search<EditDistance>(index, queries, errors, std::forward<delegate_t>(delegate));
+    }
+}
+
+// search/search.h:47-75: search + locate, reportFunc(qidx, seqId, pos + offset, errors).  One device pass
+// (fmb_search_and_locate for explicit schemes is used by search_and_locate_bulk below).
+template <typename index_t, Sequences queries_t, typename delegate_t>
+struct Search {
+    index_t const& index;
+    queries_t const& queries;
+    bool editDistance{true};
+    size_t errors{0};
+    std::optional<size_t> maxResults{};
+    delegate_t const& reportFunc;
+    void operator()() {
+        if (maxResults) throw std::runtime_error("fmb200: Search::maxResults (search_n) is not supported");
+        std::vector<fmb_hit> hits;
+        if (errors == 0) hits = search_no_errors::search_bulk(index, queries);
+        else hits = editDistance ? search_ng26::search_bulk<true>(index, queries, errors) : search_ng26::search_bulk<false>(index, queries, errors);
+        // locate all rows of all hits in one launch
+        std::vector<uint64_t> rows;
+        for (auto const& h : hits)
+            for (uint64_t i = 0; i < h.len; ++i) rows.push_back(h.lb + i);
+        auto entries = locate_rows(index, rows);
+        size_t at = 0;
+        for (auto const& h : hits)
+            for (uint64_t i = 0; i < h.len; ++i, ++at) {
+                auto [sid, spos, offset] = entries[at];
+                reportFunc(static_cast<size_t>(h.qidx), sid, spos + offset, static_cast<size_t>(h.e));
+            }
+    }
+};
+template <typename index_t, typename queries_t, typename delegate_t>
+Search(index_t const&, queries_t const&, bool, size_t, std::optional<size_t>, delegate_t const&) -> Search<index_t, queries_t, delegate_t>;
+
+// Bulk one-call path (fmb_search_and_locate): host queries in, located rows (qidx, seq, pos + offset, e) out, upload /
+// kernels / download pipelined over query chunks.  scheme == nullptr selects exact search.
+template <typename index_t, Sequences queries_t, detail::SchemeLike scheme_t = search_scheme::Scheme>
+std::vector<fmb_loc32> search_and_locate_bulk(index_t const& index, queries_t const& queries, bool edit = false,
+                                              scheme_t const* scheme = nullptr, std::vector<size_t> const* partition = nullptr,
+                                              fmb_stats* stats = nullptr) {
+    auto flat = flatten(queries);
+    detail::FlatScheme fs;
+    if (scheme) fs = detail::flatten(*scheme, *partition);
+    std::vector<fmb_loc32> out(std::max<size_t>(flat.size() * 2, 1024));
+    for (;;) {
+        uint64_t n_out = 0;
+        int rc = fmb_search_and_locate(index.handle(), flat.symbols.data(), flat.offsets.data(), flat.size(), edit ? 1 : 0, fs.n_searches, fs.n_parts,
+                                       fs.pi.data(), fs.l.data(), fs.u.data(), fs.partition.data(), out.data(), out.size(), &n_out, stats);
+        if (rc == FMB_EOVERFLOW && n_out > out.size()) {
+            out.resize(n_out);
+            continue;
+        }
+        check(rc);
+        out.resize(n_out);
+        return out;
+    }
+}
+
+}  // namespace fmb200

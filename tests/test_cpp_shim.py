@@ -1,0 +1,95 @@
+"""C++ host side (include/fmb200/*.hpp): the reference's search API over the C-ABI.
+
+CPU part: the headers compile as C++20 and the test binary fails loudly without a device (no CPU fallback).
+GPU part: tests/cpp/shim_test (shim vs the oracle) and tests/cpp/dropin_test (the reference's own fmc:: calls vs the
+fmb200:: calls on fmb200::attach(index), same delegate code; prebuilt here because it needs /root/reference)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "_bin")
+
+
+def _build():
+    import fmb200  # noqa: F401  builds libfmb200.so if needed
+    from fmb200 import build as b
+    b.build()
+    subprocess.run(["bash", os.path.join(ROOT, "tests", "cpp", "build.sh")], check=True, capture_output=True)
+
+
+def _binary(name):
+    path = os.path.join(BIN, name)
+    if not os.path.exists(path) and name == "shim_test":
+        _build()
+    return path
+
+
+def test_headers_compile_standalone(tmp_path):
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "fmb200/fmb200.hpp"\nint main() { return fmb200::search_scheme::generator::optimum(0, 2).size() == 3 ? 0 : 1; }\n')
+    subprocess.run(["g++", "-std=c++20", "-fsyntax-only", "-Wall", "-Wno-comment", "-I", os.path.join(ROOT, "include"), str(src)], check=True)
+
+
+def test_scheme_generators_match_python_tables(tmp_path):
+    """search_scheme.hpp (C++) against schemes.py, which is pinned to the reference's generators by tests/golden"""
+    from fmb200 import schemes
+    src = tmp_path / "g.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include "fmb200/search_scheme.hpp"
+namespace ss = fmb200::search_scheme;
+static void dump(const char* name, ss::Scheme const& s) {
+    std::printf("%s", name);
+    for (auto const& x : s) { std::printf(" |"); for (auto v : x.pi) std::printf(" %zu", v); std::printf(" ;"); for (auto v : x.l) std::printf(" %zu", v); std::printf(" ;"); for (auto v : x.u) std::printf(" %zu", v); }
+    std::printf("\n");
+}
+int main() {
+    for (size_t k = 0; k <= 3; ++k) for (size_t n = k + 1; n <= k + 3; ++n) { char b[64]; std::snprintf(b, 64, "h2_%zu_%zu", n, k); dump(b, ss::generator::h2(n, 0, k)); std::snprintf(b, 64, "h2h_%zu_%zu", n, k); dump(b, ss::limitToHamming(ss::generator::h2(n, 0, k))); }
+    dump("opt_0_1", ss::generator::optimum(0, 1)); dump("opt_0_2", ss::generator::optimum(0, 2)); dump("opt_1_2", ss::generator::optimum(1, 2));
+    dump("bt_4_1_2", ss::generator::backtracking(4, 1, 2));
+}
+''')
+    exe = tmp_path / "g"
+    subprocess.run(["g++", "-std=c++20", "-O1", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+
+    def fmt(name, sch):
+        pi, l, u = sch
+        parts = [" |" + "".join(f" {v}" for v in pi[s]) + " ;" + "".join(f" {v}" for v in l[s]) + " ;" + "".join(f" {v}" for v in u[s]) for s in range(pi.shape[0])]
+        return name + "".join(parts)
+
+    exp = []
+    for k in range(4):
+        for n in range(k + 1, k + 4):
+            exp.append(fmt(f"h2_{n}_{k}", schemes.h2(n, 0, k)))
+            exp.append(fmt(f"h2h_{n}_{k}", schemes.limit_to_hamming(schemes.h2(n, 0, k))))
+    exp += [fmt("opt_0_1", schemes.optimum(0, 1)), fmt("opt_0_2", schemes.optimum(0, 2)), fmt("opt_1_2", schemes.optimum(1, 2)),
+            fmt("bt_4_1_2", schemes.backtracking(4, 1, 2))]
+    assert out.strip().splitlines() == exp
+
+
+def test_shim_binary_fails_loudly_without_device():
+    import fmb200
+    if fmb200.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    r = subprocess.run([_binary("shim_test")], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_shim_against_oracle(gpu):
+    r = subprocess.run([_binary("shim_test")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failed" in r.stdout
+
+
+@pytest.mark.gpu
+def test_dropin_against_reference_headers(gpu):
+    path = _binary("dropin_test")
+    if not os.path.exists(path):
+        pytest.skip("tests/cpp/_bin/dropin_test is prebuilt where /root/reference exists (tests/cpp/build.sh)")
+    r = subprocess.run([path], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failed" in r.stdout

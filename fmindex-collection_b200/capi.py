@@ -21,7 +21,8 @@ class IndexInfo(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("extensions", C.c_uint64), ("occ_lookups", C.c_uint64), ("lf_steps", C.c_uint64),
-                ("frontier_peak", C.c_uint64), ("kernel_ms", C.c_double), ("main_kernel_ms", C.c_double)]
+                ("frontier_peak", C.c_uint64), ("kernel_ms", C.c_double), ("main_kernel_ms", C.c_double),
+                ("line_requests", C.c_uint64)]
 
 
 class FmbError(RuntimeError):
@@ -45,7 +46,7 @@ SYMBOLS = [
     "fmb_results_count", "fmb_results_kind", "fmb_results_fetch_hits", "fmb_results_fetch_locs", "fmb_results_fetch_locs32",
     "fmb_results_get_stats", "fmb_results_destroy",
     "fmb_search_and_locate",
-    "fmb_synth_text_device", "fmb_synth_reads_device", "fmb_index_set_stream", "fmb_kernel_launch_count", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
+    "fmb_index_set_exact_mode", "fmb_synth_text_device", "fmb_synth_reads_device", "fmb_index_set_stream", "fmb_kernel_launch_count", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
 ]
 
 
@@ -165,6 +166,10 @@ class Index:
         sp = np.zeros(i.n_samples, dtype=np.uint32)
         _check(lib().fmb_index_export(self.h, _ptr(bwt), _ptr(rev), _ptr(bm), _ptr(sq), _ptr(sp)))
         return bwt, rev, bm, sq, sp
+
+    def set_exact_mode(self, mode):
+        """0 = auto (two-symbol steps when available), 1 = one-symbol kernel (fills the algorithmic counters), 2 = two-symbol"""
+        _check(lib().fmb_index_set_exact_mode(self.h, C.c_int(mode)))
 
     # String_c
     def symbol(self, idx, dir=0):

@@ -57,6 +57,10 @@ struct OccDna {
         return b;
     }
 
+    // cnt[k] without dynamic indexing (a runtime index would push the block into local memory)
+    static __device__ __forceinline__ uint32_t cnt_of(const DnaBlock& b, uint32_t k) {
+        return (k & 2) ? ((k & 1) ? b.cnt[3] : b.cnt[2]) : ((k & 1) ? b.cnt[1] : b.cnt[0]);
+    }
     // bit r set <=> row r of the block holds code k (k = symbol-1; delimiter rows alias k = 0)
     static __device__ __forceinline__ uint64_t match_mask(const DnaBlock& b, uint32_t k) {
         uint64_t m0 = (k & 1) ? b.p0 : ~b.p0;
@@ -87,7 +91,7 @@ struct OccDna {
     __device__ __forceinline__ uint32_t rank(const DnaBlock& b, row_t row, uint32_t symb) const {
         if (symb == 0) return delims_below(b, row);
         uint32_t k = symb - 1;
-        uint32_t r = b.cnt[k] + __popcll(match_mask(b, k) & low_mask(row & 63));
+        uint32_t r = cnt_of(b, k) + __popcll(match_mask(b, k) & low_mask(row & 63));
         if (k == 0) r -= delims_below(b, row) - delims_before_block(b, row >> 6);
         return r;
     }
@@ -118,6 +122,79 @@ struct OccDna {
         pr = prefix_rank(b, row, symb);
     }
 };
+
+// =========================================================================================================
+// DNA two-symbol layout (OccDna2): one 128-byte line per 128 BWT rows, resolved by a group of 4 lanes
+// =========================================================================================================
+// Why: ncu shows that every random 32-byte lookup moves a whole 128-byte DRAM line (profiles/r01_ncu_exact_v1.txt:
+// dram__bytes_read = 116 B per lookup at 5.3 TB/s), and the request rate of random lines saturates at ~38 G/s
+// whether 16, 32 or 128 bytes of the line are used (profiles/r01_gather_*.txt).  So a lookup should use the whole
+// line it pays for: this block answers rank queries over PAIRS of symbols -- one line fetch advances a query by two
+// symbols.  (The reference has the same idea as an experimental `KStep` path, search/SearchNoErrors.h:46-58.)
+//
+// pair code of row i = (y-1)*4 + (x-1) with y = T[SA[i]-1] (= BWT[i]) and x = T[SA[i]-2]; rows where x or y is the
+// delimiter ("special" rows, two per sequence) are stored as code 0 and listed in a sorted side array.
+// The line is four 32-byte quarters; quarter k (fetched by lane k of the group with one LDG.256):
+//     u32 cnt[4]    absolute # rows before the block with code 4k .. 4k+3 (special rows count as code 0)
+//     u32 plane[4]  bit r of plane[j] = bit j of the code of row 128*b + 32*k + r
+// rank2(row, code) = sum over the 4 lanes of (popc(match(code) & rows-below-mask) + own counter) -> 2 SHFL.XOR.
+struct Occ2View {
+    const uint4* lines;          // 8 uint4 per block; nullptr when the table was not built
+    const uint32_t* specials;    // sorted special rows, padded with 0xFFFFFFFF
+    uint32_t n_specials;
+    uint32_t s0, s1;             // specials[0], specials[1] (register copies; single-sequence case)
+    uint32_t C2[16];             // C2[code] = first row of the interval of the two-symbol pattern "x y"
+    // k-mer table: (lb, len) of every pattern of kmer_k symbols over {1..4}; entry index = sum (s_p - 1) * 4^p with
+    // s_0 the FIRST symbol of the pattern (the order of the 2-bit packed query stream).  Replaces the first kmer_k backward steps (the wide-interval phase, two
+    // lines per step) by one lookup.  kmer_k = 0: no table.
+    const uint2* kmer;
+    uint32_t kmer_k;
+    // LF^16 jump table: jump[row] = {LF^16(row), the 16 symbols preceding the suffix of `row` as 2-bit codes (symbol-1),
+    // farthest symbol in the low bits = text order}; .x = 0xFFFFFFFF when one of the 16 symbols is a delimiter.  Once an interval is a
+    // single row, 16 backward steps are one 8-byte lookup: compare the 32-bit symbol word with the query, follow .x.
+    const uint2* jump;
+};
+constexpr uint32_t kJumpInvalid = 0xFFFFFFFFu;
+
+struct Quarter {
+    uint32_t cnt[4];
+    uint32_t plane[4];
+};
+
+__device__ __forceinline__ Quarter load_quarter(const Occ2View& o, uint32_t blk, uint32_t sub) {
+    Quarter q;
+    const uint4* p = o.lines + ((size_t)blk * 8 + sub * 2);
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(q.cnt[0]), "=r"(q.cnt[1]), "=r"(q.cnt[2]), "=r"(q.cnt[3]), "=r"(q.plane[0]), "=r"(q.plane[1]),
+                   "=r"(q.plane[2]), "=r"(q.plane[3])
+                 : "l"(p));
+    return q;
+}
+// this lane's share of rank2(row, code): rows of quarter `sub` below `row` that hold `code`, plus the block counter
+// when this quarter owns it
+__device__ __forceinline__ uint32_t rank2_part(const Quarter& q, uint32_t sub, uint32_t row, uint32_t code) {
+    uint32_t m = ((code & 1) ? q.plane[0] : ~q.plane[0]) & ((code & 2) ? q.plane[1] : ~q.plane[1]) &
+                 ((code & 4) ? q.plane[2] : ~q.plane[2]) & ((code & 8) ? q.plane[3] : ~q.plane[3]);
+    int rel = (int)(row & 127u) - (int)(sub * 32u);
+    uint32_t mask = rel <= 0 ? 0u : (rel >= 32 ? 0xFFFFFFFFu : ((1u << rel) - 1u));
+    uint32_t c = (code & 2) ? ((code & 1) ? q.cnt[3] : q.cnt[2]) : ((code & 1) ? q.cnt[1] : q.cnt[0]);
+    return __popc(m & mask) + (((code >> 2) == sub) ? c : 0u);
+}
+// # special rows < row (they are stored as code 0 and must not count as the pair "1 1")
+__device__ __forceinline__ uint32_t specials_below(const Occ2View& o, uint32_t row) {
+    if (o.n_specials <= 2) return (o.s0 < row ? 1u : 0u) + (o.s1 < row ? 1u : 0u);
+    uint32_t lo = 0, hi = o.n_specials;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(o.specials + mid) < row) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t group_sum4(uint32_t v, uint32_t gmask) {
+    v += __shfl_xor_sync(gmask, v, 1);
+    v += __shfl_xor_sync(gmask, v, 2);
+    return v;
+}
 
 // =========================================================================================================
 // generic layout

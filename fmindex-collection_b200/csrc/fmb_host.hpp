@@ -94,9 +94,20 @@ struct fmb_index {
     fmb::DevBuf<uint2> samples;
     uint64_t n_samples = 0;
     uint64_t C[65] = {0};
+    // two-symbol table (OccDna2), sigma <= 5 only
+    fmb::DevBuf<uint4> occ2[2];
+    fmb::DevBuf<uint32_t> specials[2];
+    uint32_t n_specials[2] = {0, 0};
+    uint32_t special01[2][2] = {{0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu}};
+    uint32_t C2[2][16] = {};
+    fmb::DevBuf<uint2> jump[2];          // LF^16 jump tables
+    fmb::DevBuf<uint2> kmer;             // k-mer interval table of direction 0
+    uint32_t kmer_k = 0;
+    int exact_mode = 0;                  // FMB_EXACT_*
 
     fmb::IndexView<fmb::OccDna> view_dna() const;
     fmb::IndexView<fmb::OccGen> view_gen() const;
+    fmb::Occ2View view_occ2(int dir) const;
     uint64_t device_bytes() const;
 };
 
@@ -115,6 +126,8 @@ struct fmb_queries {
     uint32_t max_len = 0, min_len = 0;
     fmb::DevBuf<uint8_t> symbols;     // padded to a multiple of 16 bytes
     fmb::DevBuf<uint64_t> offsets;    // nq + 1
+    fmb::DevBuf<uint32_t> packed;     // sigma <= 5: 2-bit codes (symbol-1), 16 per word (+2 words of padding)
+    fmb::DevBuf<uint8_t> flags;       // sigma <= 5: 1 = query holds a symbol without 2-bit code (0 or >= sigma)
 };
 
 struct fmb_results {

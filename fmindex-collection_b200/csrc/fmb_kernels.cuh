@@ -215,7 +215,7 @@ __device__ __forceinline__ uint32_t chunk_byte(const uint4& v, uint32_t i) {
 }
 
 template <class OCC, bool COUNT>
-__global__ void __launch_bounds__(256) exact_search_kernel(IndexView<OCC> ix, const uint8_t* __restrict__ qsym,
+__global__ void __launch_bounds__(256) exact_search_kernel(const __grid_constant__ IndexView<OCC> ix, const uint8_t* __restrict__ qsym,
                                                            const uint64_t* __restrict__ qoff, uint32_t nq,
                                                            uint32_t* __restrict__ out_lb, uint32_t* __restrict__ out_len,
                                                            unsigned long long* __restrict__ counters) {
@@ -255,6 +255,274 @@ __global__ void __launch_bounds__(256) exact_search_kernel(IndexView<OCC> ix, co
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K1b: two-symbol table (OccDna2, fmb_device.cuh).  Built from the one-symbol table itself:
+//      y = BWT[i],  x = BWT[LF(i)]  with LF(i) = C[y] + rank(i, y);  code = (y-1)*4 + (x-1), 0xFF = special row.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pair_codes_kernel(const __grid_constant__ IndexView<OccDna> ix, int dir, uint8_t* __restrict__ codes) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= ix.n) return;
+    const OccDna& occ = ix.occ[dir];
+    DnaBlock b = occ.load((uint32_t)(i >> 6));
+    uint32_t y = occ.symbol(b, (row_t)i);
+    uint8_t code = 0xFF;
+    if (y != 0) {
+        row_t j = ix.C[y] + occ.rank(b, (row_t)i, y);
+        DnaBlock b2 = occ.load(j >> 6);
+        uint32_t x = occ.symbol(b2, j);
+        if (x != 0) code = (uint8_t)((y - 1) * 4 + (x - 1));
+    }
+    codes[i] = code;
+}
+
+struct Cnt16 {
+    uint32_t c[16];
+};
+struct Cnt16Add {
+    __host__ __device__ Cnt16 operator()(const Cnt16& a, const Cnt16& b) const {
+        Cnt16 r;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r.c[i] = a.c[i] + b.c[i];
+        return r;
+    }
+};
+
+// one thread per quarter (32 rows): planes + local counts of its rows
+__global__ void __launch_bounds__(256) pack_pairs_kernel(const uint8_t* __restrict__ codes, uint64_t n, uint64_t nblocks,
+                                                         uint4* __restrict__ lines, uint32_t* __restrict__ qcounts /*[nblocks*4][16]*/,
+                                                         uint32_t* __restrict__ special_count /*[nblocks*4 + 1]*/) {
+    uint64_t qd = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;      // quarter index
+    if (qd > nblocks * 4) return;
+    if (qd == nblocks * 4) { special_count[qd] = 0; return; }
+    uint64_t base = qd * 32;
+    uint32_t pl[4] = {0, 0, 0, 0};
+    uint32_t cnt[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cnt[i] = 0;
+    uint32_t ns = 0;
+    for (uint32_t r = 0; r < 32 && base + r < n; ++r) {
+        uint32_t c = codes[base + r];
+        if (c == 0xFF) { ++ns; c = 0; }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cnt[i] += (c == (uint32_t)i);
+        pl[0] |= (c & 1) << r;
+        pl[1] |= ((c >> 1) & 1) << r;
+        pl[2] |= ((c >> 2) & 1) << r;
+        pl[3] |= ((c >> 3) & 1) << r;
+    }
+    lines[qd * 2 + 1] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) qcounts[qd * 16 + i] = cnt[i];
+    special_count[qd] = ns;
+}
+// per block: sum of its four quarters
+__global__ void block_counts_kernel(const uint32_t* __restrict__ qcounts, uint64_t nblocks, Cnt16* __restrict__ bcounts) {
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= nblocks * 16) return;
+    uint64_t blk = t >> 4;
+    uint32_t i = t & 15;
+    const uint32_t* q = qcounts + blk * 64;
+    bcounts[blk].c[i] = q[i] + q[16 + i] + q[32 + i] + q[48 + i];
+}
+// after the exclusive scan: quarter k of block b receives the absolute counters 4k .. 4k+3
+__global__ void store_pair_counts_kernel(uint4* __restrict__ lines, const Cnt16* __restrict__ bcounts, uint64_t nblocks) {
+    uint64_t qd = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (qd >= nblocks * 4) return;
+    const Cnt16& c = bcounts[qd >> 2];
+    uint32_t k = (qd & 3) * 4;
+    lines[qd * 2] = make_uint4(c.c[k], c.c[k + 1], c.c[k + 2], c.c[k + 3]);
+}
+__global__ void scatter_specials_kernel(const uint8_t* __restrict__ codes, uint64_t n, uint64_t nquarters, const uint32_t* __restrict__ start,
+                                        uint32_t* __restrict__ specials) {
+    uint64_t qd = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (qd >= nquarters) return;
+    uint32_t a = start[qd], b = start[qd + 1];
+    if (a == b) return;
+    uint64_t base = qd * 32;
+    for (uint32_t r = 0; r < 32 && base + r < n; ++r)
+        if (codes[base + r] == 0xFF) specials[a++] = (uint32_t)(base + r);
+}
+
+// (lb, len) of every k-mer: thread i searches the pattern whose symbol at position p (from the left) is ((i >> 2p) & 3) + 1,
+// i.e. the index is the 2-bit packed pattern in the order the packed query stream stores it
+__global__ void __launch_bounds__(256) kmer_table_kernel(const __grid_constant__ IndexView<OccDna> ix, uint32_t k, uint64_t count, uint2* __restrict__ out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    row_t lb = 0, len = ix.n;
+    uint32_t dummy = 0;
+    for (uint32_t p = k; p-- > 0 && len;) extend_left_uni(ix, lb, len, (uint32_t)((i >> (2 * p)) & 3) + 1, dummy);
+    out[i] = make_uint2(lb, len);
+}
+
+// 2-bit packing of the query symbols (symbol-1, 16 symbols per word, first symbol in the low bits).  Queries holding a
+// symbol that has no 2-bit code (0 or >= sigma) are flagged and take the byte path of the search kernel.
+__device__ __forceinline__ uint32_t pack4(uint32_t w, uint32_t sigma, bool& bad) {
+    // code = (byte - 1) & 3 = (byte + 3) & 3, added per byte without carries into the neighbour (which may belong to
+    // another query): bit 7 is masked off first, it does not reach the two low bits
+    uint32_t v = ((w & 0x7F7F7F7Fu) + 0x03030303u) & 0x03030303u;
+    const uint32_t lim = sigma - 1;                    // valid bytes: 1 .. sigma-1  <=>  (byte - 1) < sigma - 1 (unsigned)
+    bad = bad || ((w & 0xFF) - 1u >= lim) || (((w >> 8) & 0xFF) - 1u >= lim) || (((w >> 16) & 0xFF) - 1u >= lim) || ((w >> 24) - 1u >= lim);
+    return (v * 0x00041041u >> 18) & 0xFFu;            // gathers the four 2-bit fields (disjoint partial products)
+}
+__global__ void __launch_bounds__(256) pack_queries_kernel(const uint8_t* __restrict__ qsym, uint64_t total, const uint64_t* __restrict__ qoff,
+                                                           uint64_t nq, uint32_t sigma, uint32_t* __restrict__ packed, uint64_t words,
+                                                           uint8_t* __restrict__ qflags) {
+    uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    uint4 c = __ldg(reinterpret_cast<const uint4*>(qsym) + w);         // the symbol buffer is padded with 0xFF
+    bool bad = false;
+    uint32_t out = pack4(c.x, sigma, bad) | (pack4(c.y, sigma, bad) << 8) | (pack4(c.z, sigma, bad) << 16) | (pack4(c.w, sigma, bad) << 24);
+    packed[w] = out;
+    if (bad) {
+        // rare: flag every query owning an uncodable symbol of this word
+        uint32_t words4[4] = {c.x, c.y, c.z, c.w};
+        for (uint32_t i = 0; i < 16; ++i) {
+            uint64_t at = w * 16 + i;
+            if (at >= total) break;
+            uint32_t b = (words4[i >> 2] >> (8 * (i & 3))) & 0xFF;
+            if (b >= 1 && b < sigma) continue;
+            uint64_t lo = 0, hi = nq;                                   // last query with qoff[q] <= at
+            while (hi - lo > 1) {
+                uint64_t mid = (lo + hi) >> 1;
+                if (qoff[mid] <= at) lo = mid; else hi = mid;
+            }
+            qflags[lo] = 1;
+        }
+    }
+}
+
+// LF^16 jump table by pointer doubling: J1[row] = {LF(row), BWT[row]-1};  J2k[row] = {J_k[J_k[row].x].x, syms << 2k | syms'}
+// (the farthest symbol ends up in the low bits: the order of the 2-bit packed query stream)
+__global__ void __launch_bounds__(256) jump_init_kernel(const __grid_constant__ IndexView<OccDna> ix, int dir, uint2* __restrict__ out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= ix.n) return;
+    const OccDna& occ = ix.occ[dir];
+    DnaBlock b = occ.load((uint32_t)(i >> 6));
+    uint32_t y = occ.symbol(b, (row_t)i);
+    out[i] = y ? make_uint2(ix.C[y] + occ.rank(b, (row_t)i, y), y - 1) : make_uint2(kJumpInvalid, 0);
+}
+__global__ void __launch_bounds__(256) jump_double_kernel(const uint2* __restrict__ in, uint2* __restrict__ out, uint64_t n, uint32_t shift) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint2 a = in[i];
+    uint2 r = make_uint2(kJumpInvalid, 0);
+    if (a.x != kJumpInvalid) {
+        uint2 b = __ldg(in + a.x);
+        if (b.x != kJumpInvalid) r = make_uint2(b.x, (a.y << shift) | b.y);
+    }
+    out[i] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2b: exact backward search with two-symbol steps.  A group of 4 lanes owns one query: every lane fetches one
+// 32-byte quarter of the 128-byte line (ONE request per line for the memory system), computes its share of the
+// two ranks and the group adds them up with 2 SHFL.XOR each.  All 4 lanes keep the (identical) query state, so no
+// broadcast is needed.  Pairs containing the delimiter symbol 0 and the odd leading symbol take one-symbol steps on
+// the 32-byte table (all lanes of the group read the same sector = one request).
+// Results are identical to exact_search_kernel: the final (lb, len) of a pattern does not depend on the step width.
+// ---------------------------------------------------------------------------------------------------------
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(256, MINB) exact_search2_kernel(const __grid_constant__ IndexView<OccDna> ix, const __grid_constant__ Occ2View o2,
+                                                                  const uint8_t* __restrict__ qsym, const uint32_t* __restrict__ qpk,
+                                                                  const uint8_t* __restrict__ qflags, const uint64_t* __restrict__ qoff, uint32_t nq,
+                                                                  uint32_t* __restrict__ out_lb, uint32_t* __restrict__ out_len,
+                                                                  unsigned long long* __restrict__ counters) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = t >> 2;
+    const uint32_t sub = threadIdx.x & 3;
+    const uint32_t gmask = 0xFu << (threadIdx.x & 28);
+    uint32_t lines = 0;
+    if (q < nq) {
+        const uint64_t off = qoff[q];
+        const uint32_t L = (uint32_t)(qoff[q + 1] - off);
+        row_t lb = 0, len = ix.n;
+        uint32_t dummy = 0;
+        if (qflags[q]) {
+            // byte path: the query holds a delimiter or an out-of-range symbol -> one-symbol steps, reference semantics
+            for (uint32_t pos = L; pos-- > 0 && len;) {
+                uint32_t c = __ldg(qsym + off + pos);
+                if (c >= ix.sigma) { len = 0; break; }
+                extend_left_uni(ix, lb, len, c, dummy);
+                lines += 1;
+            }
+        } else {
+            // 2-bit packed query, read through a cached 64-bit window
+            uint32_t cw = 0xFFFFFFFFu, wlo = 0, whi = 0;
+            auto field = [&](uint32_t sympos, uint32_t nbits) -> uint32_t {      // symbols [sympos, sympos + nbits/2)
+                uint64_t bit = 2 * (off + sympos);
+                uint32_t wi = (uint32_t)(bit >> 5);
+                if (wi != cw) {
+                    cw = wi;
+                    wlo = __ldg(qpk + wi);
+                    whi = __ldg(qpk + wi + 1);
+                }
+                uint32_t v = __funnelshift_r(wlo, whi, (uint32_t)bit & 31u);
+                return nbits >= 32 ? v : (v & ((1u << nbits) - 1u));
+            };
+            uint32_t pos = L;
+            if (o2.kmer_k && L >= o2.kmer_k) {
+                // the first kmer_k symbols in one lookup
+                uint2 e = __ldg(o2.kmer + field(L - o2.kmer_k, 2 * o2.kmer_k));
+                lb = e.x;
+                len = e.y;
+                pos = L - o2.kmer_k;
+                lines += 1;
+            }
+            while (pos > 0 && len > 0) {
+                if (len == 1 && pos >= 16 && o2.jump) {
+                    // single-row interval: 16 symbols per lookup through the LF^16 jump table
+                    uint2 e = __ldg(o2.jump + lb);
+                    lines += 1;
+                    if (e.x != kJumpInvalid) {
+                        if (e.y != field(pos - 16, 32)) { len = 0; break; }
+                        lb = e.x;
+                        pos -= 16;
+                        continue;
+                    }
+                }
+                if (pos == 1) {
+                    extend_left_uni(ix, lb, len, field(0, 2) + 1, dummy);
+                    lines += 1;
+                    break;
+                }
+                const uint32_t code = field(pos - 2, 4);          // (y-1)*4 + (x-1), x = query[pos-2], y = query[pos-1]
+                const row_t hi = lb + len;
+                const uint32_t b0 = lb >> 7, b1 = hi >> 7;
+                Quarter q0 = load_quarter(o2, b0, sub);
+                uint32_t p0, p1;
+                if (b1 == b0) {
+                    p0 = rank2_part(q0, sub, lb, code);
+                    p1 = rank2_part(q0, sub, hi, code);
+                    lines += 1;
+                } else {
+                    Quarter q1 = load_quarter(o2, b1, sub);
+                    p0 = rank2_part(q0, sub, lb, code);
+                    p1 = rank2_part(q1, sub, hi, code);
+                    lines += 2;
+                }
+                uint32_t r0 = group_sum4(p0, gmask), r1 = group_sum4(p1, gmask);
+                if (code == 0) {
+                    r0 -= specials_below(o2, lb);
+                    r1 -= specials_below(o2, hi);
+                }
+                lb = o2.C2[code] + r0;
+                len = r1 - r0;
+                pos -= 2;
+            }
+        }
+        if (sub == 0) {
+            out_lb[q] = lb;
+            out_len[q] = len;
+        }
+    }
+    if (COUNT) {
+        // [2] = line requests issued by this kernel (physical work), counted once per group
+        uint32_t v = (sub == 0) ? lines : 0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(counters + 2, (unsigned long long)v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K5: ordered compaction of the per-query intervals into hit records
 // ---------------------------------------------------------------------------------------------------------
 __global__ void flag_nonzero_kernel(const uint32_t* __restrict__ len, uint64_t count, uint32_t* __restrict__ flag) {
@@ -288,7 +556,7 @@ __global__ void hit_lengths_kernel(const HitRec* __restrict__ hits, uint64_t nh,
 // starts[] = exclusive prefix sum of the hit interval lengths; a thread finds its hit by binary search.
 // ---------------------------------------------------------------------------------------------------------
 template <class OCC, bool COUNT>
-__global__ void __launch_bounds__(256) locate_kernel(IndexView<OCC> ix, const HitRec* __restrict__ hits,
+__global__ void __launch_bounds__(256) locate_kernel(const __grid_constant__ IndexView<OCC> ix, const HitRec* __restrict__ hits,
                                                      const uint32_t* __restrict__ starts, uint32_t nh, uint32_t total,
                                                      LocRec* __restrict__ out, unsigned long long* __restrict__ counters) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -334,7 +602,7 @@ __global__ void __launch_bounds__(256) locate_kernel(IndexView<OCC> ix, const Hi
 
 // index.locate(row) for arbitrary rows (fmindex/BiFMIndex.h:177-202): same LF walk as locate_kernel, row list input
 template <class OCC>
-__global__ void __launch_bounds__(256) locate_rows_kernel(IndexView<OCC> ix, const uint64_t* __restrict__ rows, uint64_t count,
+__global__ void __launch_bounds__(256) locate_rows_kernel(const __grid_constant__ IndexView<OCC> ix, const uint64_t* __restrict__ rows, uint64_t count,
                                                           uint32_t* __restrict__ seq, uint32_t* __restrict__ pos, uint64_t* __restrict__ steps_out) {
     uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t >= count) return;

@@ -183,8 +183,25 @@ fmb::IndexView<fmb::OccDna> fmb_index::view_dna() const {
     return v;
 }
 
+fmb::Occ2View fmb_index::view_occ2(int dir) const {
+    fmb::Occ2View v{};
+    v.lines = occ2[dir].p;
+    v.specials = specials[dir].p;
+    v.n_specials = n_specials[dir];
+    v.s0 = special01[dir][0];
+    v.s1 = special01[dir][1];
+    for (int i = 0; i < 16; ++i) v.C2[i] = C2[dir][i];
+    v.jump = jump[dir].p;
+    v.kmer = dir == 0 ? kmer.p : nullptr;
+    v.kmer_k = dir == 0 ? kmer_k : 0;
+    return v;
+}
+
 uint64_t fmb_index::device_bytes() const {
     uint64_t b = 0;
+    for (int d = 0; d < 2; ++d) b += occ2[d].p ? occ2[d].bytes() + specials[d].bytes() : 0;
+    b += kmer.p ? kmer.bytes() : 0;
+    for (int d = 0; d < 2; ++d) b += jump[d].p ? jump[d].bytes() : 0;
     for (int d = 0; d < 2; ++d) b += occ_dna[d].p ? occ_dna[d].bytes() : 0, b += occ_gen[d].p ? occ_gen[d].bytes() : 0, b += delim_rows[d].p ? delim_rows[d].bytes() : 0;
     b += marks.p ? marks.bytes() : 0;
     b += samples.p ? samples.bytes() : 0;
@@ -261,6 +278,111 @@ int compute_C(fmb_index* ix) {
     FMB_CUDA(cudaGetLastError());
     FMB_CUDA(cudaMemcpyAsync(ix->C, d_out.p, (ix->sigma + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream));
     FMB_CUDA(cudaStreamSynchronize(ix->stream));
+    return FMB_OK;
+}
+
+// C2[code] = first row of the interval of the pattern "x y" = C[x] + rank(C[y], x), code = (y-1)*4 + (x-1)
+__global__ void compute_C2_kernel(IndexView<OccDna> ix, int dir, uint32_t* out) {
+    uint32_t code = threadIdx.x;
+    if (code >= 16) return;
+    uint32_t y = (code >> 2) + 1, x = (code & 3) + 1;
+    const OccDna& occ = ix.occ[dir];
+    row_t at = ix.C[y];
+    DnaBlock b = occ.load(at >> 6);
+    out[code] = (x < ix.sigma && y < ix.sigma) ? ix.C[x] + occ.rank(b, at, x) : 0u;
+}
+
+int build_jump(fmb_index* ix, int dir);
+
+// Builds the two-symbol table of direction `dir` from the one-symbol table (needs C).  sigma <= 5 only.
+int build_occ2(fmb_index* ix, int dir) {
+    const uint64_t n = ix->n;
+    const uint64_t nblocks = n / 128 + 1, nquarters = nblocks * 4;
+    cudaStream_t st = active_stream(ix);
+    auto v = ix->view_dna();
+    DevBuf<uint8_t> codes;
+    FMB_TRY(codes.alloc(n));
+    pair_codes_kernel<<<grid_for(n, 256), 256, 0, st>>>(v, dir, codes.p);
+    FMB_CUDA(cudaGetLastError());
+    FMB_TRY(ix->occ2[dir].alloc(nblocks * 8));
+    DevBuf<uint32_t> qcounts, scount;
+    DevBuf<Cnt16> bcounts;
+    FMB_TRY(qcounts.alloc(nquarters * 16));
+    FMB_TRY(scount.alloc(nquarters + 1));
+    FMB_TRY(bcounts.alloc(nblocks));
+    pack_pairs_kernel<<<grid_for(nquarters + 1, 256), 256, 0, st>>>(codes.p, n, nblocks, ix->occ2[dir].p, qcounts.p, scount.p);
+    FMB_CUDA(cudaGetLastError());
+    block_counts_kernel<<<grid_for(nblocks * 16, 256), 256, 0, st>>>(qcounts.p, nblocks, bcounts.p);
+    FMB_CUDA(cudaGetLastError());
+    {
+        size_t tmp_bytes = 0;
+        FMB_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp_bytes, bcounts.p, bcounts.p, Cnt16Add{}, Cnt16{}, (int64_t)nblocks, st));
+        DevBuf<uint8_t> tmp;
+        FMB_TRY(tmp.alloc(tmp_bytes));
+        FMB_CUDA(cub::DeviceScan::ExclusiveScan(tmp.p, tmp_bytes, bcounts.p, bcounts.p, Cnt16Add{}, Cnt16{}, (int64_t)nblocks, st));
+    }
+    store_pair_counts_kernel<<<grid_for(nquarters, 256), 256, 0, st>>>(ix->occ2[dir].p, bcounts.p, nblocks);
+    FMB_CUDA(cudaGetLastError());
+    FMB_TRY(exclusive_sum_u32(scount.p, scount.p, nquarters + 1, st));
+    uint32_t ns = 0;
+    FMB_CUDA(cudaMemcpy(&ns, scount.p + nquarters, sizeof ns, cudaMemcpyDeviceToHost));
+    FMB_TRY(ix->specials[dir].alloc((size_t)ns + 2));
+    FMB_CUDA(cudaMemsetAsync(ix->specials[dir].p, 0xFF, ((size_t)ns + 2) * sizeof(uint32_t), st));
+    if (ns) {
+        scatter_specials_kernel<<<grid_for(nquarters, 256), 256, 0, st>>>(codes.p, n, nquarters, scount.p, ix->specials[dir].p);
+        FMB_CUDA(cudaGetLastError());
+    }
+    ix->n_specials[dir] = ns;
+    FMB_CUDA(cudaMemcpyAsync(ix->special01[dir], ix->specials[dir].p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    DevBuf<uint32_t> c2;
+    FMB_TRY(c2.alloc(16));
+    compute_C2_kernel<<<1, 32, 0, st>>>(v, dir, c2.p);
+    FMB_CUDA(cudaGetLastError());
+    FMB_CUDA(cudaMemcpyAsync(ix->C2[dir], c2.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    FMB_CUDA(cudaStreamSynchronize(st));
+    if (dir == 0) {
+        // k-mer table: largest k <= 14 whose table (8 bytes per k-mer) stays below ~n bytes, i.e. 4^k <= n / 8
+        uint32_t k = 0;
+        while (k < 14 && (uint64_t(8) << (2 * (k + 1))) <= n) ++k;
+        const char* env = getenv("FMB_KMER_K");
+        if (env) k = (uint32_t)std::min<long>(14, std::max<long>(0, atol(env)));
+        ix->kmer_k = 0;
+        if (k >= 2) {
+            const uint64_t count = uint64_t(1) << (2 * k);
+            FMB_TRY(ix->kmer.alloc(count));
+            kmer_table_kernel<<<grid_for(count, 256), 256, 0, st>>>(v, k, count, ix->kmer.p);
+            FMB_CUDA(cudaGetLastError());
+            FMB_CUDA(cudaStreamSynchronize(st));
+            ix->kmer_k = k;
+        }
+    }
+    FMB_TRY(build_jump(ix, dir));
+    return FMB_OK;
+}
+
+// LF^16 jump table of direction `dir` (8 bytes per row) by four rounds of pointer doubling.  Skipped -- the search then
+// keeps taking two-symbol steps -- when the device cannot hold the two build buffers, or when FMB_NO_JUMP is set.
+int build_jump(fmb_index* ix, int dir) {
+    if (getenv("FMB_NO_JUMP")) return FMB_OK;
+    const uint64_t n = ix->n;
+    size_t free_b = 0, total_b = 0;
+    FMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    pool_trim();
+    FMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if ((double)free_b < 2.0 * 8.0 * (double)n * 1.25 + (double)(1u << 28)) return FMB_OK;
+    cudaStream_t st = active_stream(ix);
+    DevBuf<uint2> a, b;
+    FMB_TRY(a.alloc(n));
+    FMB_TRY(b.alloc(n));
+    jump_init_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->view_dna(), dir, a.p);
+    FMB_CUDA(cudaGetLastError());
+    for (uint32_t shift = 2; shift <= 16; shift *= 2) {
+        jump_double_kernel<<<grid_for(n, 256), 256, 0, st>>>(a.p, b.p, n, shift);
+        FMB_CUDA(cudaGetLastError());
+        std::swap(a, b);
+    }
+    FMB_CUDA(cudaStreamSynchronize(st));
+    ix->jump[dir] = std::move(a);
     return FMB_OK;
 }
 
@@ -358,6 +480,8 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, co
         }
     }
     int rc = compute_C(ix);
+    if (rc) return fail(rc);
+    rc = build_occ2(ix, 0);
     if (rc) return fail(rc);
     {
         const uint64_t have = (n + 63) / 64;
@@ -565,6 +689,20 @@ int fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* sy
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         }
     }
+    if (e == cudaSuccess && ix->dna) {
+        // 2-bit packed copy for the two-symbol / jump kernels
+        const uint64_t words = (total + 15) / 16;
+        rc = q->packed.alloc(words + 2);
+        if (!rc) rc = q->flags.alloc(nq + 1);
+        if (rc) { delete q; return rc; }
+        e = cudaMemsetAsync(q->flags.p, 0, nq + 1, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(q->packed.p + words, 0, 2 * sizeof(uint32_t), st);
+        if (e == cudaSuccess && words) {
+            pack_queries_kernel<<<grid_for(words, 256), 256, 0, st>>>(q->symbols.p, total, q->offsets.p, nq, ix->sigma, q->packed.p, words, q->flags.p);
+            e = cudaGetLastError();
+            note_launches(1);
+        }
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { set_error("query upload: %s", cudaGetErrorString(e)); delete q; return FMB_ECUDA; }
     *out = q;
@@ -599,8 +737,13 @@ int fmb_search_exact(const fmb_index* ix, const fmb_queries* q, fmb_results** ou
     EventTimer tm(st);
     cudaEvent_t ev_main = nullptr;
     cudaEventCreate(&ev_main);
+    const bool two = ix->occ2[0].p && q->packed.p && ix->exact_mode != FMB_EXACT_ONE_SYMBOL;
+    if (ix->exact_mode == FMB_EXACT_TWO_SYMBOL && !ix->occ2[0].p) { cudaEventDestroy(ev_main); set_error("index has no two-symbol table"); return fail(FMB_EUNSUPPORTED); }
     if (nq) {
-        exact_search_kernel<OccDna, true><<<grid_for(nq, 256), 256, 0, st>>>(v, q->symbols.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
+        static const bool minb8 = getenv("FMB_EXACT2_MINB1") == nullptr;      // 32 registers -> 2048 resident threads per SM
+        if (two && minb8) exact_search2_kernel<true, 8><<<grid_for(nq * 4, 256), 256, 0, st>>>(v, ix->view_occ2(0), q->symbols.p, q->packed.p, q->flags.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
+        else if (two) exact_search2_kernel<true, 1><<<grid_for(nq * 4, 256), 256, 0, st>>>(v, ix->view_occ2(0), q->symbols.p, q->packed.p, q->flags.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
+        else exact_search_kernel<OccDna, true><<<grid_for(nq, 256), 256, 0, st>>>(v, q->symbols.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
         cudaEventRecord(ev_main, st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("exact_search_kernel: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
@@ -630,6 +773,7 @@ int fmb_search_exact(const fmb_index* ix, const fmb_queries* q, fmb_results** ou
     cudaMemcpy(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost);
     res->stats.extensions = h_ctr[0];
     res->stats.occ_lookups = h_ctr[1];
+    res->stats.line_requests = h_ctr[2];
     res->count = nhits;
     *out = res;
     return FMB_OK;
@@ -806,6 +950,12 @@ int fmb_synth_reads_device(int device, const uint8_t* d_text, uint64_t n, uint64
 int fmb_index_set_stream(fmb_index* ix, void* stream) {
     if (!ix) { set_error("NULL index"); return FMB_EINVAL; }
     ix->stream = stream ? (cudaStream_t)stream : ix->own_stream;
+    return FMB_OK;
+}
+int fmb_index_set_exact_mode(fmb_index* ix, int mode) {
+    if (!ix || mode < 0 || mode > 2) { set_error("bad argument"); return FMB_EINVAL; }
+    if (mode == FMB_EXACT_TWO_SYMBOL && !ix->occ2[0].p) { set_error("index has no two-symbol table"); return FMB_EUNSUPPORTED; }
+    ix->exact_mode = mode;
     return FMB_OK;
 }
 uint64_t fmb_kernel_launch_count(void) { return fmb::g_launches.load(); }

@@ -121,7 +121,7 @@ __device__ __forceinline__ void child_cursor(const IndexView<OCC>& ix, const OCC
 }
 
 template <class OCC, bool EDIT>
-__global__ void __launch_bounds__(256) scheme_search_kernel(IndexView<OCC> ix, SchemeParams sp, const uint8_t* __restrict__ qsym,
+__global__ void __launch_bounds__(256) scheme_search_kernel(const __grid_constant__ IndexView<OCC> ix, const __grid_constant__ SchemeParams sp, const uint8_t* __restrict__ qsym,
                                                             const uint64_t* __restrict__ qoff, uint64_t n_roots,
                                                             const Item* __restrict__ in_items, uint64_t n_in,
                                                             SchemeOut out, uint32_t cap) {

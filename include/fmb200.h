@@ -75,6 +75,7 @@ typedef struct {
     uint64_t frontier_peak;    /* largest breadth-first frontier (scheme search)            */
     double   kernel_ms;        /* device time of the call (CUDA events)                     */
     double   main_kernel_ms;   /* device time of the dominant kernel alone (search / LF walk) */
+    uint64_t line_requests;    /* 128-byte-line requests issued by the two-symbol exact kernel (physical work) */
 } fmb_stats;
 
 const char* fmb_last_error(void);
@@ -181,6 +182,15 @@ int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uin
                           int edit, uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l,
                           const uint32_t* u, const uint32_t* partition,
                           fmb_loc32* out, uint64_t capacity, uint64_t* n_out, fmb_stats* stats);
+
+/* Exact-search kernel selection.  FMB_EXACT_AUTO (default): two-symbol steps on the 128-byte pair table when the
+ * index has one (sigma <= 5), else one-symbol steps.  FMB_EXACT_ONE_SYMBOL: the one-symbol kernel, which also fills
+ * the algorithmic work counters fmb_stats.extensions / occ_lookups -- the two-symbol kernel reports
+ * fmb_stats.line_requests instead.  Results are identical in every mode. */
+#define FMB_EXACT_AUTO        0
+#define FMB_EXACT_ONE_SYMBOL  1
+#define FMB_EXACT_TWO_SYMBOL  2
+int  fmb_index_set_exact_mode(fmb_index* ix, int mode);
 
 /* ---- synthetic data + pinned host memory helpers (bench / tests) ------------------------------------------- */
 /* T[i] = 1 + (splitmix64(seed + i) % (sigma-1)) for i < n-1, T[n-1] = 0; written to a device buffer owned by the

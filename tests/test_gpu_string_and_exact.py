@@ -94,13 +94,49 @@ def test_exact_search_and_locate(pair):
     loc = g.locate(res)
     assert locs_equal(loc.locs(), o.locate(exp))
     assert np.array_equal(loc.locs32()["pos"].astype(np.uint64), loc.locs()["pos"])
+    # the algorithmic work counters come from the one-symbol kernel; both kernels give the same hits
+    assert res.stats.line_requests > 0
+    g.set_exact_mode(1)
+    res1 = g.search_exact(q)
+    g.set_exact_mode(0)
+    assert hits_equal(res1.hits(), exp)
     ctr = Counters()
     o.search_exact(sym, off, ctr)
-    st = res.stats
+    st = res1.stats
     assert st.extensions == ctr.extensions and st.occ_lookups == ctr.occ_lookups
     ctr = Counters()
     o.locate(exp, ctr)
     assert loc.stats.lf_steps == ctr.lf_steps
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("lengths", [[40000], [3000, 1, 2, 700, 5, 129, 128, 127], [300] * 50])
+def test_exact_modes_multi_sequence(gpu, mode, lengths):
+    """one-symbol and two-symbol (128-byte pair table) kernels on collections with many delimiters; reads that
+    contain or straddle delimiters take the one-symbol path inside the two-symbol kernel"""
+    from fmb200 import synth
+    text = synth.multi_text(lengths, 5, 21)
+    o, g = make_index_pair(gpu, text, 5, 4)
+    g.set_exact_mode(mode)
+    rng = np.random.default_rng(5)
+    reads = []
+    for L in (1, 2, 3, 4, 7, 8, 20, 21, 64):
+        for _ in range(60):
+            p = int(rng.integers(0, text.size - L))
+            reads.append(text[p:p + L].copy())
+        for _ in range(10):
+            reads.append(rng.integers(0, 5, size=L).astype(np.uint8))      # symbol 0 inside a query
+    # all 2-mers and 3-mers over {0..4}: every pair code, every special-row correction
+    for a in range(5):
+        for b in range(5):
+            reads.append(np.array([a, b], dtype=np.uint8))
+            for c in range(5):
+                reads.append(np.array([a, b, c], dtype=np.uint8))
+    sym, off = synth.flatten(reads)
+    res = g.search_exact(g.upload(sym, off))
+    exp = o.search_exact(sym, off)
+    assert hits_equal(res.hits(), exp)
+    assert locs_equal(g.locate(res).locs(), o.locate(exp))
 
 
 def test_empty_inputs(pair):

@@ -207,10 +207,18 @@ def main():
         loc = index.locate(res)
         return res, loc
 
+    # algorithmic work of the reference algorithm on this batch (occ-block lookups of one-symbol steps),
+    # counted once, untimed, by the one-symbol kernel; the timed steps use the default (two-symbol + jump) kernel
+    index.set_exact_mode(1)
+    res = index.search_exact(queries)
+    alg_lookups = res.stats.occ_lookups
+    one_symbol_ms = res.stats.main_kernel_ms
+    del res
+    index.set_exact_mode(0)
+
     for _ in range(W):
         res, loc = step()
     n_hits, n_locs = len(res), len(loc)
-    st_s, st_l = res.stats, loc.stats
     del res, loc
 
     def barrier():
@@ -224,12 +232,12 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    search_ms, locate_ms, look_s, look_l = [], [], 0, 0
+    search_ms, locate_ms, lines_s, look_l = [], [], 0, 0
     for _ in range(K):
         res, loc = step()
         search_ms.append(res.stats.main_kernel_ms)
         locate_ms.append(loc.stats.main_kernel_ms)
-        look_s, look_l = res.stats.occ_lookups, loc.stats.lf_steps
+        lines_s, look_l = res.stats.line_requests, loc.stats.lf_steps
         del res, loc
     ev1.record(stream)
     barrier()
@@ -261,16 +269,27 @@ def main():
     h2d = nq * L + (nq + 1) * 8
     d2h = len(locs) * 16
 
-    # ---- roofline of the dominant kernel (exact_search_kernel) ------------------------------------------------
+    # ---- roofline of the dominant kernel (exact_search2_kernel) -----------------------------------------------------
+    # achieved = ALGORITHMIC bytes (the reference algorithm's occ-block lookups x 32 B) / kernel time.
+    # The kernel answers those lookups with far fewer physical line fetches (k-mer table, two-symbol lines, LF^16
+    # jumps), so `frac` can exceed 1; `physical` is the kernel's own traffic (line requests x 128 B) against the same peak.
     peak, peak_src = load_peaks()
     k_ms = float(np.mean(search_ms))
-    alg_bytes = look_s * 32.0                       # occ-block lookups x 32 B (SURVEY.md §8d work unit)
+    l_ms = float(np.mean(locate_ms))
+    alg_bytes = alg_lookups * 32.0
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "exact_search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    phys_bytes = lines_s * 128.0
+    loc_lookups = n_locs * 2 + look_l * 2            # per row: marker test + sample fetch, per LF step: occ block + marker word
+    roofline = {"bound": "hbm", "kernel": "exact_search2_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "lookups_per_query": look_s / nq, "kernel_ms": k_ms,
-                "random_sector_ceiling_gbs": 38.4 * 32, "frac_of_random_sector_ceiling": achieved / (38.4 * 32),
-                "locate_kernel_ms": float(np.mean(locate_ms)), "lf_steps_per_row": look_l / max(n_locs, 1)}
+                "algorithmic_bytes_per_launch": alg_bytes, "lookups_per_query": alg_lookups / nq, "kernel_ms": k_ms,
+                "physical": {"line_requests_per_query": lines_s / nq, "bytes_per_launch": phys_bytes,
+                             "gbs": phys_bytes / (k_ms * 1e-3) / 1e9, "frac": phys_bytes / (k_ms * 1e-3) / 1e9 / peak,
+                             "lines_per_s": lines_s / (k_ms * 1e-3), "measured_random_line_ceiling_per_s": 38.4e9},
+                "one_symbol_kernel_ms": one_symbol_ms,
+                "locate_kernel": {"kernel_ms": l_ms, "lf_steps_per_row": look_l / max(n_locs, 1), "algorithmic_bytes_per_launch": loc_lookups * 32.0,
+                                  "achieved": loc_lookups * 32.0 / (l_ms * 1e-3) / 1e9, "frac": loc_lookups * 32.0 / (l_ms * 1e-3) / 1e9 / peak},
+                "note": "frac > 1 is possible: algorithmic bytes are those of the reference's one-symbol algorithm; see physical.frac for the kernel's own traffic"}
 
     line = {"metric": "queries/s (150bp exact search + locate, 3 Gbp index)", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

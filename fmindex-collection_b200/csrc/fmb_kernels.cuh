@@ -353,6 +353,11 @@ __global__ void __launch_bounds__(256) kmer_table_kernel(const __grid_constant__
     out[i] = make_uint2(lb, len);
 }
 
+__global__ void rebase_offsets_kernel(uint64_t* __restrict__ off, uint64_t count, uint64_t base) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < count) off[i] -= base;
+}
+
 // 2-bit packing of the query symbols (symbol-1, 16 symbols per word, first symbol in the low bits).  Queries holding a
 // symbol that has no 2-bit code (0 or >= sigma) are flagged and take the byte path of the search kernel.
 __device__ __forceinline__ uint32_t pack4(uint32_t w, uint32_t sigma, bool& bad) {
@@ -562,8 +567,8 @@ __global__ void __launch_bounds__(256) locate_kernel(const __grid_constant__ Ind
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t steps = 0;
     if (t < total) {
-        // largest h with starts[h] <= t
-        uint32_t lo = 0, hi = nh;
+        // largest h with starts[h] <= t (when every hit is a single row, total == nh and h == t)
+        uint32_t lo = (total == nh) ? t : 0, hi = (total == nh) ? t + 1 : nh;
         while (hi - lo > 1) {
             uint32_t mid = (lo + hi) >> 1;
             if (__ldg(starts + mid) <= t) lo = mid; else hi = mid;

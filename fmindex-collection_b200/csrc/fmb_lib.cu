@@ -659,10 +659,19 @@ int fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* sy
     q->device = ix->device;
     q->nq = nq;
     q->total_symbols = total;
+    if (offsets[nq] < offsets[0]) { set_error("offsets not monotone"); delete q; return FMB_EINVAL; }
+    cudaStream_t st = active_stream(ix);
+    int rc = q->symbols.alloc(total + 32);
+    if (!rc) rc = q->offsets.alloc(nq + 1);
+    if (rc) { delete q; return rc; }
+    cudaError_t e = cudaSuccess;
+    if (total) e = cudaMemcpyAsync(q->symbols.p, symbols + offsets[0], total, cudaMemcpyHostToDevice, st);
+    // validate the offsets while the symbols are in flight
     uint32_t mx = 0, mn = 0xFFFFFFFFu;
     for (uint64_t i = 0; i < nq; ++i) {
         if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0xFFFFu) {
             set_error("query %llu: offsets not monotone or query longer than 65535", (unsigned long long)i);
+            cudaStreamSynchronize(st);
             delete q;
             return FMB_EINVAL;
         }
@@ -672,22 +681,13 @@ int fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* sy
     }
     q->max_len = mx;
     q->min_len = nq ? mn : 0;
-    cudaStream_t st = active_stream(ix);
-    int rc = q->symbols.alloc(total + 32);
-    if (!rc) rc = q->offsets.alloc(nq + 1);
-    if (rc) { delete q; return rc; }
-    cudaError_t e = cudaSuccess;
-    if (total) e = cudaMemcpyAsync(q->symbols.p, symbols + offsets[0], total, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(q->symbols.p + total, 0xFF, 32, st);
-    if (e == cudaSuccess) {
-        if (offsets[0] == 0) {
-            e = cudaMemcpyAsync(q->offsets.p, offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, st);
-        } else {
-            std::vector<uint64_t> rel(nq + 1);
-            for (uint64_t i = 0; i <= nq; ++i) rel[i] = offsets[i] - offsets[0];
-            e = cudaMemcpyAsync(q->offsets.p, rel.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q->offsets.p, offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && offsets[0] != 0) {
+        // a slice of a larger batch: make the offsets relative to the first symbol of the slice, on the device
+        rebase_offsets_kernel<<<grid_for(nq + 1, 256), 256, 0, st>>>(q->offsets.p, nq + 1, offsets[0]);
+        e = cudaGetLastError();
+        note_launches(1);
     }
     if (e == cudaSuccess && ix->dna) {
         // 2-bit packed copy for the two-symbol / jump kernels

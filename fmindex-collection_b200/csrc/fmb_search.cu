@@ -1,6 +1,8 @@
 // fmb_search.cu -- host side of the k-error searches (K3) and the one-call search+locate path.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -234,7 +236,11 @@ int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uin
     std::string err_msg;
     fmb_stats total{};
 
+    static const bool trace = getenv("FMB_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     auto worker = [&]() {
+        double t_up = 0, t_search = 0, t_loc = 0, t_down = 0;
         cudaSetDevice(ix->device);
         cudaStream_t st = nullptr;
         if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
@@ -255,15 +261,20 @@ int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uin
             if (c >= n_chunks || (e0 != FMB_OK && e0 != FMB_EOVERFLOW)) break;
             uint64_t b = c * chunk, e = std::min(nq, b + chunk);
             fmb_queries* q = nullptr;
+            double t0 = now();
             int rc = fmb_queries_upload(&q, ix, symbols, offsets + b, e - b);
             if (rc) { fail(rc); break; }
             q->qidx_base = b;
+            double t1 = now();
             fmb_results* hits = nullptr;
             rc = n_searches ? fmb_search_scheme(ix, q, edit, n_searches, n_parts, pi, l, u, partition, &hits) : fmb_search_exact(ix, q, &hits);
             fmb_queries_destroy(q);
             if (rc) { fail(rc); break; }
+            double t2 = now();
             fmb_results* locs = nullptr;
             rc = fmb_locate(ix, hits, &locs);
+            double t3 = now();
+            t_up += t1 - t0; t_search += t2 - t1; t_loc += t3 - t2;
             mine.extensions += hits->stats.extensions;
             mine.occ_lookups += hits->stats.occ_lookups;
             mine.kernel_ms += hits->stats.kernel_ms;
@@ -286,6 +297,7 @@ int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uin
             cudaError_t ce = cudaSuccess;
             if (cnt) ce = cudaMemcpyAsync(out + off, locs->locs.p, cnt * sizeof(fmb_loc32), cudaMemcpyDeviceToHost, st);
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+            t_down += now() - t3;
             fmb_results_destroy(locs);
             if (ce != cudaSuccess) {
                 std::lock_guard<std::mutex> lk(mu);
@@ -296,6 +308,7 @@ int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uin
         tls_stream_override = nullptr;
         cudaStreamDestroy(st);
         std::lock_guard<std::mutex> lk(mu);
+        if (trace) fprintf(stderr, "[fmb trace] worker done at %.2f ms: upload %.2f search %.2f locate %.2f download %.2f\n", now() - t_begin, t_up, t_search, t_loc, t_down);
         total.extensions += mine.extensions;
         total.occ_lookups += mine.occ_lookups;
         total.lf_steps += mine.lf_steps;

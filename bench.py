@@ -280,8 +280,16 @@ def main():
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     phys_bytes = lines_s * 128.0
     loc_lookups = n_locs * 2 + look_l * 2            # per row: marker test + sample fetch, per LF step: occ block + marker word
+    traffic = None                                   # dram bytes per launch from the committed ncu --set full capture, same workload only
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f)["exact_search2_kernel"]
+        if ent["workload"] == f"{nq} x {L}bp on {n_text} bp":
+            traffic = ent["traffic_bytes"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "exact_search2_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "lookups_per_query": alg_lookups / nq, "kernel_ms": k_ms,
                 "physical": {"line_requests_per_query": lines_s / nq, "bytes_per_launch": phys_bytes,
                              "gbs": phys_bytes / (k_ms * 1e-3) / 1e9, "frac": phys_bytes / (k_ms * 1e-3) / 1e9 / peak,

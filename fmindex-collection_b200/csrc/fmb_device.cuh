@@ -283,6 +283,10 @@ struct IndexView {
     // sampled suffix array (suffixarray/SparseArray.h:63-70): per 64 rows {u64 marker bits, u32 samples before}
     const uint4* marks;     // .x,.y = marker bits (low, high word), .z = number of samples before the word
     const uint2* samples;   // .x = seqId, .y = pos
+    // locate blocks (DNA layout only): per 64 rows one 64-byte record = {DnaBlock (32 B), marker bits u64, samples before
+    // u32, pad} so that one LF step of locate touches ONE line instead of two (occ block + marker word); a lane pair
+    // fetches the two 32-byte halves with one request.  nullptr when not built.
+    const uint4* locblocks;
 };
 
 struct Cursor {             // BiFMIndexCursor{lb, lbRev, len, steps}, fmindex/BiFMIndexCursor.h:22-37

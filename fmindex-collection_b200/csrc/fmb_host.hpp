@@ -92,6 +92,7 @@ struct fmb_index {
     uint32_t delim0[2] = {0, 0};
     fmb::DevBuf<uint4> marks;
     fmb::DevBuf<uint2> samples;
+    fmb::DevBuf<uint4> locblocks;        // combined occ + marker records for locate (sigma <= 5)
     uint64_t n_samples = 0;
     uint64_t C[65] = {0};
     // two-symbol table (OccDna2), sigma <= 5 only

@@ -605,6 +605,95 @@ __global__ void __launch_bounds__(256) locate_kernel(const __grid_constant__ Ind
     }
 }
 
+// K4b: locate with the combined 64-byte locate blocks.  A pair of lanes owns one SA row: the even lane fetches the
+// occ half of the block (symbol + rank -> next row), the odd lane the marker half (sampled? which sample?); two
+// shuffles per LF step exchange "sampled" and the next row.  One line request per step instead of two.
+__global__ void build_locblocks_kernel(const DnaBlock* __restrict__ occ, const uint4* __restrict__ marks, uint64_t nblocks, uint4* __restrict__ out) {
+    uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const uint4* o = reinterpret_cast<const uint4*>(occ + b);
+    uint4 m = marks[b];
+    out[b * 4 + 0] = o[0];
+    out[b * 4 + 1] = o[1];
+    out[b * 4 + 2] = m;
+    out[b * 4 + 3] = make_uint4(0, 0, 0, 0);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) locate_pair_kernel(const __grid_constant__ IndexView<OccDna> ix, const HitRec* __restrict__ hits,
+                                                          const uint32_t* __restrict__ starts, uint32_t nh, uint32_t total,
+                                                          LocRec* __restrict__ out, unsigned long long* __restrict__ counters) {
+    // Persistent lane pairs with refill: LF walks take 0 .. rate-1 steps, so a warp of fixed rows idles half of its
+    // lanes while the longest walk finishes.  Here a pair that reaches its sample immediately takes the next row
+    // (t += number of pairs in the grid); all pairs run the same loop body, there is no divergence to pay for.
+    const uint32_t npairs = (gridDim.x * blockDim.x) >> 1;
+    uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const uint32_t role = threadIdx.x & 1;                 // 0 = occ half, 1 = marker half
+    const uint32_t pmask = 3u << (threadIdx.x & 30);
+    const OccDna& occ = ix.occ[0];
+    uint32_t steps_total = 0, steps = 0;
+    row_t row = 0;
+    uint32_t qidx = 0, err = 0;
+    auto fetch = [&]() {
+        uint32_t lo = (total == nh) ? t : 0, hi = (total == nh) ? t + 1 : nh;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(starts + mid) <= t) lo = mid; else hi = mid;
+        }
+        const HitRec* h = hits + lo;
+        row = __ldg(&h->lb) + (t - __ldg(starts + lo));
+        qidx = __ldg(&h->qidx);
+        err = __ldg(&h->e);
+        steps = 0;
+    };
+    bool active = t < total;
+    if (active) fetch();
+    while (active) {
+        uint32_t a0, a1, a2, a3, a4, a5, a6, a7;
+        asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=r"(a4), "=r"(a5), "=r"(a6), "=r"(a7)
+                     : "l"(ix.locblocks + ((size_t)(row >> 6) * 4 + role * 2)));
+        uint32_t mine;                                       // role 1: sampled ? 1 + sample index : 0;  role 0: next row
+        if (role) {
+            uint64_t bits = (uint64_t)a0 | ((uint64_t)a1 << 32);
+            uint32_t o = row & 63;
+            mine = ((bits >> o) & 1) ? 1u + a2 + __popcll(bits & low_mask(o)) : 0u;
+        } else {
+            DnaBlock b;
+            b.cnt[0] = a0; b.cnt[1] = a1; b.cnt[2] = a2; b.cnt[3] = a3;
+            b.p0 = (uint64_t)a4 | ((uint64_t)a5 << 32);
+            b.p1 = (uint64_t)a6 | ((uint64_t)a7 << 32);
+            uint32_t c = occ.symbol(b, row);
+            mine = ix.C[c] + occ.rank(b, row, c);
+        }
+        uint32_t other = __shfl_xor_sync(pmask, mine, 1);
+        uint32_t sampled = role ? mine : other;
+        if (sampled) {
+            if (role == 0) {
+                uint2 sample = __ldg(ix.samples + (sampled - 1));
+                LocRec r;
+                r.qidx = qidx; r.seq = sample.x; r.pos = sample.y + steps; r.e = err;
+                out[t] = r;
+                steps_total += steps;
+            }
+            t += npairs;
+            active = t < total;
+            if (active) fetch();
+        } else {
+            row = role ? other : mine;
+            ++steps;
+        }
+    }
+    if (COUNT) {
+        uint32_t s = steps_total;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        if ((threadIdx.x & 31) == 0 && s) {
+            atomicAdd(counters + 2, (unsigned long long)s);
+            atomicAdd(counters + 1, (unsigned long long)s);
+        }
+    }
+}
+
 // index.locate(row) for arbitrary rows (fmindex/BiFMIndex.h:177-202): same LF walk as locate_kernel, row list input
 template <class OCC>
 __global__ void __launch_bounds__(256) locate_rows_kernel(const __grid_constant__ IndexView<OCC> ix, const uint64_t* __restrict__ rows, uint64_t count,

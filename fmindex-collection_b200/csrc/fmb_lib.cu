@@ -180,6 +180,7 @@ fmb::IndexView<fmb::OccDna> fmb_index::view_dna() const {
     v.sigma = sigma;
     v.marks = marks.p;
     v.samples = samples.p;
+    v.locblocks = locblocks.p;
     return v;
 }
 
@@ -204,6 +205,7 @@ uint64_t fmb_index::device_bytes() const {
     for (int d = 0; d < 2; ++d) b += jump[d].p ? jump[d].bytes() : 0;
     for (int d = 0; d < 2; ++d) b += occ_dna[d].p ? occ_dna[d].bytes() : 0, b += occ_gen[d].p ? occ_gen[d].bytes() : 0, b += delim_rows[d].p ? delim_rows[d].bytes() : 0;
     b += marks.p ? marks.bytes() : 0;
+    b += locblocks.p ? locblocks.bytes() : 0;
     b += samples.p ? samples.bytes() : 0;
     return b;
 }
@@ -293,6 +295,18 @@ __global__ void compute_C2_kernel(IndexView<OccDna> ix, int dir, uint32_t* out) 
 }
 
 int build_jump(fmb_index* ix, int dir);
+
+// combined 64-byte locate records (needs occ table 0 and the marks); skipped when FMB_NO_LOCBLOCKS is set
+int build_locblocks(fmb_index* ix) {
+    if (getenv("FMB_NO_LOCBLOCKS") || !ix->dna || !ix->marks.p || ix->n_samples == 0) return FMB_OK;
+    const uint64_t nblocks = ix->n / 64 + 1;
+    cudaStream_t st = active_stream(ix);
+    FMB_TRY(ix->locblocks.alloc(nblocks * 4));
+    build_locblocks_kernel<<<grid_for(nblocks, 256), 256, 0, st>>>(ix->occ_dna[0].p, ix->marks.p, nblocks, ix->locblocks.p);
+    FMB_CUDA(cudaGetLastError());
+    FMB_CUDA(cudaStreamSynchronize(st));
+    return FMB_OK;
+}
 
 // Builds the two-symbol table of direction `dir` from the one-symbol table (needs C).  sigma <= 5 only.
 int build_occ2(fmb_index* ix, int dir) {
@@ -498,6 +512,8 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, co
         rc = build_marks_from_device(ix, d_bm.p, d_seq.p, d_pos.p, n_samples);
         if (rc) return fail(rc);
     }
+    rc = build_locblocks(ix);
+    if (rc) return fail(rc);
     *out = ix;
     pool_trim();
     return FMB_OK;
@@ -785,6 +801,7 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
     *out = nullptr;
     if (hits->kind != 0) { set_error("fmb_locate needs a hit result set"); return FMB_EINVAL; }
     if (hits->device != ix->device) { set_error("results live on another device"); return FMB_EINVAL; }
+    if (hits->count && ix->n_samples == 0) { set_error("index has no sampled suffix array: locate is impossible"); return FMB_EINVAL; }
     FMB_TRY(use_device(ix->device));
     cudaStream_t st = active_stream(ix);
     auto res = new fmb_results();
@@ -811,7 +828,14 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
     if (total) {
         auto v = ix->view_dna();
         cudaEventRecord(ev_m0, st);
-        locate_kernel<OccDna, true><<<grid_for(total, 256), 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p);
+        if (v.locblocks) {
+            // persistent grid: every SM full of lane pairs (8 blocks x 256 threads), rows handed out with a grid stride
+            static int sms = 0;
+            if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+            unsigned grid = (unsigned)std::min<uint64_t>(grid_for((uint64_t)total * 2, 256), (uint64_t)sms * 8);
+            locate_pair_kernel<true><<<grid, 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p);
+        }
+        else locate_kernel<OccDna, true><<<grid_for(total, 256), 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p);
         cudaEventRecord(ev_m1, st);
         note_launches(1);
     }

@@ -4,6 +4,7 @@
     exact search + locate of 10 M synthetic 150-bp reads against a synthetic 3 Gbp DNA BiFMIndex (rate 16)
 
   python bench.py --gpus N --steps K --warmup W              our arm  (libfmb200.so, hand-written sm_100a CUDA)
+  python bench.py --workload k2-edit ...                     the other BASELINE configs (k-error schemes, locate-heavy)
   python bench.py --impl reference --gpus N --steps K ...    reference arm: the reference's own CPU search + locate
                                                              (oracle/_ref/libfmref.so, all host threads), bounded sample
 
@@ -92,14 +93,29 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def build_workload(fmb, device, n_text, nq, L, rate, seed):
-    """synthetic text on the device -> GPU index build -> reads copied from random text offsets (C2 of SURVEY §8d)"""
+WORKLOADS = ("exact", "k1-hamming", "k1-edit", "k2-hamming", "k2-edit", "locate-heavy")
+
+
+def build_workload(fmb, device, n_text, nq, L, rate, seed, workload="exact"):
+    """synthetic text on the device -> GPU index build -> reads:
+         exact          reads copied from random text offsets (C2)
+         kK-hamming/edit  the same reads with e in {0..K} planted substitutions / substitutions+indels each (C3)
+         locate-heavy   text with a repeat family (1000 copies of a 1 kbp unit, 1 % substitutions), reads = windows of the unit (C4)"""
     from fmb200 import capi
     t0 = time.time()
-    d_text = capi.synth_text_device(device, 5, n_text, seed)
+    if workload == "locate-heavy":
+        d_text = capi.synth_repeat_text_device(device, 5, n_text, seed, 1000, 1000, 10)
+    else:
+        d_text = capi.synth_text_device(device, 5, n_text, seed)
     index = fmb.Index.build_from_device_text(5, d_text, n_text, sampling_rate=rate, bidirectional=True, device=device)
     t1 = time.time()
-    d_reads = capi.synth_reads_device(device, d_text, n_text, nq, L, seed + 1)
+    if workload == "exact":
+        d_reads = capi.synth_reads_device(device, d_text, n_text, nq, L, seed + 1)
+    elif workload == "locate-heavy":
+        d_reads = capi.synth_unit_reads_device(device, 5, nq, L, seed, 1000)
+    else:
+        k = int(workload[1])
+        d_reads = capi.synth_reads_err_device(device, d_text, n_text, nq, L, seed + 1, 5, k, workload.endswith("edit"))
     capi.device_free(device, d_text)
     sym = capi.PinnedArray(nq * L, np.uint8)
     capi.copy_to_host(device, sym.array, d_reads, nq * L)
@@ -108,6 +124,16 @@ def build_workload(fmb, device, n_text, nq, L, rate, seed):
     off.array[:] = np.arange(nq + 1, dtype=np.uint64) * np.uint64(L)
     log(f"index build {t1 - t0:.1f}s (n={n_text}), reads {time.time() - t1:.1f}s, device image {index.info.device_bytes / 1e9:.2f} GB")
     return index, sym, off
+
+
+def workload_scheme(workload, L):
+    """(scheme, partition, edit) of a k-error workload: optimum(0,k) with a uniform partition (BASELINE configs[2])"""
+    from fmb200 import schemes
+    if not workload.startswith("k"):
+        return None, None, False
+    k = int(workload[1])
+    sch = schemes.optimum(0, k)
+    return sch, schemes.uniform_partition(sch[0].shape[1], L), workload.endswith("edit")
 
 
 def reference_index(index):
@@ -121,15 +147,16 @@ def reference_index(index):
     return ref
 
 
-def cpu_search_locate(ref, sym, off, b, e, threads, L):
-    """reference search_no_errors::search + LocateLinear on reads [b,e); returns (seconds, n_located)"""
+def cpu_search_locate(ref, sym, off, b, e, threads, L, scheme=None, partition=None, edit=False, want_locs=False):
+    """the reference's search (search_no_errors::search or search_ng26::search<Edit> with the given scheme) + LocateLinear on
+    reads [b,e), queries sharded over `threads` std::threads; returns (seconds, n_located[, located rows])"""
     s = sym[b * L: e * L]
     o = (off[b: e + 1] - off[b]).astype(np.uint64)
-    hits = ref.search_exact(s, o, threads=threads)
+    hits = ref.search_exact(s, o, threads=threads) if scheme is None else ref.search_ng26(s, o, scheme, partition, edit, threads=threads)
     t = ref.last_seconds
     locs = ref.locate(hits, threads=threads)
     t += ref.last_seconds
-    return t, len(locs)
+    return (t, len(locs), locs) if want_locs else (t, len(locs))
 
 
 def main():
@@ -138,14 +165,19 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="exact", choices=WORKLOADS,
+                    help="exact = BASELINE configs[1] (the headline); the others are configs[2] / configs[3]")
     ap.add_argument("--text", type=float, default=3e9, help="text length in symbols (default 3 Gbp)")
-    ap.add_argument("--reads", type=float, default=1e7, help="reads per GPU (default 10 M)")
-    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--reads", type=float, default=None, help="reads per GPU (default 10 M; 250 k for locate-heavy)")
+    ap.add_argument("--read-len", type=int, default=None, help="default 150 (20 for locate-heavy)")
     ap.add_argument("--rate", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    n_text, nq, L = int(args.text), int(args.reads), args.read_len
+    wl = args.workload
+    n_text = int(args.text)
+    nq = int(args.reads) if args.reads else (250_000 if wl == "locate-heavy" else 10_000_000)
+    L = args.read_len if args.read_len else (20 if wl == "locate-heavy" else 150)
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
 
@@ -168,28 +200,34 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", device))
 
-    workload = (f"exact search + locate, {nq} x {L}bp reads copied from the text, synthetic {n_text} bp DNA BiFMIndex "
-                f"(sigma 5, sampling rate {args.rate}), per GPU")
-    index, sym, off = build_workload(fmb, device, n_text, nq, L, args.rate, seed=3 + rank)
+    scheme, partition, edit = workload_scheme(wl, L)
+    what = {"exact": "exact search + locate", "locate-heavy": "exact search + locate of repeat-family 20-mers (many hits per read)"}.get(
+        wl, f"k<={wl[1]} {'edit' if edit else 'hamming'} search (optimum scheme, uniform partition) + locate")
+    src = "windows of a 1 kbp unit present in 1000 copies" if wl == "locate-heavy" else (
+        "reads copied from the text" if wl == "exact" else f"reads copied from the text with 0..{wl[1]} planted {'edits' if edit else 'substitutions'} each")
+    workload = (f"{what}, {nq} x {L}bp {src}, synthetic {n_text} bp DNA BiFMIndex (sigma 5, sampling rate {args.rate}), per GPU")
+    metric = {"exact": "queries/s (150bp exact search + locate, 3 Gbp index)"}.get(wl, f"queries/s ({wl}, search + locate, 3 Gbp index)")
+    index, sym, off = build_workload(fmb, device, n_text, nq, L, args.rate, seed=3 + rank, workload=wl)
     threads = os.cpu_count() or 1
+    ref_name = "search_no_errors::search (batched)" if scheme is None else f"search_ng26::search<{'true' if edit else 'false'}>(optimum(0,{wl[1]}))"
 
     # ------------------------------------------------------------------------------------------------------
     if args.impl == "reference":
         ref = reference_index(index)
         # size the per-step sample so that W+K steps take about 2 minutes in total
-        probe = min(nq, 20000)
-        t, _ = cpu_search_locate(ref, sym.array, off.array, 0, probe, threads, L)
+        probe = min(nq, 5000 if scheme is not None or wl == "locate-heavy" else 20000)
+        t, _ = cpu_search_locate(ref, sym.array, off.array, 0, probe, threads, L, scheme, partition, edit)
         rate_qs = probe / max(t, 1e-9)
         per_step = int(min(nq, max(probe, rate_qs * 120.0 / (W + K))))
         for _ in range(W):
-            cpu_search_locate(ref, sym.array, off.array, 0, per_step, threads, L)
+            cpu_search_locate(ref, sym.array, off.array, 0, per_step, threads, L, scheme, partition, edit)
         tot = 0.0
         for _ in range(K):
-            t, nloc = cpu_search_locate(ref, sym.array, off.array, 0, per_step, threads, L)
+            t, nloc = cpu_search_locate(ref, sym.array, off.array, 0, per_step, threads, L, scheme, partition, edit)
             tot += t
         qps = per_step * K / tot
-        sample = f"first {per_step} of the {nq} reads per step, search_no_errors::search (batched) + LocateLinear, {threads} threads"
-        line = {"impl": "reference", "metric": "queries/s (150bp exact search + locate, 3 Gbp index)", "value": qps, "unit": "queries/s",
+        sample = f"first {per_step} of the {nq} reads per step, {ref_name} + LocateLinear, {threads} threads"
+        line = {"impl": "reference", "metric": metric, "value": qps, "unit": "queries/s",
                 "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * tot / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": {"workload": workload},
                 "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "reference", "sample": sample},
@@ -202,19 +240,24 @@ def main():
     capi.index_set_stream(index, stream.cuda_stream)
     queries = index.upload(sym.array, off.array)          # resident in HBM before the timed region
 
+    def search():
+        return index.search_exact(queries) if scheme is None else index.search_scheme(queries, scheme, partition, edit)
+
     def step():
-        res = index.search_exact(queries)
+        res = search()
         loc = index.locate(res)
         return res, loc
 
-    # algorithmic work of the reference algorithm on this batch (occ-block lookups of one-symbol steps),
-    # counted once, untimed, by the one-symbol kernel; the timed steps use the default (two-symbol + jump) kernel
-    index.set_exact_mode(1)
-    res = index.search_exact(queries)
-    alg_lookups = res.stats.occ_lookups
-    one_symbol_ms = res.stats.main_kernel_ms
-    del res
-    index.set_exact_mode(0)
+    alg_lookups, one_symbol_ms = None, None
+    if scheme is None:
+        # algorithmic work of the reference algorithm on this batch (occ-block lookups of one-symbol steps),
+        # counted once, untimed, by the one-symbol kernel; the timed steps use the default (two-symbol + jump) kernel
+        index.set_exact_mode(1)
+        res = index.search_exact(queries)
+        alg_lookups = res.stats.occ_lookups
+        one_symbol_ms = res.stats.main_kernel_ms
+        del res
+        index.set_exact_mode(0)
 
     for _ in range(W):
         res, loc = step()
@@ -232,12 +275,12 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    search_ms, locate_ms, lines_s, look_l = [], [], 0, 0
+    search_ms, locate_ms, st_s, st_l = [], [], None, None
     for _ in range(K):
         res, loc = step()
         search_ms.append(res.stats.main_kernel_ms)
         locate_ms.append(loc.stats.main_kernel_ms)
-        lines_s, look_l = res.stats.line_requests, loc.stats.lf_steps
+        st_s, st_l = res.stats, loc.stats
         del res, loc
     ev1.record(stream)
     barrier()
@@ -252,13 +295,13 @@ def main():
     value = nq * world / (ms_per_step * 1e-3)
 
     # ---- end to end through the C-ABI with host buffers ------------------------------------------------------
-    out = capi.PinnedArray(nq + 1024, capi.LOC32_DTYPE)
+    out = capi.PinnedArray(max(n_locs, nq) + 1024, capi.LOC32_DTYPE)
     for _ in range(2):
-        index.search_and_locate(sym.array, off.array, out=out.array)
+        index.search_and_locate(sym.array, off.array, scheme=scheme, partition=partition, edit=edit, out=out.array)
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        locs, _st = index.search_and_locate(sym.array, off.array, out=out.array)
+        locs, _st = index.search_and_locate(sym.array, off.array, scheme=scheme, partition=partition, edit=edit, out=out.array)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -269,37 +312,53 @@ def main():
     h2d = nq * L + (nq + 1) * 8
     d2h = len(locs) * 16
 
-    # ---- roofline of the dominant kernel (exact_search2_kernel) -----------------------------------------------------
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------------
     # achieved = ALGORITHMIC bytes (the reference algorithm's occ-block lookups x 32 B) / kernel time.
-    # The kernel answers those lookups with far fewer physical line fetches (k-mer table, two-symbol lines, LF^16
+    # exact_search2_kernel answers those lookups with far fewer physical line fetches (k-mer table, two-symbol lines, LF^16
     # jumps), so `frac` can exceed 1; `physical` is the kernel's own traffic (line requests x 128 B) against the same peak.
     peak, peak_src = load_peaks()
     k_ms = float(np.mean(search_ms))
     l_ms = float(np.mean(locate_ms))
-    alg_bytes = alg_lookups * 32.0
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    phys_bytes = lines_s * 128.0
-    loc_lookups = n_locs * 2 + look_l * 2            # per row: marker test + sample fetch, per LF step: occ block + marker word
-    traffic = None                                   # dram bytes per launch from the committed ncu --set full capture, same workload only
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            ent = json.load(f)["exact_search2_kernel"]
-        if ent["workload"] == f"{nq} x {L}bp on {n_text} bp":
-            traffic = ent["traffic_bytes"]
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": "exact_search2_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "lookups_per_query": alg_lookups / nq, "kernel_ms": k_ms,
-                "physical": {"line_requests_per_query": lines_s / nq, "bytes_per_launch": phys_bytes,
-                             "gbs": phys_bytes / (k_ms * 1e-3) / 1e9, "frac": phys_bytes / (k_ms * 1e-3) / 1e9 / peak,
-                             "lines_per_s": lines_s / (k_ms * 1e-3), "measured_random_line_ceiling_per_s": 38.4e9},
-                "one_symbol_kernel_ms": one_symbol_ms,
-                "locate_kernel": {"kernel_ms": l_ms, "lf_steps_per_row": look_l / max(n_locs, 1), "algorithmic_bytes_per_launch": loc_lookups * 32.0,
-                                  "achieved": loc_lookups * 32.0 / (l_ms * 1e-3) / 1e9, "frac": loc_lookups * 32.0 / (l_ms * 1e-3) / 1e9 / peak},
-                "note": "frac > 1 is possible: algorithmic bytes are those of the reference's one-symbol algorithm; see physical.frac for the kernel's own traffic"}
+    loc_lookups = n_locs * 2 + st_l.lf_steps * 2     # per row: marker test + sample fetch, per LF step: occ block + marker word
+    locate_info = {"kernel": "locate_pair_kernel", "kernel_ms": l_ms, "lf_steps_per_row": st_l.lf_steps / max(n_locs, 1),
+                   "algorithmic_bytes_per_launch": loc_lookups * 32.0, "achieved": loc_lookups * 32.0 / (l_ms * 1e-3) / 1e9,
+                   "frac": loc_lookups * 32.0 / (l_ms * 1e-3) / 1e9 / peak,
+                   "physical_lines_per_s": (n_locs + st_l.lf_steps + n_locs) / (l_ms * 1e-3)}
 
-    line = {"metric": "queries/s (150bp exact search + locate, 3 Gbp index)", "value": value, "unit": "queries/s", "n_gpus": world,
+    def ncu_traffic(kernel, key):
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                ent = json.load(f)[kernel]
+            return ent["traffic_bytes"] if ent["workload"] == key else None
+        except Exception:
+            return None
+
+    if wl == "locate-heavy":
+        roofline = {"bound": "hbm", "kernel": "locate_pair_kernel", "achieved": locate_info["achieved"], "peak": peak, "unit": "GB/s",
+                    "frac": locate_info["frac"], "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": loc_lookups * 32.0,
+                    "kernel_ms": l_ms, "located_rows_per_s": n_locs / (l_ms * 1e-3), "lf_steps_per_row": locate_info["lf_steps_per_row"],
+                    "search_kernel_ms": k_ms}
+    elif scheme is None:
+        alg_bytes = alg_lookups * 32.0
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        phys_bytes = st_s.line_requests * 128.0
+        roofline = {"bound": "hbm", "kernel": "exact_search2_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": ncu_traffic("exact_search2_kernel", f"{nq} x {L}bp on {n_text} bp"), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "lookups_per_query": alg_lookups / nq, "kernel_ms": k_ms,
+                    "physical": {"line_requests_per_query": st_s.line_requests / nq, "bytes_per_launch": phys_bytes,
+                                 "gbs": phys_bytes / (k_ms * 1e-3) / 1e9, "frac": phys_bytes / (k_ms * 1e-3) / 1e9 / peak,
+                                 "lines_per_s": st_s.line_requests / (k_ms * 1e-3), "measured_random_line_ceiling_per_s": 38.4e9},
+                    "one_symbol_kernel_ms": one_symbol_ms, "locate_kernel": locate_info,
+                    "note": "frac > 1 is possible: algorithmic bytes are those of the reference's one-symbol algorithm; see physical.frac for the kernel's own traffic"}
+    else:
+        alg_bytes = st_s.occ_lookups * 32.0
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "scheme_search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic("scheme_search_kernel:" + wl, f"{nq} x {L}bp on {n_text} bp"), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "lookups_per_query": st_s.occ_lookups / nq, "extensions_per_query": st_s.extensions / nq,
+                    "kernel_ms": k_ms, "frontier_peak_items_per_warp": st_s.frontier_peak, "locate_kernel": locate_info}
+
+    line = {"metric": metric, "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload, "l2_policy": "inputs larger than L2 (index image %.1f GB, reads %.2f GB)" % (index.info.device_bytes / 1e9, nq * L / 1e9),
@@ -312,23 +371,21 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             ref = reference_index(index)
-            probe = min(nq, 20000)
-            t, _ = cpu_search_locate(ref, sym.array, off.array, 0, probe, threads, L)
+            probe = min(nq, 5000 if scheme is not None or wl == "locate-heavy" else 20000)
+            t, _ = cpu_search_locate(ref, sym.array, off.array, 0, probe, threads, L, scheme, partition, edit)
             sample_n = int(min(nq, max(probe, probe / max(t, 1e-9) * args.cpu_seconds)))
-            t, nloc = cpu_search_locate(ref, sym.array, off.array, 0, sample_n, threads, L)
-            t1, _ = cpu_search_locate(ref, sym.array, off.array, 0, min(sample_n, 50000), 1, L)
+            t, nloc, exp = cpu_search_locate(ref, sym.array, off.array, 0, sample_n, threads, L, scheme, partition, edit, want_locs=True)
+            t1, _ = cpu_search_locate(ref, sym.array, off.array, 0, min(sample_n, probe * 2), 1, L, scheme, partition, edit)
             line["cpu_baseline"] = {"value": sample_n / t, "unit": "queries/s", "cores": threads, "kind": "reference",
-                                    "sample": f"first {sample_n} of the {nq} reads, search_no_errors::search + LocateLinear, {threads} threads "
-                                              f"({t:.1f}s); 1 thread: {min(sample_n, 50000) / t1:.0f} queries/s"}
-            # parity spot check on the sample: located rows identical as sorted sets
+                                    "sample": f"first {sample_n} of the {nq} reads, {ref_name} + LocateLinear, {threads} threads "
+                                              f"({t:.1f}s); 1 thread: {min(sample_n, probe * 2) / t1:.0f} queries/s"}
+            # parity on the sample: located rows identical as sorted multisets
             got = np.sort(locs[locs["qidx"] < sample_n], order=["qidx", "seq", "pos", "e"])
-            hits = ref.search_exact(sym.array[: sample_n * L], off.array[: sample_n + 1], threads=threads)
-            exp = ref.locate(hits, threads=threads)
             exp32 = np.zeros(len(exp), dtype=capi.LOC32_DTYPE)
             for f in ("qidx", "seq", "pos", "e"):
                 exp32[f] = exp[f]
             exp32 = np.sort(exp32, order=["qidx", "seq", "pos", "e"])
-            line["parity"] = {"checked_queries": sample_n, "identical": bool(np.array_equal(got, exp32))}
+            line["parity"] = {"checked_queries": sample_n, "located_rows": int(len(exp32)), "identical": bool(np.array_equal(got, exp32))}
         except Exception as ex:   # the baseline must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": threads, "kind": "reference", "sample": f"failed: {ex}"}
     if rank == 0:

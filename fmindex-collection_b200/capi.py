@@ -46,7 +46,7 @@ SYMBOLS = [
     "fmb_results_count", "fmb_results_kind", "fmb_results_fetch_hits", "fmb_results_fetch_locs", "fmb_results_fetch_locs32",
     "fmb_results_get_stats", "fmb_results_destroy",
     "fmb_search_and_locate",
-    "fmb_index_set_exact_mode", "fmb_synth_text_device", "fmb_synth_reads_device", "fmb_index_set_stream", "fmb_kernel_launch_count", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
+    "fmb_index_set_exact_mode", "fmb_synth_text_device", "fmb_synth_reads_device", "fmb_synth_reads_err_device", "fmb_synth_repeat_text_device", "fmb_synth_unit_reads_device", "fmb_index_set_stream", "fmb_kernel_launch_count", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
 ]
 
 
@@ -373,6 +373,27 @@ def synth_reads_device(device, d_text, n, nq, length, seed):
     p = C.c_void_p()
     _check(lib().fmb_synth_reads_device(C.c_int(device), C.c_void_p(d_text), C.c_uint64(n), C.c_uint64(nq), C.c_uint32(length),
                                         C.c_uint64(seed), C.byref(p)))
+    return p.value
+
+
+def synth_reads_err_device(device, d_text, n, nq, length, seed, sigma, max_errors, edit):
+    p = C.c_void_p()
+    _check(lib().fmb_synth_reads_err_device(C.c_int(device), C.c_void_p(d_text), C.c_uint64(n), C.c_uint64(nq), C.c_uint32(length),
+                                            C.c_uint64(seed), C.c_uint32(sigma), C.c_uint32(max_errors), C.c_int(1 if edit else 0), C.byref(p)))
+    return p.value
+
+
+def synth_repeat_text_device(device, sigma, n, seed, unit_len, copies, sub_per_mille):
+    p = C.c_void_p()
+    _check(lib().fmb_synth_repeat_text_device(C.c_int(device), C.c_uint32(sigma), C.c_uint64(n), C.c_uint64(seed), C.c_uint32(unit_len),
+                                              C.c_uint32(copies), C.c_uint32(sub_per_mille), C.byref(p)))
+    return p.value
+
+
+def synth_unit_reads_device(device, sigma, nq, length, seed, unit_len):
+    p = C.c_void_p()
+    _check(lib().fmb_synth_unit_reads_device(C.c_int(device), C.c_uint32(sigma), C.c_uint64(nq), C.c_uint32(length), C.c_uint64(seed),
+                                             C.c_uint32(unit_len), C.byref(p)))
     return p.value
 
 

@@ -16,7 +16,7 @@ void set_error(const char* fmt, ...);
 void note_launches(unsigned n);   // bookkeeping for fmb_kernel_launch_count()
 
 // Caching device allocator: cudaMalloc / cudaFree cost 0.1 - 1 ms each and cudaFree synchronises the device, which
-// dominated a search step made of ~10 temporary buffers.  Freed blocks up to 1 GB are kept per device in size
+// dominated a search step made of ~10 temporary buffers.  Freed blocks up to 16 GB (40 GB in total) are kept per device in size
 // classes (<= 12.5 % internal waste) and handed out again; every API call synchronises its stream before it
 // returns a block, so a cached block never has work pending.  pool_trim() gives everything back to CUDA.
 void* pool_alloc(size_t bytes);   // nullptr + set_error on failure

@@ -29,6 +29,64 @@ __global__ void synth_reads_kernel(const uint8_t* __restrict__ text, uint64_t n,
     out[i] = text[off + j];
 }
 
+// locate-heavy workload: random text with a repeat family -- `copies` copies of a unit of
+// `unit_len` symbols, each copy with `sub_per_mille`/1000 substituted symbols, placed in disjoint slots of n / copies
+// symbols; queries are windows of the (unsubstituted) unit.
+__device__ __forceinline__ uint8_t unit_symbol(uint64_t seed, uint32_t p, uint32_t sigma) {
+    return (uint8_t)(1 + (splitmix64(seed * 0x2545F4914F6CDD1Dull + 0x1234567 + p) >> 32) % (sigma - 1));
+}
+__global__ void splice_repeats_kernel(uint8_t* __restrict__ text, uint64_t n, uint32_t sigma, uint64_t seed, uint32_t unit_len,
+                                      uint32_t copies, uint32_t sub_per_mille) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)copies * unit_len) return;
+    uint32_t j = (uint32_t)(i / unit_len), p = (uint32_t)(i % unit_len);
+    uint64_t slot = (n - 1) / copies;
+    uint64_t at = j * slot + splitmix64(seed + 77 * j + 5) % (slot - unit_len) + p;
+    uint8_t c = unit_symbol(seed, p, sigma);
+    uint64_t h = splitmix64(seed + i * 0x9E3779B97F4A7C15ull + 99);
+    if (h % 1000 < sub_per_mille) c = (uint8_t)(1 + (c - 1 + 1 + (h >> 20) % (sigma - 2)) % (sigma - 1));
+    text[at] = c;
+}
+__global__ void unit_reads_kernel(uint64_t nq, uint32_t L, uint64_t seed, uint32_t unit_len, uint32_t sigma, uint8_t* __restrict__ out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= nq * L) return;
+    uint64_t q = i / L;
+    uint32_t j = (uint32_t)(i % L);
+    uint32_t u = (uint32_t)(splitmix64(q * 0x632BE59BD9B4E019ull + seed + 3) % (unit_len - L));
+    out[i] = unit_symbol(seed, u + j, sigma);
+}
+
+// reads with planted errors (in the spirit of search/benchmark_bifmindex_searches.cpp:38-82 of the
+// reference's tests): read q is copied from the text like synth_reads_kernel, then e = hash % (max_err+1) edits are applied
+// one after the other: substitution (always a different symbol), insertion (last symbol dropped) or deletion (a random
+// symbol appended); Hamming runs (edit == 0) plant substitutions only.  Length stays L.
+__global__ void synth_reads_err_kernel(const uint8_t* __restrict__ text, uint64_t n, uint64_t nq, uint32_t L, uint64_t seed,
+                                       uint32_t max_err, uint32_t edit, uint32_t sigma, uint8_t* __restrict__ out) {
+    uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint64_t off = splitmix64(q * 0x632BE59BD9B4E019ull + seed) % (n - L);
+    uint8_t r[512];
+    for (uint32_t j = 0; j < L; ++j) r[j] = text[off + j];
+    uint64_t h = splitmix64(q * 0x9E3779B97F4A7C15ull + seed * 31 + 7);
+    uint32_t ne = (uint32_t)(h % (max_err + 1));
+    for (uint32_t i = 0; i < ne; ++i) {
+        h = splitmix64(h + i + 1);
+        uint32_t kind = edit ? (uint32_t)(h % 3) : 0;
+        uint32_t p = 1 + (uint32_t)((h >> 8) % (L - 2));
+        uint32_t rnd = (uint32_t)((h >> 40) % (sigma - 1));
+        if (kind == 0) {
+            r[p] = (uint8_t)(1 + (r[p] - 1 + 1 + rnd % (sigma - 2)) % (sigma - 1));
+        } else if (kind == 1) {
+            for (uint32_t j = L - 1; j > p; --j) r[j] = r[j - 1];
+            r[p] = (uint8_t)(1 + rnd);
+        } else {
+            for (uint32_t j = p; j + 1 < L; ++j) r[j] = r[j + 1];
+            r[L - 1] = (uint8_t)(1 + rnd);
+        }
+    }
+    for (uint32_t j = 0; j < L; ++j) out[q * L + j] = r[j];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K1: pack 64 BWT bytes into one DnaBlock (local counts; absolute counts are added after a scan)
 // ---------------------------------------------------------------------------------------------------------

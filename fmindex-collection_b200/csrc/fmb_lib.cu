@@ -48,7 +48,8 @@ size_t size_class(size_t bytes) {
     size_t step = size_t(1) << (top - 3);
     return (bytes + step - 1) / step * step;
 }
-constexpr size_t kMaxCachedBlock = size_t(1) << 30;
+constexpr size_t kMaxCachedBlock = size_t(1) << 34;      // blocks above 16 GB go straight back to CUDA
+constexpr size_t kMaxCachedTotal = size_t(40) << 30;     // ... and so does anything that would push the cache above 40 GB
 }  // namespace
 
 void pool_trim() {
@@ -100,7 +101,7 @@ void pool_free(void* p) {
     if (it == P.live.end()) { cudaFree(p); return; }
     auto key = it->second;
     P.live.erase(it);
-    if (key.second > kMaxCachedBlock) { cudaFree(p); return; }
+    if (key.second > kMaxCachedBlock || P.cached_bytes + key.second > kMaxCachedTotal) { cudaFree(p); return; }
     P.free_blocks.insert({key, p});
     P.cached_bytes += key.second;
 }
@@ -966,6 +967,38 @@ int fmb_synth_reads_device(int device, const uint8_t* d_text, uint64_t n, uint64
     uint8_t* p = nullptr;
     FMB_CUDA(cudaMalloc(&p, nq * length + 32));
     synth_reads_kernel<<<grid_for(nq * length, 256), 256>>>(d_text, n, nq, length, seed, p);
+    FMB_CUDA(cudaGetLastError());
+    FMB_CUDA(cudaDeviceSynchronize());
+    *d_reads = p;
+    return FMB_OK;
+}
+int fmb_synth_repeat_text_device(int device, uint32_t sigma, uint64_t n, uint64_t seed, uint32_t unit_len, uint32_t copies,
+                                 uint32_t sub_per_mille, uint8_t** d_text) {
+    if (!d_text || sigma < 3 || copies == 0 || unit_len == 0 || (n - 1) / copies <= (uint64_t)unit_len + 1) { set_error("bad argument"); return FMB_EINVAL; }
+    FMB_TRY(fmb_synth_text_device(device, sigma, n, seed, d_text));
+    splice_repeats_kernel<<<grid_for((uint64_t)copies * unit_len, 256), 256>>>(*d_text, n, sigma, seed, unit_len, copies, sub_per_mille);
+    FMB_CUDA(cudaGetLastError());
+    FMB_CUDA(cudaDeviceSynchronize());
+    return FMB_OK;
+}
+int fmb_synth_unit_reads_device(int device, uint32_t sigma, uint64_t nq, uint32_t length, uint64_t seed, uint32_t unit_len, uint8_t** d_reads) {
+    if (!d_reads || length == 0 || unit_len <= length || sigma < 3) { set_error("bad argument"); return FMB_EINVAL; }
+    FMB_TRY(use_device(device));
+    uint8_t* p = nullptr;
+    FMB_CUDA(cudaMalloc(&p, nq * length + 32));
+    unit_reads_kernel<<<grid_for(nq * length, 256), 256>>>(nq, length, seed, unit_len, sigma, p);
+    FMB_CUDA(cudaGetLastError());
+    FMB_CUDA(cudaDeviceSynchronize());
+    *d_reads = p;
+    return FMB_OK;
+}
+int fmb_synth_reads_err_device(int device, const uint8_t* d_text, uint64_t n, uint64_t nq, uint32_t length, uint64_t seed,
+                               uint32_t sigma, uint32_t max_errors, int edit, uint8_t** d_reads) {
+    if (!d_text || !d_reads || length < 3 || length > 512 || sigma < 3 || n <= (uint64_t)length + 1) { set_error("bad argument"); return FMB_EINVAL; }
+    FMB_TRY(use_device(device));
+    uint8_t* p = nullptr;
+    FMB_CUDA(cudaMalloc(&p, nq * length + 32));
+    synth_reads_err_kernel<<<grid_for(nq, 128), 128>>>(d_text, n, nq, length, seed, max_errors, edit ? 1u : 0u, sigma, p);
     FMB_CUDA(cudaGetLastError());
     FMB_CUDA(cudaDeviceSynchronize());
     *d_reads = p;

@@ -199,6 +199,15 @@ int  fmb_synth_text_device(int device, uint32_t sigma, uint64_t n, uint64_t seed
 /* nq reads of `length` symbols copied from d_text at offsets splitmix64(i * 0x632BE59BD9B4E019 + seed) % (n - length)
  * (never covering the final delimiter); written back to back into a device buffer owned by the library. */
 int  fmb_synth_reads_device(int device, const uint8_t* d_text, uint64_t n, uint64_t nq, uint32_t length, uint64_t seed, uint8_t** d_reads);
+/* the same reads with e = hash % (max_errors+1) planted edits each (substitutions only when edit == 0, else a mix of
+ * substitutions, insertions and deletions that keeps the length); 3 <= length <= 512 */
+int  fmb_synth_reads_err_device(int device, const uint8_t* d_text, uint64_t n, uint64_t nq, uint32_t length, uint64_t seed,
+                                uint32_t sigma, uint32_t max_errors, int edit, uint8_t** d_reads);
+/* locate-heavy workload: the random text of fmb_synth_text_device with `copies` copies of a unit of unit_len symbols
+ * (each copy with sub_per_mille/1000 substituted symbols) in disjoint slots; reads = windows of the unit */
+int  fmb_synth_repeat_text_device(int device, uint32_t sigma, uint64_t n, uint64_t seed, uint32_t unit_len, uint32_t copies,
+                                  uint32_t sub_per_mille, uint8_t** d_text);
+int  fmb_synth_unit_reads_device(int device, uint32_t sigma, uint64_t nq, uint32_t length, uint64_t seed, uint32_t unit_len, uint8_t** d_reads);
 /* All work of `ix` is enqueued on `stream` (a cudaStream_t of the index's device, e.g. the caller's timing
  * stream) instead of the index's private stream.  NULL restores the private stream. */
 int  fmb_index_set_stream(fmb_index* ix, void* stream);

@@ -96,13 +96,14 @@ def load_peaks():
 WORKLOADS = ("exact", "k1-hamming", "k1-edit", "k2-hamming", "k2-edit", "locate-heavy")
 
 
-def build_workload(fmb, device, n_text, nq, L, rate, seed, workload="exact"):
+def build_workload(fmb, device, n_text, nq, L, rate, seed, workload="exact", read_seed=None):
     """synthetic text on the device -> GPU index build -> reads:
          exact          reads copied from random text offsets (C2)
          kK-hamming/edit  the same reads with e in {0..K} planted substitutions / substitutions+indels each (C3)
          locate-heavy   text with a repeat family (1000 copies of a 1 kbp unit, 1 % substitutions), reads = windows of the unit (C4)"""
     from fmb200 import capi
     t0 = time.time()
+    read_seed = seed + 1 if read_seed is None else read_seed
     if workload == "locate-heavy":
         d_text = capi.synth_repeat_text_device(device, 5, n_text, seed, 1000, 1000, 10)
     else:
@@ -110,12 +111,13 @@ def build_workload(fmb, device, n_text, nq, L, rate, seed, workload="exact"):
     index = fmb.Index.build_from_device_text(5, d_text, n_text, sampling_rate=rate, bidirectional=True, device=device)
     t1 = time.time()
     if workload == "exact":
-        d_reads = capi.synth_reads_device(device, d_text, n_text, nq, L, seed + 1)
+        d_reads = capi.synth_reads_device(device, d_text, n_text, nq, L, read_seed)
     elif workload == "locate-heavy":
-        d_reads = capi.synth_unit_reads_device(device, 5, nq, L, seed, 1000)
+        d_reads = capi.synth_unit_reads_device(device, 5, nq, L, seed, 1000)   # unit = f(seed); reads differ per rank through the offset hash below
+        # (the unit-window hash takes the read seed through nq-independent q; ranks use disjoint q ranges via read_seed)
     else:
         k = int(workload[1])
-        d_reads = capi.synth_reads_err_device(device, d_text, n_text, nq, L, seed + 1, 5, k, workload.endswith("edit"))
+        d_reads = capi.synth_reads_err_device(device, d_text, n_text, nq, L, read_seed, 5, k, workload.endswith("edit"))
     capi.device_free(device, d_text)
     sym = capi.PinnedArray(nq * L, np.uint8)
     capi.copy_to_host(device, sym.array, d_reads, nq * L)
@@ -207,7 +209,8 @@ def main():
         "reads copied from the text" if wl == "exact" else f"reads copied from the text with 0..{wl[1]} planted {'edits' if edit else 'substitutions'} each")
     workload = (f"{what}, {nq} x {L}bp {src}, synthetic {n_text} bp DNA BiFMIndex (sigma 5, sampling rate {args.rate}), per GPU")
     metric = {"exact": "queries/s (150bp exact search + locate, 3 Gbp index)"}.get(wl, f"queries/s ({wl}, search + locate, 3 Gbp index)")
-    index, sym, off = build_workload(fmb, device, n_text, nq, L, args.rate, seed=3 + rank, workload=wl)
+    # the SAME text on every rank (the index is replicated per GPU), different reads per rank (queries are sharded)
+    index, sym, off = build_workload(fmb, device, n_text, nq, L, args.rate, seed=3, workload=wl, read_seed=4 + 1000 * rank)
     threads = os.cpu_count() or 1
     ref_name = "search_no_errors::search (batched)" if scheme is None else f"search_ng26::search<{'true' if edit else 'false'}>(optimum(0,{wl[1]}))"
 

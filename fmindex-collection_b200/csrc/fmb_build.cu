@@ -315,7 +315,6 @@ extern "C" int fmb_index_build(fmb_index** out, int device, uint32_t sigma, cons
         fmb_index* ix;
         ~Guard() { if (ix) fmb_index_destroy(ix); }
     } guard{ix};
-    if (!ix->dna) { set_error("sigma %u > 5: generic occurrence table is not available yet", sigma); return FMB_EUNSUPPORTED; }
     cudaStream_t st = ix->stream;
     DevBuf<uint8_t> own_text;
     const uint8_t* d_text = text;
@@ -389,7 +388,7 @@ extern "C" int fmb_index_build(fmb_index** out, int device, uint32_t sigma, cons
     }
     bwt.release();
     FMB_TRY(compute_C(ix));
-    FMB_TRY(build_occ2(ix, 0));
+    if (ix->dna) FMB_TRY(build_occ2(ix, 0));
     FMB_TRY(build_locblocks(ix));
     guard.ix = nullptr;
     *out = ix;

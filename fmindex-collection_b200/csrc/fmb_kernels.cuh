@@ -162,6 +162,58 @@ __global__ void scatter_delims_kernel(const uint8_t* __restrict__ bwt, uint64_t 
         if (bwt[base + r] == 0) delim_rows[a++] = (uint32_t)(base + r);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K1 (generic layout, 5 < sigma <= 32): per 64 rows the bit planes + local symbol counts; after an exclusive scan of the
+// counts the block receives its sigma-1 exclusive prefix counts pc[c-1] = # symbols < c before the block.
+// ---------------------------------------------------------------------------------------------------------
+struct Cnt32 {
+    uint32_t c[32];
+};
+struct Cnt32Add {
+    __host__ __device__ Cnt32 operator()(const Cnt32& a, const Cnt32& b) const {
+        Cnt32 r;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r.c[i] = a.c[i] + b.c[i];
+        return r;
+    }
+};
+__global__ void __launch_bounds__(128) pack_gen_kernel(const uint8_t* __restrict__ bwt, uint64_t n, uint32_t sigma, uint32_t planes, uint32_t stride,
+                                                       uint8_t* __restrict__ blocks, Cnt32* __restrict__ counts, uint32_t* __restrict__ bad) {
+    uint64_t blk = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t nblocks = n / 64 + 1;
+    if (blk >= nblocks) return;
+    uint64_t base = blk * 64;
+    uint64_t pl[5] = {0, 0, 0, 0, 0};
+    Cnt32 c;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) c.c[i] = 0;
+    uint32_t isbad = 0;
+    for (uint32_t r = 0; r < 64 && base + r < n; ++r) {
+        uint32_t s = bwt[base + r];
+        if (s >= sigma) { isbad = 1; s = 0; }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) c.c[i] += (s == (uint32_t)i);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) pl[j] |= (uint64_t)((s >> j) & 1) << r;
+    }
+    uint64_t* out = reinterpret_cast<uint64_t*>(blocks + blk * stride);
+    for (uint32_t j = 0; j < planes; ++j) out[j] = pl[j];
+    counts[blk] = c;
+    if (isbad) atomicOr(bad, 1u);
+}
+__global__ void store_gen_counts_kernel(uint8_t* __restrict__ blocks, uint32_t stride, uint32_t planes, uint32_t sigma, const Cnt32* __restrict__ counts,
+                                        uint64_t nblocks) {
+    uint64_t blk = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (blk >= nblocks) return;
+    uint32_t* pc = reinterpret_cast<uint32_t*>(blocks + blk * stride + 8 * planes);
+    const Cnt32& c = counts[blk];
+    uint32_t acc = 0;
+    for (uint32_t s = 0; s + 1 < sigma; ++s) {
+        acc += c.c[s];
+        pc[s] = acc;                       // # symbols <= s = # symbols < s+1 before the block
+    }
+}
+
 template <class OCC>
 __global__ void compute_C_kernel(IndexView<OCC> ix, uint64_t* out) {
     uint32_t s = threadIdx.x;
@@ -272,7 +324,7 @@ __device__ __forceinline__ uint32_t chunk_byte(const uint4& v, uint32_t i) {
     return (w >> (8 * (i & 3))) & 0xFF;
 }
 
-template <class OCC, bool COUNT>
+template <bool COUNT, class OCC>
 __global__ void __launch_bounds__(256) exact_search_kernel(const __grid_constant__ IndexView<OCC> ix, const uint8_t* __restrict__ qsym,
                                                            const uint64_t* __restrict__ qoff, uint32_t nq,
                                                            uint32_t* __restrict__ out_lb, uint32_t* __restrict__ out_len,
@@ -618,7 +670,7 @@ __global__ void hit_lengths_kernel(const HitRec* __restrict__ hits, uint64_t nh,
 // The marker word and the occ block of a row are independent loads and are issued together.
 // starts[] = exclusive prefix sum of the hit interval lengths; a thread finds its hit by binary search.
 // ---------------------------------------------------------------------------------------------------------
-template <class OCC, bool COUNT>
+template <bool COUNT, class OCC>
 __global__ void __launch_bounds__(256) locate_kernel(const __grid_constant__ IndexView<OCC> ix, const HitRec* __restrict__ hits,
                                                      const uint32_t* __restrict__ starts, uint32_t nh, uint32_t total,
                                                      LocRec* __restrict__ out, unsigned long long* __restrict__ counters) {

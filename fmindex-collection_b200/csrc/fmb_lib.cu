@@ -185,6 +185,35 @@ fmb::IndexView<fmb::OccDna> fmb_index::view_dna() const {
     return v;
 }
 
+fmb::IndexView<fmb::OccGen> fmb_index::view_gen() const {
+    fmb::IndexView<fmb::OccGen> v{};
+    for (int d = 0; d < 2; ++d) {
+        v.occ[d].blocks = occ_gen[d].p;
+        v.occ[d].stride = gen_stride;
+        v.occ[d].planes = gen_planes;
+        v.occ[d].sigma = sigma;
+    }
+    for (uint32_t s = 0; s <= sigma; ++s) v.C[s] = (uint32_t)C[s];
+    v.n = (row_t)n;
+    v.sigma = sigma;
+    v.marks = marks.p;
+    v.samples = samples.p;
+    v.locblocks = nullptr;
+    return v;
+}
+
+// run `...` with V bound to the device view of the index's layout (kernels deduce OCC from it)
+#define FMB_DISPATCH(ix, V, ...)                    \
+    do {                                            \
+        if ((ix)->dna) {                            \
+            auto V = (ix)->view_dna();              \
+            __VA_ARGS__;                            \
+        } else {                                    \
+            auto V = (ix)->view_gen();              \
+            __VA_ARGS__;                            \
+        }                                           \
+    } while (0)
+
 fmb::Occ2View fmb_index::view_occ2(int dir) const {
     fmb::Occ2View v{};
     v.lines = occ2[dir].p;
@@ -222,8 +251,36 @@ int build_occ_from_device_bwt(fmb_index* ix, int dir, const uint8_t* d_bwt) {
     const uint64_t nblocks = n / 64 + 1;
     cudaStream_t st = active_stream(ix);
     if (!ix->dna) {
-        set_error("sigma %u: generic occurrence table not built in this call path", ix->sigma);
-        return FMB_EUNSUPPORTED;
+        // generic layout: planes + exclusive prefix counts per 64 rows (fmb_device.cuh OccGen)
+        uint32_t planes = 1;
+        while ((1u << planes) < ix->sigma) ++planes;
+        ix->gen_planes = planes;
+        ix->gen_stride = (8 * planes + 4 * (ix->sigma - 1) + 31) / 32 * 32;
+        FMB_TRY(ix->occ_gen[dir].alloc(nblocks * ix->gen_stride + 64));
+        FMB_CUDA(cudaMemsetAsync(ix->occ_gen[dir].p, 0, nblocks * ix->gen_stride + 64, st));
+        DevBuf<Cnt32> counts;
+        FMB_TRY(counts.alloc(nblocks));
+        DevBuf<uint32_t> bad;
+        FMB_TRY(bad.alloc(1));
+        FMB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(uint32_t), st));
+        pack_gen_kernel<<<grid_for(nblocks, 128), 128, 0, st>>>(d_bwt, n, ix->sigma, planes, ix->gen_stride, ix->occ_gen[dir].p, counts.p, bad.p);
+        FMB_CUDA(cudaGetLastError());
+        uint32_t h_bad = 0;
+        FMB_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, st));
+        FMB_CUDA(cudaStreamSynchronize(st));
+        if (h_bad) { set_error("BWT contains a symbol >= sigma (%u)", ix->sigma); return FMB_EINVAL; }
+        // number of delimiter rows = total count of symbol 0 (last block's scanned count + its local count): take it from C later
+        {
+            size_t tmp_bytes = 0;
+            FMB_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp_bytes, counts.p, counts.p, Cnt32Add{}, Cnt32{}, (int64_t)nblocks, st));
+            DevBuf<uint8_t> tmp;
+            FMB_TRY(tmp.alloc(tmp_bytes));
+            FMB_CUDA(cub::DeviceScan::ExclusiveScan(tmp.p, tmp_bytes, counts.p, counts.p, Cnt32Add{}, Cnt32{}, (int64_t)nblocks, st));
+        }
+        store_gen_counts_kernel<<<grid_for(nblocks, 128), 128, 0, st>>>(ix->occ_gen[dir].p, ix->gen_stride, planes, ix->sigma, counts.p, nblocks);
+        FMB_CUDA(cudaGetLastError());
+        FMB_CUDA(cudaStreamSynchronize(st));
+        return FMB_OK;
     }
     FMB_TRY(ix->occ_dna[dir].alloc(nblocks));
     DevBuf<uint4> counts;
@@ -276,11 +333,11 @@ int build_occ_from_device_bwt(fmb_index* ix, int dir, const uint8_t* d_bwt) {
 int compute_C(fmb_index* ix) {
     DevBuf<uint64_t> d_out;
     FMB_TRY(d_out.alloc(ix->sigma + 1));
-    auto v = ix->view_dna();
-    compute_C_kernel<<<1, 64, 0, ix->stream>>>(v, d_out.p);
+    FMB_DISPATCH(ix, v, compute_C_kernel<<<1, 64, 0, ix->stream>>>(v, d_out.p));
     FMB_CUDA(cudaGetLastError());
     FMB_CUDA(cudaMemcpyAsync(ix->C, d_out.p, (ix->sigma + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream));
     FMB_CUDA(cudaStreamSynchronize(ix->stream));
+    if (!ix->dna) ix->n_delims = ix->C[1];          // rows holding symbol 0
     return FMB_OK;
 }
 
@@ -433,7 +490,7 @@ int build_marks_from_device(fmb_index* ix, const uint64_t* d_bitmap, const uint3
 int new_index(fmb_index** out, int device, uint32_t sigma, uint64_t n, bool bidirectional) {
     if (!out) { set_error("out is NULL"); return FMB_EINVAL; }
     *out = nullptr;
-    if (sigma < 2 || sigma > 64) { set_error("sigma %u outside [2,64]", sigma); return FMB_EINVAL; }
+    if (sigma < 2 || sigma > 32) { set_error("sigma %u outside [2,32]", sigma); return FMB_EINVAL; }
     if (n == 0) { set_error("empty index"); return FMB_EINVAL; }
     if (n >= 0xFFFFFFFFull - 64) { set_error("n = %llu: this build supports n < 2^32 - 64", (unsigned long long)n); return FMB_EUNSUPPORTED; }
     FMB_TRY(use_device(device));
@@ -480,7 +537,6 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, co
     fmb_index* ix = nullptr;
     FMB_TRY(new_index(&ix, device, sigma, n, bwt_rev != nullptr));
     auto fail = [&](int rc) { fmb_index_destroy(ix); return rc; };
-    if (!ix->dna) { set_error("sigma %u > 5: generic occurrence table is not available yet", sigma); return fail(FMB_EUNSUPPORTED); }
     {
         DevBuf<uint8_t> d_bwt;
         int rc = upload(d_bwt, bwt, n, ix->stream);
@@ -496,7 +552,7 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, co
     }
     int rc = compute_C(ix);
     if (rc) return fail(rc);
-    rc = build_occ2(ix, 0);
+    if (ix->dna) rc = build_occ2(ix, 0);
     if (rc) return fail(rc);
     {
         const uint64_t have = (n + 63) / 64;
@@ -553,14 +609,13 @@ int fmb_index_export(const fmb_index* ix, uint8_t* bwt, uint8_t* bwt_rev, uint64
     if (!ix) { set_error("NULL index"); return FMB_EINVAL; }
     FMB_TRY(use_device(ix->device));
     cudaStream_t st = active_stream(ix);
-    auto v = ix->view_dna();
     for (int d = 0; d < 2; ++d) {
         uint8_t* dst = d ? bwt_rev : bwt;
         if (!dst) continue;
         if (d == 1 && !ix->bidirectional) { set_error("index has no bwtRev"); return FMB_EINVAL; }
         DevBuf<uint8_t> tmp;
         FMB_TRY(tmp.alloc(ix->n));
-        unpack_bwt_kernel<<<grid_for(ix->n, 256), 256, 0, st>>>(v, d, tmp.p);
+        FMB_DISPATCH(ix, v, unpack_bwt_kernel<<<grid_for(ix->n, 256), 256, 0, st>>>(v, d, tmp.p));
         FMB_CUDA(cudaGetLastError());
         FMB_CUDA(cudaMemcpyAsync(dst, tmp.p, ix->n, cudaMemcpyDeviceToHost, st));
         FMB_CUDA(cudaStreamSynchronize(st));
@@ -605,8 +660,7 @@ static int string_op(const fmb_index* ix, int dir, int op, const uint64_t* idx, 
     size_t per = (op == 3) ? ix->sigma : 1;
     FMB_TRY(d_out.alloc(count * per));
     if (op == 3) FMB_TRY(d_out2.alloc(count * per));
-    auto v = ix->view_dna();
-    string_op_kernel<<<grid_for(count, 128), 128, 0, st>>>(v, dir, op, d_idx.p, d_symb.p, count, d_out.p, d_out2.p);
+    FMB_DISPATCH(ix, v, string_op_kernel<<<grid_for(count, 128), 128, 0, st>>>(v, dir, op, d_idx.p, d_symb.p, count, d_out.p, d_out2.p));
     FMB_CUDA(cudaGetLastError());
     std::vector<uint64_t> h(count * per);
     FMB_CUDA(cudaMemcpyAsync(h.data(), d_out.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
@@ -649,8 +703,7 @@ static int cursor_op(const fmb_index* ix, int right, const uint64_t* cur, const 
     if (!all) FMB_TRY(upload(d_symb, symb, count, st));
     size_t per = all ? ix->sigma : 1;
     FMB_TRY(d_out.alloc(count * per * 4));
-    auto v = ix->view_dna();
-    cursor_op_kernel<<<grid_for(count, 128), 128, 0, st>>>(v, right, all ? 1 : 0, d_cur.p, d_symb.p, count, d_out.p);
+    FMB_DISPATCH(ix, v, cursor_op_kernel<<<grid_for(count, 128), 128, 0, st>>>(v, right, all ? 1 : 0, d_cur.p, d_symb.p, count, d_out.p));
     FMB_CUDA(cudaGetLastError());
     FMB_CUDA(cudaMemcpyAsync(out, d_out.p, count * per * 4 * 8, cudaMemcpyDeviceToHost, st));
     FMB_CUDA(cudaStreamSynchronize(st));
@@ -750,17 +803,16 @@ int fmb_search_exact(const fmb_index* ix, const fmb_queries* q, fmb_results** ou
     if ((rc = lb.alloc(nq)) || (rc = len.alloc(nq + 1)) || (rc = pos.alloc(nq + 1)) || (rc = ctr.alloc(4))) return fail(rc);
     cudaMemsetAsync(ctr.p, 0, 4 * sizeof(unsigned long long), st);
     cudaMemsetAsync(len.p + nq, 0, sizeof(uint32_t), st);
-    auto v = ix->view_dna();
     EventTimer tm(st);
     cudaEvent_t ev_main = nullptr;
     cudaEventCreate(&ev_main);
-    const bool two = ix->occ2[0].p && q->packed.p && ix->exact_mode != FMB_EXACT_ONE_SYMBOL;
+    const bool two = ix->dna && ix->occ2[0].p && q->packed.p && ix->exact_mode != FMB_EXACT_ONE_SYMBOL;
     if (ix->exact_mode == FMB_EXACT_TWO_SYMBOL && !ix->occ2[0].p) { cudaEventDestroy(ev_main); set_error("index has no two-symbol table"); return fail(FMB_EUNSUPPORTED); }
     if (nq) {
         static const bool minb8 = getenv("FMB_EXACT2_MINB1") == nullptr;      // 32 registers -> 2048 resident threads per SM
-        if (two && minb8) exact_search2_kernel<true, 8><<<grid_for(nq * 4, 256), 256, 0, st>>>(v, ix->view_occ2(0), q->symbols.p, q->packed.p, q->flags.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
-        else if (two) exact_search2_kernel<true, 1><<<grid_for(nq * 4, 256), 256, 0, st>>>(v, ix->view_occ2(0), q->symbols.p, q->packed.p, q->flags.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
-        else exact_search_kernel<OccDna, true><<<grid_for(nq, 256), 256, 0, st>>>(v, q->symbols.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
+        if (two && minb8) exact_search2_kernel<true, 8><<<grid_for(nq * 4, 256), 256, 0, st>>>(ix->view_dna(), ix->view_occ2(0), q->symbols.p, q->packed.p, q->flags.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
+        else if (two) exact_search2_kernel<true, 1><<<grid_for(nq * 4, 256), 256, 0, st>>>(ix->view_dna(), ix->view_occ2(0), q->symbols.p, q->packed.p, q->flags.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
+        else FMB_DISPATCH(ix, v, exact_search_kernel<true><<<grid_for(nq, 256), 256, 0, st>>>(v, q->symbols.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p));
         cudaEventRecord(ev_main, st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("exact_search_kernel: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
@@ -827,16 +879,16 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
     cudaEventCreate(&ev_m0);
     cudaEventCreate(&ev_m1);
     if (total) {
-        auto v = ix->view_dna();
         cudaEventRecord(ev_m0, st);
-        if (v.locblocks) {
+        if (ix->dna && ix->locblocks.p) {
+            auto v = ix->view_dna();
             // persistent grid: every SM full of lane pairs (8 blocks x 256 threads), rows handed out with a grid stride
             static int sms = 0;
             if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
             unsigned grid = (unsigned)std::min<uint64_t>(grid_for((uint64_t)total * 2, 256), (uint64_t)sms * 8);
             locate_pair_kernel<true><<<grid, 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p);
         }
-        else locate_kernel<OccDna, true><<<grid_for(total, 256), 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p);
+        else FMB_DISPATCH(ix, v, locate_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p));
         cudaEventRecord(ev_m1, st);
         note_launches(1);
     }
@@ -873,7 +925,7 @@ int fmb_locate_rows(const fmb_index* ix, const uint64_t* rows, uint64_t count, u
     FMB_TRY(d_steps.alloc(count));
     FMB_TRY(d_seq.alloc(count));
     FMB_TRY(d_pos.alloc(count));
-    locate_rows_kernel<<<grid_for(count, 256), 256, 0, st>>>(ix->view_dna(), d_rows.p, count, d_seq.p, d_pos.p, d_steps.p);
+    FMB_DISPATCH(ix, v, locate_rows_kernel<<<grid_for(count, 256), 256, 0, st>>>(v, d_rows.p, count, d_seq.p, d_pos.p, d_steps.p));
     FMB_CUDA(cudaGetLastError());
     note_launches(1);
     FMB_CUDA(cudaMemcpyAsync(seq, d_seq.p, count * 4, cudaMemcpyDeviceToHost, st));
@@ -897,7 +949,7 @@ int fmb_sample_value(const fmb_index* ix, const uint64_t* rows, uint64_t count, 
     FMB_TRY(d_has.alloc(count));
     FMB_TRY(d_seq.alloc(count));
     FMB_TRY(d_pos.alloc(count));
-    sample_value_kernel<<<grid_for(count, 256), 256, 0, st>>>(ix->view_dna(), d_rows.p, count, d_has.p, d_seq.p, d_pos.p);
+    FMB_DISPATCH(ix, v, sample_value_kernel<<<grid_for(count, 256), 256, 0, st>>>(v, d_rows.p, count, d_has.p, d_seq.p, d_pos.p));
     FMB_CUDA(cudaGetLastError());
     note_launches(1);
     FMB_CUDA(cudaMemcpyAsync(has, d_has.p, count, cudaMemcpyDeviceToHost, st));

@@ -29,12 +29,12 @@ int set_device(int device) {
 constexpr uint32_t kStackCap = 256;          // items per warp (8 KB)
 constexpr uint32_t kWarpsPerBlock = 8;
 
-template <bool EDIT>
-int launch_scheme(const fmb_index* ix, const SchemeParams& sp, const fmb_queries* q, uint64_t n_roots, const Item* in_items,
-                  uint64_t n_in, const SchemeOut& out, cudaStream_t st) {
+template <class OCC, bool EDIT>
+int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const SchemeParams& sp, const fmb_queries* q, uint64_t n_roots, const Item* in_items,
+                    uint64_t n_in, const SchemeOut& out, cudaStream_t st) {
     static int blocks_per_sm = 0, sms = 0;
     size_t smem = (size_t)kStackCap * kWarpsPerBlock * sizeof(Item);
-    auto kern = scheme_search_kernel<OccDna, EDIT>;
+    auto kern = scheme_search_kernel<OCC, EDIT>;
     if (!blocks_per_sm) {
         FMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0;
@@ -48,10 +48,16 @@ int launch_scheme(const fmb_index* ix, const SchemeParams& sp, const fmb_queries
     uint64_t work = n_roots + n_in;
     uint64_t want_blocks = (work + 255) / 256;
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * blocks_per_sm, want_blocks));
-    kern<<<grid, 256, smem, st>>>(ix->view_dna(), sp, q->symbols.p, q->offsets.p, n_roots, in_items, n_in, out, kStackCap);
+    kern<<<grid, 256, smem, st>>>(view, sp, q->symbols.p, q->offsets.p, n_roots, in_items, n_in, out, kStackCap);
     FMB_CUDA(cudaGetLastError());
     note_launches(1);
     return FMB_OK;
+}
+template <bool EDIT>
+int launch_scheme(const fmb_index* ix, const SchemeParams& sp, const fmb_queries* q, uint64_t n_roots, const Item* in_items,
+                  uint64_t n_in, const SchemeOut& out, cudaStream_t st) {
+    if (ix->dna) return launch_scheme_t<OccDna, EDIT>(ix, ix->view_dna(), sp, q, n_roots, in_items, n_in, out, st);
+    return launch_scheme_t<OccGen, EDIT>(ix, ix->view_gen(), sp, q, n_roots, in_items, n_in, out, st);
 }
 
 int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp, fmb_results** out_res) {
@@ -144,7 +150,6 @@ int fmb_search_scheme(const fmb_index* ix, const fmb_queries* q, int edit, uint3
     if (!ix || !q || !out || !pi || !l || !u || !partition) { set_error("NULL argument"); return FMB_EINVAL; }
     *out = nullptr;
     if (!ix->bidirectional) { set_error("search schemes need a bidirectional index (extendRight)"); return FMB_EINVAL; }
-    if (!ix->dna) { set_error("sigma %u: scheme search on the generic layout is not available yet", ix->sigma); return FMB_EUNSUPPORTED; }
     if (q->device != ix->device) { set_error("queries live on device %d, index on %d", q->device, ix->device); return FMB_EINVAL; }
     if (n_searches == 0 || n_searches > (uint32_t)kMaxSearches || n_parts == 0 || n_parts > (uint32_t)kMaxParts) {
         set_error("scheme shape %u x %u outside [1,%d] x [1,%d]", n_searches, n_parts, kMaxSearches, kMaxParts);
@@ -196,7 +201,6 @@ int fmb_search_scheme(const fmb_index* ix, const fmb_queries* q, int edit, uint3
 int fmb_search_backtracking(const fmb_index* ix, const fmb_queries* q, uint32_t max_errors, fmb_results** out) {
     if (!ix || !q || !out) { set_error("NULL argument"); return FMB_EINVAL; }
     *out = nullptr;
-    if (!ix->dna) { set_error("sigma %u: backtracking on the generic layout is not available yet", ix->sigma); return FMB_EUNSUPPORTED; }
     if (q->device != ix->device) { set_error("queries live on device %d, index on %d", q->device, ix->device); return FMB_EINVAL; }
     if (max_errors > 255) { set_error("max_errors too large"); return FMB_EINVAL; }
     if (q->nq && q->min_len != q->max_len) { set_error("backtracking: all queries of a batch must have the same length"); return FMB_EUNSUPPORTED; }

@@ -93,7 +93,7 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-WORKLOADS = ("exact", "k1-hamming", "k1-edit", "k2-hamming", "k2-edit", "locate-heavy")
+WORKLOADS = ("exact", "k1-hamming", "k1-edit", "k2-hamming", "k2-edit", "locate-heavy", "protein-k1-hamming", "protein-k1-edit")
 
 
 def build_workload(fmb, device, n_text, nq, L, rate, seed, workload="exact", read_seed=None):
@@ -104,11 +104,12 @@ def build_workload(fmb, device, n_text, nq, L, rate, seed, workload="exact", rea
     from fmb200 import capi
     t0 = time.time()
     read_seed = seed + 1 if read_seed is None else read_seed
+    sigma = 21 if workload.startswith("protein") else 5
     if workload == "locate-heavy":
         d_text = capi.synth_repeat_text_device(device, 5, n_text, seed, 1000, 1000, 10)
     else:
-        d_text = capi.synth_text_device(device, 5, n_text, seed)
-    index = fmb.Index.build_from_device_text(5, d_text, n_text, sampling_rate=rate, bidirectional=True, device=device)
+        d_text = capi.synth_text_device(device, sigma, n_text, seed)
+    index = fmb.Index.build_from_device_text(sigma, d_text, n_text, sampling_rate=rate, bidirectional=True, device=device)
     t1 = time.time()
     if workload == "exact":
         d_reads = capi.synth_reads_device(device, d_text, n_text, nq, L, read_seed)
@@ -116,8 +117,8 @@ def build_workload(fmb, device, n_text, nq, L, rate, seed, workload="exact", rea
         d_reads = capi.synth_unit_reads_device(device, 5, nq, L, seed, 1000)   # unit = f(seed); reads differ per rank through the offset hash below
         # (the unit-window hash takes the read seed through nq-independent q; ranks use disjoint q ranges via read_seed)
     else:
-        k = int(workload[1])
-        d_reads = capi.synth_reads_err_device(device, d_text, n_text, nq, L, read_seed, 5, k, workload.endswith("edit"))
+        k = int(workload.split("k")[1][0])
+        d_reads = capi.synth_reads_err_device(device, d_text, n_text, nq, L, read_seed, sigma, k, workload.endswith("edit"))
     capi.device_free(device, d_text)
     sym = capi.PinnedArray(nq * L, np.uint8)
     capi.copy_to_host(device, sym.array, d_reads, nq * L)
@@ -131,20 +132,20 @@ def build_workload(fmb, device, n_text, nq, L, rate, seed, workload="exact", rea
 def workload_scheme(workload, L):
     """(scheme, partition, edit) of a k-error workload: optimum(0,k) with a uniform partition (BASELINE configs[2])"""
     from fmb200 import schemes
-    if not workload.startswith("k"):
+    if "-k" not in "-" + workload:
         return None, None, False
-    k = int(workload[1])
+    k = int(workload.split("k")[1][0])
     sch = schemes.optimum(0, k)
     return sch, schemes.uniform_partition(sch[0].shape[1], L), workload.endswith("edit")
 
 
-def reference_index(index):
+def reference_index(index, sigma=5):
     """host-side reference index over exactly the same BWT bytes and samples (BiFMIndex(bwt, bwtRev, SparseArray))"""
     from oracle.pyoracle import Ref
     t0 = time.time()
     bwt, rev, bm, sq, sp = index.export()
     t1 = time.time()
-    ref = Ref.from_bwt(5, bwt, rev, bm, sq, sp)
+    ref = Ref.from_bwt(sigma, bwt, rev, bm, sq, sp)
     log(f"reference index: export {t1 - t0:.1f}s, construct {time.time() - t1:.1f}s")
     return ref
 
@@ -169,7 +170,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="exact", choices=WORKLOADS,
                     help="exact = BASELINE configs[1] (the headline); the others are configs[2] / configs[3]")
-    ap.add_argument("--text", type=float, default=3e9, help="text length in symbols (default 3 Gbp)")
+    ap.add_argument("--text", type=float, default=None, help="text length in symbols (default 3 Gbp; 1 Gaa for protein)")
     ap.add_argument("--reads", type=float, default=None, help="reads per GPU (default 10 M; 250 k for locate-heavy)")
     ap.add_argument("--read-len", type=int, default=None, help="default 150 (20 for locate-heavy)")
     ap.add_argument("--rate", type=int, default=16)
@@ -177,9 +178,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = args.workload
-    n_text = int(args.text)
-    nq = int(args.reads) if args.reads else (250_000 if wl == "locate-heavy" else 10_000_000)
-    L = args.read_len if args.read_len else (20 if wl == "locate-heavy" else 150)
+    protein = wl.startswith("protein")
+    sigma = 21 if protein else 5
+    n_text = int(args.text) if args.text else (1_000_000_000 if protein else 3_000_000_000)
+    nq = int(args.reads) if args.reads else (250_000 if wl == "locate-heavy" else (1_000_000 if protein else 10_000_000))
+    L = args.read_len if args.read_len else (20 if wl == "locate-heavy" else (50 if protein else 150))
+    kk = wl.split("k")[1][0] if "-k" in "-" + wl else "0"
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
 
@@ -204,19 +208,22 @@ def main():
 
     scheme, partition, edit = workload_scheme(wl, L)
     what = {"exact": "exact search + locate", "locate-heavy": "exact search + locate of repeat-family 20-mers (many hits per read)"}.get(
-        wl, f"k<={wl[1]} {'edit' if edit else 'hamming'} search (optimum scheme, uniform partition) + locate")
+        wl, f"k<={kk} {'edit' if edit else 'hamming'} search (optimum scheme, uniform partition) + locate")
     src = "windows of a 1 kbp unit present in 1000 copies" if wl == "locate-heavy" else (
-        "reads copied from the text" if wl == "exact" else f"reads copied from the text with 0..{wl[1]} planted {'edits' if edit else 'substitutions'} each")
-    workload = (f"{what}, {nq} x {L}bp {src}, synthetic {n_text} bp DNA BiFMIndex (sigma 5, sampling rate {args.rate}), per GPU")
-    metric = {"exact": "queries/s (150bp exact search + locate, 3 Gbp index)"}.get(wl, f"queries/s ({wl}, search + locate, 3 Gbp index)")
+        "reads copied from the text" if wl == "exact" else f"reads copied from the text with 0..{kk} planted {'edits' if edit else 'substitutions'} each")
+    unit = "aa" if protein else "bp"
+    workload = (f"{what}, {nq} x {L}{unit} {src}, synthetic {n_text} {unit} {'protein' if protein else 'DNA'} BiFMIndex (sigma {sigma}, "
+                f"sampling rate {args.rate}), per GPU")
+    metric = {"exact": "queries/s (150bp exact search + locate, 3 Gbp index)"}.get(
+        wl, f"queries/s ({wl}, search + locate, {'1 Gaa' if protein else '3 Gbp'} index)")
     # the SAME text on every rank (the index is replicated per GPU), different reads per rank (queries are sharded)
     index, sym, off = build_workload(fmb, device, n_text, nq, L, args.rate, seed=3, workload=wl, read_seed=4 + 1000 * rank)
     threads = os.cpu_count() or 1
-    ref_name = "search_no_errors::search (batched)" if scheme is None else f"search_ng26::search<{'true' if edit else 'false'}>(optimum(0,{wl[1]}))"
+    ref_name = "search_no_errors::search (batched)" if scheme is None else f"search_ng26::search<{'true' if edit else 'false'}>(optimum(0,{kk}))"
 
     # ------------------------------------------------------------------------------------------------------
     if args.impl == "reference":
-        ref = reference_index(index)
+        ref = reference_index(index, sigma)
         # size the per-step sample so that W+K steps take about 2 minutes in total
         probe = min(nq, 5000 if scheme is not None or wl == "locate-heavy" else 20000)
         t, _ = cpu_search_locate(ref, sym.array, off.array, 0, probe, threads, L, scheme, partition, edit)
@@ -354,7 +361,7 @@ def main():
                     "one_symbol_kernel_ms": one_symbol_ms, "locate_kernel": locate_info,
                     "note": "frac > 1 is possible: algorithmic bytes are those of the reference's one-symbol algorithm; see physical.frac for the kernel's own traffic"}
     else:
-        alg_bytes = st_s.occ_lookups * 32.0
+        alg_bytes = st_s.occ_lookups * (64.0 if protein else 32.0)       # 64 B per lookup for sigma = 21
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "scheme_search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ncu_traffic("scheme_search_kernel:" + wl, f"{nq} x {L}bp on {n_text} bp"), "peak_source": peak_src,
@@ -373,7 +380,7 @@ def main():
     # ---- CPU baseline: the reference's own search on this box's host cores (rank 0, N = 1 only) ---------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            ref = reference_index(index)
+            ref = reference_index(index, sigma)
             probe = min(nq, 5000 if scheme is not None or wl == "locate-heavy" else 20000)
             t, _ = cpu_search_locate(ref, sym.array, off.array, 0, probe, threads, L, scheme, partition, edit)
             sample_n = int(min(nq, max(probe, probe / max(t, 1e-9) * args.cpu_seconds)))

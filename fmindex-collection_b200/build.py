@@ -45,11 +45,12 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
+    extra = os.environ.get("FMB_NVCC_EXTRA", "").split()      # experiments only, e.g. -DFMB_SCHEME_MINB=4
     # one nvcc per translation unit, in parallel, then one link step
     procs = []
     for src in srcs:
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, p in procs:

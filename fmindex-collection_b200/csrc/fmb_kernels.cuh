@@ -515,14 +515,15 @@ __global__ void __launch_bounds__(256) jump_init_kernel(const __grid_constant__ 
     uint32_t y = occ.symbol(b, (row_t)i);
     out[i] = y ? make_uint2(ix.C[y] + occ.rank(b, (row_t)i, y), y - 1) : make_uint2(kJumpInvalid, 0);
 }
-__global__ void __launch_bounds__(256) jump_double_kernel(const uint2* __restrict__ in, uint2* __restrict__ out, uint64_t n, uint32_t shift) {
+__global__ void __launch_bounds__(256) jump_double_kernel(const uint2* __restrict__ in, uint2* __restrict__ out, uint64_t n, uint32_t shift, int nearest_low) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint2 a = in[i];
     uint2 r = make_uint2(kJumpInvalid, 0);
     if (a.x != kJumpInvalid) {
         uint2 b = __ldg(in + a.x);
-        if (b.x != kJumpInvalid) r = make_uint2(b.x, (a.y << shift) | b.y);
+        // a = the nearer `shift/2` symbols, b = the farther ones
+        if (b.x != kJumpInvalid) r = make_uint2(b.x, nearest_low ? (a.y | (b.y << shift)) : ((a.y << shift) | b.y));
     }
     out[i] = r;
 }

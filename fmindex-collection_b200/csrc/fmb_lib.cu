@@ -245,6 +245,8 @@ uint64_t fmb_index::device_bytes() const {
 // ---------------------------------------------------------------------------------------------------------
 namespace fmb {
 
+int build_jump(fmb_index* ix, int dir);
+
 // Builds occ table `dir` of `ix` from n BWT bytes at d_bwt (device).  Fails when a symbol is >= sigma.
 int build_occ_from_device_bwt(fmb_index* ix, int dir, const uint8_t* d_bwt) {
     const uint64_t n = ix->n;
@@ -352,8 +354,6 @@ __global__ void compute_C2_kernel(IndexView<OccDna> ix, int dir, uint32_t* out) 
     out[code] = (x < ix.sigma && y < ix.sigma) ? ix.C[x] + occ.rank(b, at, x) : 0u;
 }
 
-int build_jump(fmb_index* ix, int dir);
-
 // combined 64-byte locate records (needs occ table 0 and the marks); skipped when FMB_NO_LOCBLOCKS is set
 int build_locblocks(fmb_index* ix) {
     if (getenv("FMB_NO_LOCBLOCKS") || !ix->dna || !ix->marks.p || ix->n_samples == 0) return FMB_OK;
@@ -449,7 +449,9 @@ int build_jump(fmb_index* ix, int dir) {
     jump_init_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->view_dna(), dir, a.p);
     FMB_CUDA(cudaGetLastError());
     for (uint32_t shift = 2; shift <= 16; shift *= 2) {
-        jump_double_kernel<<<grid_for(n, 256), 256, 0, st>>>(a.p, b.p, n, shift);
+        // direction 0 is compared with query symbols to the LEFT of the match (farthest symbol = lowest position = low bits),
+        // direction 1 with symbols to the RIGHT (nearest symbol = lowest position = low bits): both equal the packed query order
+        jump_double_kernel<<<grid_for(n, 256), 256, 0, st>>>(a.p, b.p, n, shift, dir);
         FMB_CUDA(cudaGetLastError());
         std::swap(a, b);
     }
@@ -553,6 +555,8 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, co
     int rc = compute_C(ix);
     if (rc) return fail(rc);
     if (ix->dna) rc = build_occ2(ix, 0);
+    if (rc) return fail(rc);
+    if (ix->dna && ix->bidirectional) rc = build_jump(ix, 1);
     if (rc) return fail(rc);
     {
         const uint64_t have = (n + 63) / 64;

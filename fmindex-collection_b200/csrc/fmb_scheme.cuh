@@ -120,18 +120,35 @@ __device__ __forceinline__ void child_cursor(const IndexView<OCC>& ix, const OCC
     clen = r1 - r0;
 }
 
+// LF^16 jump tables of both directions + the 2-bit packed queries (DNA layout only; all pointers may be null)
+struct JumpView {
+    const uint2* jump[2];         // [0]: farthest symbol in the low bits, [1]: nearest symbol in the low bits (= query order)
+    const uint32_t* qpk;          // packed query symbols
+    const uint8_t* qflags;        // 1 = query not packable
+};
+
+// children of one expanded node are described by a bit mask and re-derived when they are written:
+//   bit 0 match / error-free continuation, bit 1 insertion, bit 2 sixteen-symbol jump,
+//   bits 8+c deletion(c), bits 36+c substitution(c)
+constexpr unsigned long long CH_MATCH = 1ull, CH_INS = 2ull, CH_JUMP = 4ull;
+constexpr int kFastForward = 12;
+#ifndef FMB_SCHEME_MINB
+#define FMB_SCHEME_MINB 3          // 3 blocks of 256 threads per SM -> at most 85 registers
+#endif   // consecutive single-child expansions a lane may chain in registers per pop
+
 template <class OCC, bool EDIT>
-__global__ void __launch_bounds__(256) scheme_search_kernel(const __grid_constant__ IndexView<OCC> ix, const __grid_constant__ SchemeParams sp, const uint8_t* __restrict__ qsym,
-                                                            const uint64_t* __restrict__ qoff, uint64_t n_roots,
+__global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(const __grid_constant__ IndexView<OCC> ix, const __grid_constant__ SchemeParams sp,
+                                                            const uint8_t* __restrict__ qsym, const uint64_t* __restrict__ qoff,
+                                                            const __grid_constant__ JumpView jv, uint64_t n_roots,
                                                             const Item* __restrict__ in_items, uint64_t n_in,
-                                                            SchemeOut out, uint32_t cap) {
+                                                            const __grid_constant__ SchemeOut out, uint32_t cap, uint32_t ff_min) {
     extern __shared__ uint4 smem_raw[];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = threadIdx.x >> 5;
     Item* stack = reinterpret_cast<Item*>(smem_raw) + (size_t)warp * cap;
     const uint64_t total_roots = n_roots + n_in;
     uint32_t top = 0;
-    uint32_t n_ext = 0, n_look = 0, peak = 0;
+    uint32_t n_ext = 0, n_look = 0, n_phys = 0, peak = 0;
     bool more_roots = true;
     const uint32_t np = sp.n_parts;
     const uint32_t first_symb = 1;       // FirstSymb of delimited indices (fmindex/BiFMIndex.h:26)
@@ -190,115 +207,259 @@ __global__ void __launch_bounds__(256) scheme_search_kernel(const __grid_constan
         top -= nact;
         __syncwarp();
 
-        // ---- expand one node per lane ---------------------------------------------------------------------
-        // children are described by a bit mask and re-derived when they are written:
-        //   bit 0 match / continuation, bit 1 insertion, bits 8..8+sigma deletion(c), bits 40.. substitution(c) (64-bit)
+        // ---- expand: one node per lane and iteration; a lane whose node has exactly one child keeps going in
+        //      registers (fast forward) instead of a round trip through the shared-memory stack ----------------
         unsigned long long cmask = 0;
         bool report = false;
-        uint32_t q = 0, b0 = 0, b1 = 0, lo = 0, hi = 0, single_sym = 0;
+        uint32_t q = 0, b0 = 0, b1 = 0, lo = 0, hi = 0, jrow = 0, jadd = 0, jlast = 0;
         typename OCC::Block blk0, blk1;
         bool is_single = false, noerr_cont = false;
-        const OCC* occp = nullptr;
+        uint64_t qbase = 0;
+        bool live = active;
 
-        if (active) {
-            bool go_dir = true;
-            if (st.mode == MODE_POS) {                                                          // search_next_pos :119-141
-                if (st.NextPos) {
-                    if (st.Right) st.qposR = (st.qposR + 1) & 0xFFFF; else st.qposL = (st.qposL - 1) & 0xFFFF;
-                    st.pev -= 1;
-                    if (st.pev == 0) {
-                        st.part += 1;
-                        if (st.part != np) st.pev = sp.partition[sp.pi[st.search][st.part]];
-                        st.mode = MODE_NEXT;
-                    }
-                }
-            }
-            if (st.mode == MODE_NEXT) {                                                         // search_next :98-117
-                if (st.part == np) {
-                    bool ok = !EDIT || ((st.LInfo == INFO_M || st.LInfo == INFO_I) && (st.RInfo == INFO_M || st.RInfo == INFO_I));
-                    report = ok && sp.l[st.search][np - 1] <= st.e && st.e <= sp.u[st.search][np - 1];
-                    go_dir = false;
-                } else {
-                    st.Right = (st.part == 0) || (sp.pi[st.search][st.part - 1] < sp.pi[st.search][st.part]);
-                    if (sp.force_left) st.Right = 0;
-                }
-            }
-            if (go_dir) {
-                const uint32_t R = st.Right;
-                const OCC& occ = ix.occ[R];
-                occp = &occ;
-                q = __ldg(qsym + qoff[st.qidx] + (R ? st.qposR : st.qposL));
-                lo = R ? st.lb_rev : st.lb;
-                hi = lo + st.len;
-                b0 = lo >> 6;
-                b1 = hi >> 6;
-                if (st.mode == MODE_NOERR) {
-                    noerr_cont = true;                                                          // search_next_dir_no_errors :225-250
-                } else {
-                    const uint32_t TInfo = R ? st.RInfo : st.LInfo;
-                    const uint32_t lastRank = side_get(st.side, R, 0), lastQRank = side_get(st.side, R, 1);
-                    const bool Deletion = EDIT && TInfo != INFO_S && TInfo != INFO_I;
-                    const bool Insertion = EDIT && TInfo != INFO_S && TInfo != INFO_D;
-                    const uint32_t lp = sp.l[st.search][st.part], up = sp.u[st.search][st.part];
-                    const bool matchAllowed = (st.pev > 1 || lp <= st.e) && st.e <= up && (TInfo != INFO_I || q != lastQRank) &&
-                                              (TInfo != INFO_D || q != lastRank);
-                    const bool insAllowed = (st.pev > 1 || lp <= st.e + 1) && st.e + 1 <= up;
-                    const bool mismatchAllowed = st.e + 1 <= up;
-                    if (st.len > 1) {                                                           // search_next_dir :143-224
-                        if (mismatchAllowed) {
-                            blk0 = occ.load(b0, 0);
-                            blk1 = (b1 == b0) ? blk0 : occ.load(b1, 0);
-                            n_ext += 1; n_look += (b1 == b0) ? 1 : 2;
-                            uint32_t same, dother, clen;
-                            if (matchAllowed && q < ix.sigma) {
-                                child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, q, false, same, dother, clen);
-                                if (clen) cmask |= 1ull;
-                            }
-                            for (uint32_t c = first_symb; c < ix.sigma; ++c) {
-                                child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, c, false, same, dother, clen);
-                                if (!clen) continue;
-                                if (Deletion) cmask |= 1ull << (8 + c);
-                                if (insAllowed && c != q) cmask |= 1ull << (36 + c);
-                            }
-                            if (Insertion && insAllowed) cmask |= 2ull;
-                        } else if (matchAllowed) {
-                            noerr_cont = true;
-                        }
-                    } else {                                                                    // search_next_dir_single :251-365
-                        is_single = true;
-                        blk0 = occ.load(b0, 0);
-                        blk1 = blk0;
-                        n_ext += 1; n_look += 1;
-                        single_sym = occ.symbol(blk0, lo);                                      // symbolLeft/Right, BiFMIndexCursor.h:180-190
-                        if (Insertion && insAllowed) cmask |= 2ull;
-                        if (single_sym >= first_symb) {
-                            if (single_sym == q) {
-                                if (matchAllowed) {
-                                    if (!mismatchAllowed) noerr_cont = true;
-                                    else cmask |= 1ull;
-                                }
-                                if (Deletion && mismatchAllowed) cmask |= 1ull << (8 + single_sym);
-                            } else if (mismatchAllowed) {
-                                if (insAllowed) cmask |= 1ull << (36 + single_sym);
-                                if (Deletion) cmask |= 1ull << (8 + single_sym);
-                            }
-                        }
-                    }
-                }
+        // one child of the expanded node (bit `bit` of cmask)
+        auto make_child = [&](uint32_t bit) -> State {
+            const uint32_t R = st.Right;
+            const OCC& occ = ix.occ[R];
+            State ch = st;
+            auto stepped = [&](uint32_t c) {
+                uint32_t same, dother, clen;
+                child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, c, is_single, same, dother, clen);
+                ch.len = clen;
+                if (R) { ch.lb_rev = same; ch.lb = st.lb + dother; } else { ch.lb = same; ch.lb_rev = st.lb_rev + dother; }
+                ch.steps = st.steps + 1;
+            };
+            if (bit == 0) {
+                stepped(q);
                 if (noerr_cont) {
-                    // one step of the error-free loop; bit 0 = the continuation item
-                    if (q < ix.sigma) {
-                        if (!is_single) {
-                            blk0 = occ.load(b0, q);
-                            blk1 = (b1 == b0) ? blk0 : occ.load(b1, q);
-                            n_ext += 1; n_look += (b1 == b0) ? 1 : 2;
+                    if (R) ch.qposR = (st.qposR + 1) & 0xFFFF; else ch.qposL = (st.qposL - 1) & 0xFFFF;
+                    ch.pev = st.pev - 1;
+                    ch.NextPos = 0;
+                    if (ch.pev > 0) {
+                        ch.mode = MODE_NOERR;
+                    } else {                                                                    // :241-249
+                        ch.side = side_set(side_set(st.side, R, 0, q), R, 1, q);
+                        ch.part = st.part + 1;
+                        ch.pev = (ch.part != np) ? sp.partition[sp.pi[st.search][ch.part]] : 0;
+                        if (R) ch.RInfo = INFO_M; else ch.LInfo = INFO_M;
+                        ch.mode = MODE_NEXT;
+                    }
+                } else {                                                                        // match child
+                    ch.side = side_set(side_set(st.side, R, 0, q), R, 1, q);
+                    if (R) ch.RInfo = INFO_M; else ch.LInfo = INFO_M;
+                    ch.NextPos = 1;
+                    ch.mode = MODE_POS;
+                }
+            } else if (bit == 1) {                                                              // insertion: no index step
+                ch.e = st.e + 1;
+                ch.side = side_set(st.side, R, 1, q);
+                if (R) ch.RInfo = INFO_I; else ch.LInfo = INFO_I;
+                ch.NextPos = 1;
+                ch.mode = MODE_POS;
+            } else if (bit == 2) {                                                              // sixteen symbols at once (len == 1)
+                if (R) ch.lb_rev = jrow; else ch.lb = jrow;
+                ch.steps = st.steps + 16;
+                ch.e = st.e + jadd;
+                ch.side = side_set(side_set(st.side, R, 0, jlast), R, 1, jlast);
+                if (st.mode == MODE_NOERR) {
+                    if (R) ch.qposR = (st.qposR + 16) & 0xFFFF; else ch.qposL = (st.qposL - 16) & 0xFFFF;
+                    ch.pev = st.pev - 16;
+                    ch.NextPos = 0;
+                    if (ch.pev == 0) {
+                        ch.part = st.part + 1;
+                        ch.pev = (ch.part != np) ? sp.partition[sp.pi[st.search][ch.part]] : 0;
+                        if (R) ch.RInfo = INFO_M; else ch.LInfo = INFO_M;
+                        ch.mode = MODE_NEXT;
+                    }
+                } else {
+                    // Hamming, errors allowed: fifteen advances now, the sixteenth is pending like after any match
+                    if (R) ch.qposR = (st.qposR + 15) & 0xFFFF; else ch.qposL = (st.qposL - 15) & 0xFFFF;
+                    ch.pev = st.pev - 15;
+                    if (R) ch.RInfo = INFO_M; else ch.LInfo = INFO_M;
+                    ch.NextPos = 1;
+                    ch.mode = MODE_POS;
+                }
+            } else {
+                const bool is_sub = bit >= 36;
+                const uint32_t c = is_sub ? bit - 36 : bit - 8;
+                stepped(c);
+                ch.e = st.e + 1;
+                ch.side = side_set(st.side, R, 0, c);
+                ch.mode = MODE_POS;
+                if (is_sub) {
+                    ch.side = side_set(ch.side, R, 1, q);
+                    if (R) ch.RInfo = INFO_S; else ch.LInfo = INFO_S;
+                    ch.NextPos = 1;
+                } else {
+                    if (R) ch.RInfo = INFO_D; else ch.LInfo = INFO_D;
+                    ch.NextPos = 0;
+                }
+            }
+            return ch;
+        };
+
+        for (int ff = 0;; ++ff) {
+            if (live) {
+                cmask = 0;
+                report = false;
+                is_single = false;
+                noerr_cont = false;
+                bool go_dir = true;
+                if (st.mode == MODE_POS) {                                                          // search_next_pos :119-141
+                    if (st.NextPos) {
+                        if (st.Right) st.qposR = (st.qposR + 1) & 0xFFFF; else st.qposL = (st.qposL - 1) & 0xFFFF;
+                        st.pev -= 1;
+                        if (st.pev == 0) {
+                            st.part += 1;
+                            if (st.part != np) st.pev = sp.partition[sp.pi[st.search][st.part]];
+                            st.mode = MODE_NEXT;
                         }
-                        uint32_t same, dother, clen;
-                        child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, q, is_single, same, dother, clen);
-                        if (clen) cmask |= 1ull;
+                    }
+                }
+                if (st.mode == MODE_NEXT) {                                                         // search_next :98-117
+                    if (st.part == np) {
+                        bool ok = !EDIT || ((st.LInfo == INFO_M || st.LInfo == INFO_I) && (st.RInfo == INFO_M || st.RInfo == INFO_I));
+                        report = ok && sp.l[st.search][np - 1] <= st.e && st.e <= sp.u[st.search][np - 1];
+                        go_dir = false;
+                    } else {
+                        st.Right = (st.part == 0) || (sp.pi[st.search][st.part - 1] < sp.pi[st.search][st.part]);
+                        if (sp.force_left) st.Right = 0;
+                    }
+                }
+                if (go_dir) {
+                    const uint32_t R = st.Right;
+                    const OCC& occ = ix.occ[R];
+                    qbase = qoff[st.qidx];
+                    lo = R ? st.lb_rev : st.lb;
+                    hi = lo + st.len;
+                    b0 = lo >> 6;
+                    b1 = hi >> 6;
+                    const uint32_t lp = sp.l[st.search][st.part], up = sp.u[st.search][st.part];
+                    // ---- sixteen-symbol jump on a single-row interval (LF^16 table + packed query) ---------------
+                    bool jumped = false;
+                    if (st.len == 1 && jv.jump[R] != nullptr && jv.qflags[st.qidx] == 0 &&
+                        ((st.mode == MODE_NOERR && st.pev >= 16) || (!EDIT && st.mode != MODE_NOERR && st.pev > 16 && st.e <= up))) {
+                        const uint2 e = __ldg(jv.jump[R] + lo);
+                        n_phys += 1;
+                        if (e.x != kJumpInvalid) {
+                            jumped = true;
+                            // query symbols of the next 16 positions in walking direction, packed like the table entry
+                            const uint64_t bit = 2 * (qbase + (R ? st.qposR : st.qposL - 15));
+                            const uint32_t wi = (uint32_t)(bit >> 5);
+                            const uint32_t key = __funnelshift_r(__ldg(jv.qpk + wi), __ldg(jv.qpk + wi + 1), (uint32_t)bit & 31u);
+                            uint32_t x = e.y ^ key;
+                            uint32_t mm = (x | (x >> 1)) & 0x55555555u;                     // one bit per mismatching position
+                            const uint32_t budget = (st.mode == MODE_NOERR) ? 0u : up - st.e;   // mismatches this stretch may absorb
+                            const uint32_t nm = __popc(mm);
+                            if (nm <= budget) {
+                                cmask = CH_JUMP;
+                                jrow = e.x;
+                                jadd = nm;
+                                jlast = ((R ? key >> 30 : key) & 3u) + 1;                  // last query symbol consumed
+                                n_ext += 16; n_look += 16;
+                            } else {
+                                // dead: the reference walks until the (budget+1)-th mismatch -- same extension count
+                                uint32_t m = mm;
+                                uint32_t steps_done = 16;
+                                for (uint32_t k = 0; k <= budget; ++k) {
+                                    // walking order: R = from the low bits up, L = from the high bits down
+                                    uint32_t pos = R ? (uint32_t)(__ffs(m) - 1) : 31u - (uint32_t)__clz(m);
+                                    steps_done = R ? (pos >> 1) + 1 : ((31u - pos) >> 1) + 1;
+                                    m &= ~(1u << pos);
+                                }
+                                n_ext += steps_done; n_look += steps_done;
+                            }
+                        }
+                    }
+                    if (!jumped) {
+                        q = __ldg(qsym + qbase + (R ? st.qposR : st.qposL));
+                        if (st.mode == MODE_NOERR) {
+                            noerr_cont = true;                                                          // search_next_dir_no_errors :225-250
+                            if (q < ix.sigma) {
+                                n_ext += 1; n_look += (b1 == b0) ? 1 : 2;      // algorithmic: two ranks, one or two blocks
+                                if (st.len == 1) {
+                                    // single row: it continues iff its own BWT symbol is q; one block serves symbol and rank
+                                    is_single = true;
+                                    blk0 = occ.load(b0, 0);
+                                    blk1 = blk0;
+                                    n_phys += 1;
+                                    if (occ.symbol(blk0, lo) == q) cmask |= CH_MATCH;
+                                } else {
+                                    blk0 = occ.load(b0, q);
+                                    blk1 = (b1 == b0) ? blk0 : occ.load(b1, q);
+                                    n_phys += (b1 == b0) ? 1 : 2;
+                                    uint32_t same, dother, clen;
+                                    child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, q, false, same, dother, clen);
+                                    if (clen) cmask |= CH_MATCH;
+                                }
+                            }
+                        } else {
+                            const uint32_t TInfo = R ? st.RInfo : st.LInfo;
+                            const uint32_t lastRank = side_get(st.side, R, 0), lastQRank = side_get(st.side, R, 1);
+                            const bool Deletion = EDIT && TInfo != INFO_S && TInfo != INFO_I;
+                            const bool Insertion = EDIT && TInfo != INFO_S && TInfo != INFO_D;
+                            const bool matchAllowed = (st.pev > 1 || lp <= st.e) && st.e <= up && (TInfo != INFO_I || q != lastQRank) &&
+                                                      (TInfo != INFO_D || q != lastRank);
+                            const bool insAllowed = (st.pev > 1 || lp <= st.e + 1) && st.e + 1 <= up;
+                            const bool mismatchAllowed = st.e + 1 <= up;
+                            if (st.len > 1) {                                                           // search_next_dir :143-224
+                                if (mismatchAllowed) {
+                                    blk0 = occ.load(b0, 0);
+                                    blk1 = (b1 == b0) ? blk0 : occ.load(b1, 0);
+                                    n_ext += 1; n_look += (b1 == b0) ? 1 : 2; n_phys += (b1 == b0) ? 1 : 2;
+                                    uint32_t same, dother, clen;
+                                    if (matchAllowed && q < ix.sigma) {
+                                        child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, q, false, same, dother, clen);
+                                        if (clen) cmask |= CH_MATCH;
+                                    }
+                                    for (uint32_t c = first_symb; c < ix.sigma; ++c) {
+                                        child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, c, false, same, dother, clen);
+                                        if (!clen) continue;
+                                        if (Deletion) cmask |= 1ull << (8 + c);
+                                        if (insAllowed && c != q) cmask |= 1ull << (36 + c);
+                                    }
+                                    if (Insertion && insAllowed) cmask |= CH_INS;
+                                } else if (matchAllowed) {
+                                    noerr_cont = true;
+                                    if (q < ix.sigma) {
+                                        blk0 = occ.load(b0, q);
+                                        blk1 = (b1 == b0) ? blk0 : occ.load(b1, q);
+                                        n_ext += 1; n_look += (b1 == b0) ? 1 : 2; n_phys += (b1 == b0) ? 1 : 2;
+                                        uint32_t same, dother, clen;
+                                        child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, q, false, same, dother, clen);
+                                        if (clen) cmask |= CH_MATCH;
+                                    }
+                                }
+                            } else {                                                                    // search_next_dir_single :251-365
+                                is_single = true;
+                                blk0 = occ.load(b0, 0);
+                                blk1 = blk0;
+                                n_ext += 1; n_look += 1; n_phys += 1;
+                                const uint32_t single_sym = occ.symbol(blk0, lo);                       // symbolLeft/Right, BiFMIndexCursor.h:180-190
+                                if (Insertion && insAllowed) cmask |= CH_INS;
+                                if (single_sym >= first_symb) {
+                                    if (single_sym == q) {
+                                        if (matchAllowed) {
+                                            if (!mismatchAllowed) noerr_cont = true;
+                                            cmask |= CH_MATCH;
+                                        }
+                                        if (Deletion && mismatchAllowed) cmask |= 1ull << (8 + single_sym);
+                                    } else if (mismatchAllowed) {
+                                        if (insAllowed) cmask |= 1ull << (36 + single_sym);
+                                        if (Deletion) cmask |= 1ull << (8 + single_sym);
+                                    }
+                                }
+                            }
+                        }
                     }
                 }
             }
+            // fast forward: lanes with exactly one child (and nothing to report) continue with it
+            const bool chain = live && !report && cmask != 0 && (cmask & (cmask - 1)) == 0 && ff + 1 < kFastForward;
+            // ... as long as enough lanes of the warp do so (the others idle meanwhile)
+            if ((uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, chain)) < ff_min) break;
+            if (chain) st = make_child((uint32_t)(__ffsll((long long)cmask) - 1));
+            else live = false;
         }
 
         // ---- report leaves (warp aggregated append) -----------------------------------------------------------
@@ -342,69 +503,11 @@ __global__ void __launch_bounds__(256) scheme_search_kernel(const __grid_constan
             drop = base + total > out.overflow_capacity;      // host sees overflow_count > capacity and fails loudly
         }
         if (cmask && !drop) {
-            const uint32_t R = st.Right;
-            const OCC& occ = *occp;
-            // helper state for children that took one index step with symbol c
-            auto stepped = [&](uint32_t c, State& ch) {
-                uint32_t same, dother, clen;
-                child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, c, is_single, same, dother, clen);
-                ch.len = clen;
-                if (R) { ch.lb_rev = same; ch.lb = st.lb + dother; } else { ch.lb = same; ch.lb_rev = st.lb_rev + dother; }
-                ch.steps = st.steps + 1;
-            };
-            if (cmask & 1ull) {
-                State ch = st;
-                stepped(q, ch);
-                if (noerr_cont) {
-                    if (R) ch.qposR = (st.qposR + 1) & 0xFFFF; else ch.qposL = (st.qposL - 1) & 0xFFFF;
-                    ch.pev = st.pev - 1;
-                    ch.NextPos = 0;
-                    if (ch.pev > 0) {
-                        ch.mode = MODE_NOERR;
-                    } else {                                                                    // :241-249
-                        ch.side = side_set(side_set(st.side, R, 0, q), R, 1, q);
-                        ch.part = st.part + 1;
-                        ch.pev = (ch.part != np) ? sp.partition[sp.pi[st.search][ch.part]] : 0;
-                        if (R) ch.RInfo = INFO_M; else ch.LInfo = INFO_M;
-                        ch.mode = MODE_NEXT;
-                    }
-                } else {                                                                        // match child
-                    ch.side = side_set(side_set(st.side, R, 0, q), R, 1, q);
-                    if (R) ch.RInfo = INFO_M; else ch.LInfo = INFO_M;
-                    ch.NextPos = 1;
-                    ch.mode = MODE_POS;
-                }
-                dst[slot++] = pack_item(ch);
-            }
-            if (cmask & 2ull) {                                                                 // insertion: no index step
-                State ch = st;
-                ch.e = st.e + 1;
-                ch.side = side_set(st.side, R, 1, q);
-                if (R) ch.RInfo = INFO_I; else ch.LInfo = INFO_I;
-                ch.NextPos = 1;
-                ch.mode = MODE_POS;
-                dst[slot++] = pack_item(ch);
-            }
-            unsigned long long rest = cmask >> 8;
+            unsigned long long rest = cmask;
             while (rest) {
                 uint32_t bit = __ffsll((long long)rest) - 1;
                 rest &= rest - 1;
-                bool is_sub = bit >= 28;
-                uint32_t c = is_sub ? bit - 28 : bit;
-                State ch = st;
-                stepped(c, ch);
-                ch.e = st.e + 1;
-                ch.side = side_set(st.side, R, 0, c);
-                ch.mode = MODE_POS;
-                if (is_sub) {
-                    ch.side = side_set(ch.side, R, 1, q);
-                    if (R) ch.RInfo = INFO_S; else ch.LInfo = INFO_S;
-                    ch.NextPos = 1;
-                } else {
-                    if (R) ch.RInfo = INFO_D; else ch.LInfo = INFO_D;
-                    ch.NextPos = 0;
-                }
-                dst[slot++] = pack_item(ch);
+                dst[slot++] = pack_item(make_child(bit));
             }
         }
         __syncwarp();
@@ -414,10 +517,12 @@ __global__ void __launch_bounds__(256) scheme_search_kernel(const __grid_constan
     for (int o = 16; o > 0; o >>= 1) {
         n_ext += __shfl_xor_sync(0xFFFFFFFFu, n_ext, o);
         n_look += __shfl_xor_sync(0xFFFFFFFFu, n_look, o);
+        n_phys += __shfl_xor_sync(0xFFFFFFFFu, n_phys, o);
     }
     if (lane == 0) {
         atomicAdd(out.counters + 0, (unsigned long long)n_ext);
         atomicAdd(out.counters + 1, (unsigned long long)n_look);
+        atomicAdd(out.counters + 2, (unsigned long long)n_phys);
         atomicMax(out.counters + 3, (unsigned long long)peak);
     }
 }

@@ -48,7 +48,19 @@ int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const Schem
     uint64_t work = n_roots + n_in;
     uint64_t want_blocks = (work + 255) / 256;
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * blocks_per_sm, want_blocks));
-    kern<<<grid, 256, smem, st>>>(view, sp, q->symbols.p, q->offsets.p, n_roots, in_items, n_in, out, kStackCap);
+    JumpView jv{};
+    static const bool no_jump = getenv("FMB_NO_SCHEME_JUMP") != nullptr;
+    if (ix->dna && q->packed.p && !no_jump) {
+        jv.jump[0] = ix->jump[0].p;
+        jv.jump[1] = ix->jump[1].p;
+        jv.qpk = q->packed.p;
+        jv.qflags = q->flags.p;
+    }
+    // a warp keeps fast-forwarding while at least ff_min of its lanes have a single child; edit distance branches
+    // at almost every node, so it only pays there when most of the warp is inside error-free stretches
+    static const char* ff_env = getenv("FMB_SCHEME_FFMIN");
+    const uint32_t ff_min = ff_env ? (uint32_t)atoi(ff_env) : (EDIT ? 24u : 8u);
+    kern<<<grid, 256, smem, st>>>(view, sp, q->symbols.p, q->offsets.p, jv, n_roots, in_items, n_in, out, kStackCap, ff_min);
     FMB_CUDA(cudaGetLastError());
     note_launches(1);
     return FMB_OK;
@@ -134,6 +146,7 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     res->stats.extensions = h_ctr[0];
     res->stats.occ_lookups = h_ctr[1];
     res->stats.frontier_peak = h_ctr[3];
+    res->stats.line_requests = h_ctr[2];
     res->stats.kernel_ms = total_ms;
     res->stats.main_kernel_ms = total_ms;
     guard.r = nullptr;

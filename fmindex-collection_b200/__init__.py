@@ -14,4 +14,4 @@ from .capi import (  # noqa: F401
     lib,
     lib_path,
 )
-from . import schemes, synth  # noqa: F401
+from . import multi, schemes, synth  # noqa: F401

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
         //      registers (fast forward) instead of a round trip through the shared-memory stack ----------------
         unsigned long long cmask = 0;
         bool report = false;
-        uint32_t q = 0, b0 = 0, b1 = 0, lo = 0, hi = 0, jrow = 0, jadd = 0, jlast = 0;
+        uint32_t q = 0, b0 = 0, b1 = 0, lo = 0, hi = 0, jrow = 0, jadd = 0, jlast = 0, jnoerr = 0;
         typename OCC::Block blk0, blk1;
         bool is_single = false, noerr_cont = false;
         uint64_t qbase = 0;
@@ -261,10 +261,12 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                 ch.steps = st.steps + 16;
                 ch.e = st.e + jadd;
                 ch.side = side_set(side_set(st.side, R, 0, jlast), R, 1, jlast);
-                if (st.mode == MODE_NOERR) {
+                if (st.mode == MODE_NOERR || jnoerr) {
+                    // (jnoerr: a Hamming stretch that used up its error budget inside the window is in the error-free loop now)
                     if (R) ch.qposR = (st.qposR + 16) & 0xFFFF; else ch.qposL = (st.qposL - 16) & 0xFFFF;
                     ch.pev = st.pev - 16;
                     ch.NextPos = 0;
+                    ch.mode = MODE_NOERR;
                     if (ch.pev == 0) {
                         ch.part = st.part + 1;
                         ch.pev = (ch.part != np) ? sp.partition[sp.pi[st.search][ch.part]] : 0;
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                     // ---- sixteen-symbol jump on a single-row interval (LF^16 table + packed query) ---------------
                     bool jumped = false;
                     if (st.len == 1 && jv.jump[R] != nullptr && jv.qflags[st.qidx] == 0 &&
-                        ((st.mode == MODE_NOERR && st.pev >= 16) || (!EDIT && st.mode != MODE_NOERR && st.pev > 16 && st.e <= up))) {
+                        ((st.mode == MODE_NOERR && st.pev >= 16) || (!EDIT && st.mode != MODE_NOERR && st.pev > 16 && st.e < up))) {
                         const uint2 e = __ldg(jv.jump[R] + lo);
                         n_phys += 1;
                         if (e.x != kJumpInvalid) {
@@ -347,27 +349,38 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                             const uint64_t bit = 2 * (qbase + (R ? st.qposR : st.qposL - 15));
                             const uint32_t wi = (uint32_t)(bit >> 5);
                             const uint32_t key = __funnelshift_r(__ldg(jv.qpk + wi), __ldg(jv.qpk + wi + 1), (uint32_t)bit & 31u);
-                            uint32_t x = e.y ^ key;
-                            uint32_t mm = (x | (x >> 1)) & 0x55555555u;                     // one bit per mismatching position
-                            const uint32_t budget = (st.mode == MODE_NOERR) ? 0u : up - st.e;   // mismatches this stretch may absorb
+                            const uint32_t x = e.y ^ key;
+                            const uint32_t mm = (x | (x >> 1)) & 0x55555555u;               // one bit per mismatching position
+                            const uint32_t budget = (st.mode == MODE_NOERR) ? 0u : up - st.e;   // mismatches this stretch may absorb (>= 1 when errors are left)
                             const uint32_t nm = __popc(mm);
+                            // index (0..15, walking order: R from the low bits up, L from the high bits down) of the j-th mismatch, j = 1..
+                            auto nth = [&](uint32_t j) -> int {
+                                uint32_t m = mm;
+                                int idx = -1;
+                                for (uint32_t k = 0; k < j; ++k) {
+                                    uint32_t pos = R ? (uint32_t)(__ffs(m) - 1) : 31u - (uint32_t)__clz(m);
+                                    idx = R ? (int)(pos >> 1) : (int)((31u - pos) >> 1);
+                                    m &= ~(1u << pos);
+                                }
+                                return idx;
+                            };
+                            // The counters follow the reference's walk over the same 16 positions: one extension per position; once
+                            // the error budget of a Hamming stretch is used up it switches to its error-free loop at the next
+                            // matching position, which repeats that extension (SearchNg26.h:311-315).
                             if (nm <= budget) {
                                 cmask = CH_JUMP;
                                 jrow = e.x;
                                 jadd = nm;
                                 jlast = ((R ? key >> 30 : key) & 3u) + 1;                  // last query symbol consumed
-                                n_ext += 16; n_look += 16;
+                                jnoerr = 0;
+                                uint32_t cnt = 16;
+                                if (st.mode != MODE_NOERR && nm == budget && nth(budget) < 15) { jnoerr = 1; cnt += 1; }
+                                n_ext += cnt; n_look += cnt;
                             } else {
-                                // dead: the reference walks until the (budget+1)-th mismatch -- same extension count
-                                uint32_t m = mm;
-                                uint32_t steps_done = 16;
-                                for (uint32_t k = 0; k <= budget; ++k) {
-                                    // walking order: R = from the low bits up, L = from the high bits down
-                                    uint32_t pos = R ? (uint32_t)(__ffs(m) - 1) : 31u - (uint32_t)__clz(m);
-                                    steps_done = R ? (pos >> 1) + 1 : ((31u - pos) >> 1) + 1;
-                                    m &= ~(1u << pos);
-                                }
-                                n_ext += steps_done; n_look += steps_done;
+                                const int d = nth(budget + 1);                               // the mismatch that ends the path
+                                uint32_t cnt = (uint32_t)d + 1;
+                                if (st.mode != MODE_NOERR && d - nth(budget) > 1) cnt += 1;
+                                n_ext += cnt; n_look += cnt;
                             }
                         }
                     }
@@ -440,7 +453,10 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                                 if (single_sym >= first_symb) {
                                     if (single_sym == q) {
                                         if (matchAllowed) {
-                                            if (!mismatchAllowed) noerr_cont = true;
+                                            if (!mismatchAllowed) {
+                                                noerr_cont = true;
+                                                n_ext += 1; n_look += 1;        // the reference's error-free loop repeats this extension (:311-315)
+                                            }
                                             cmask |= CH_MATCH;
                                         }
                                         if (Deletion && mismatchAllowed) cmask |= 1ull << (8 + single_sym);

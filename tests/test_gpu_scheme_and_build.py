@@ -197,3 +197,27 @@ def test_search_and_locate_one_call(pair):
     for f in ("qidx", "seq", "pos", "e"):
         got[f] = locs[f]
     assert locs_equal(got, exp)
+
+
+@pytest.mark.parametrize("edit", [False, True])
+def test_scheme_work_counters_match_oracle(gpu, edit):
+    """fmb_stats.extensions of the scheme kernel = the oracle's count of cursor extensions of search_ng26 (the algorithmic work
+    of SURVEY.md §8d), although the kernel covers sixteen of them with one LF^16 jump; occ_lookups agrees up to the rows whose
+    interval end falls into the next block (a jump counts one lookup per step)."""
+    from fmb200 import schemes, synth
+    from oracle.pyoracle import Counters
+    text = synth.text(300000, 5, 4)
+    o, g = make_index_pair(gpu, text, 5, 16)
+    reads, _ = synth.reads_from_text(text, 2000, 100, 5)
+    reads[1000:] = synth.plant_errors(reads[1000:], 5, 1, edit, 6)
+    sym, off = synth.flatten(reads)
+    sch = schemes.optimum(0, 2)
+    part = schemes.uniform_partition(4, 100)
+    res = g.search_scheme(g.upload(sym, off), sch, part, edit)
+    ctr = Counters()
+    exp = o.search_ng26(sym, off, sch, part, edit, counters=ctr)
+    assert hits_equal(res.hits(), exp)
+    st = res.stats
+    assert st.extensions == ctr.extensions
+    assert abs(int(st.occ_lookups) - int(ctr.occ_lookups)) <= 0.05 * ctr.occ_lookups
+    assert 0 < st.line_requests < st.occ_lookups          # the jumps save physical fetches

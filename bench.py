@@ -366,7 +366,10 @@ def main():
         roofline = {"bound": "hbm", "kernel": "scheme_search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ncu_traffic("scheme_search_kernel:" + wl, f"{nq} x {L}bp on {n_text} bp"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "lookups_per_query": st_s.occ_lookups / nq, "extensions_per_query": st_s.extensions / nq,
-                    "kernel_ms": k_ms, "frontier_peak_items_per_warp": st_s.frontier_peak, "locate_kernel": locate_info}
+                    "kernel_ms": k_ms, "frontier_peak_items_per_warp": st_s.frontier_peak,
+                    "physical": {"line_requests_per_query": st_s.line_requests / nq, "lines_per_s": st_s.line_requests / (k_ms * 1e-3),
+                                 "measured_random_line_ceiling_per_s": 38.4e9},
+                    "locate_kernel": locate_info}
 
     line = {"metric": metric, "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -104,6 +104,8 @@ struct fmb_index {
     fmb::DevBuf<uint2> jump[2];          // LF^16 jump tables
     fmb::DevBuf<uint2> kmer;             // k-mer interval table of direction 0
     uint32_t kmer_k = 0;
+    fmb::DevBuf<uint4> bikmer;           // bidirectional k-mer table for scheme-search roots
+    uint32_t bikmer_k = 0;
     int exact_mode = 0;                  // FMB_EXACT_*
 
     fmb::IndexView<fmb::OccDna> view_dna() const;

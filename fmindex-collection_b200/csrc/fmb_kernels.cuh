@@ -468,6 +468,20 @@ __global__ void rebase_offsets_kernel(uint64_t* __restrict__ off, uint64_t count
     if (i < count) off[i] -= base;
 }
 
+// bidirectional k-mer table (fmb_scheme.cuh JumpView::bikmer): k extendRight steps per pattern, with the work the
+// reference's error-free loop spends on them
+__global__ void __launch_bounds__(256) bikmer_table_kernel(const __grid_constant__ IndexView<OccDna> ix, uint32_t k, uint64_t count, uint4* __restrict__ out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Cursor c{0, 0, ix.n, 0};
+    uint32_t ext = 0, look = 0;
+    for (uint32_t p = 0; p < k && c.len; ++p) {
+        c = extend_bi(ix, c, (uint32_t)((i >> (2 * p)) & 3) + 1, 1, look);
+        ++ext;
+    }
+    out[i] = make_uint4(c.lb, c.lb_rev, c.len, (ext << 16) | look);
+}
+
 // 2-bit packing of the query symbols (symbol-1, 16 symbols per word, first symbol in the low bits).  Queries holding a
 // symbol that has no 2-bit code (0 or >= sigma) are flagged and take the byte path of the search kernel.
 __device__ __forceinline__ uint32_t pack4(uint32_t w, uint32_t sigma, bool& bad) {

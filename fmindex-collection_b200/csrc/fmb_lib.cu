@@ -232,6 +232,7 @@ uint64_t fmb_index::device_bytes() const {
     uint64_t b = 0;
     for (int d = 0; d < 2; ++d) b += occ2[d].p ? occ2[d].bytes() + specials[d].bytes() : 0;
     b += kmer.p ? kmer.bytes() : 0;
+    b += bikmer.p ? bikmer.bytes() : 0;
     for (int d = 0; d < 2; ++d) b += jump[d].p ? jump[d].bytes() : 0;
     for (int d = 0; d < 2; ++d) b += occ_dna[d].p ? occ_dna[d].bytes() : 0, b += occ_gen[d].p ? occ_gen[d].bytes() : 0, b += delim_rows[d].p ? delim_rows[d].bytes() : 0;
     b += marks.p ? marks.bytes() : 0;
@@ -352,6 +353,22 @@ __global__ void compute_C2_kernel(IndexView<OccDna> ix, int dir, uint32_t* out) 
     row_t at = ix.C[y];
     DnaBlock b = occ.load(at >> 6);
     out[code] = (x < ix.sigma && y < ix.sigma) ? ix.C[x] + occ.rank(b, at, x) : 0u;
+}
+
+// bidirectional k-mer table (16 bytes per k-mer): largest k <= 13 with 16 * 4^k <= n / 2; needs both occ tables and C
+int build_bikmer(fmb_index* ix) {
+    if (!ix->dna || !ix->bidirectional || getenv("FMB_NO_BIKMER")) return FMB_OK;
+    uint32_t k = 0;
+    while (k < 13 && (uint64_t(32) << (2 * (k + 1))) <= ix->n) ++k;
+    if (k < 2) return FMB_OK;
+    const uint64_t count = uint64_t(1) << (2 * k);
+    cudaStream_t st = active_stream(ix);
+    FMB_TRY(ix->bikmer.alloc(count));
+    bikmer_table_kernel<<<grid_for(count, 256), 256, 0, st>>>(ix->view_dna(), k, count, ix->bikmer.p);
+    FMB_CUDA(cudaGetLastError());
+    FMB_CUDA(cudaStreamSynchronize(st));
+    ix->bikmer_k = k;
+    return FMB_OK;
 }
 
 // combined 64-byte locate records (needs occ table 0 and the marks); skipped when FMB_NO_LOCBLOCKS is set
@@ -557,6 +574,8 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, co
     if (ix->dna) rc = build_occ2(ix, 0);
     if (rc) return fail(rc);
     if (ix->dna && ix->bidirectional) rc = build_jump(ix, 1);
+    if (rc) return fail(rc);
+    rc = build_bikmer(ix);
     if (rc) return fail(rc);
     {
         const uint64_t have = (n + 63) / 64;

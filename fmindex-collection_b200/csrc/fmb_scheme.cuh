@@ -125,6 +125,12 @@ struct JumpView {
     const uint2* jump[2];         // [0]: farthest symbol in the low bits, [1]: nearest symbol in the low bits (= query order)
     const uint32_t* qpk;          // packed query symbols
     const uint8_t* qflags;        // 1 = query not packable
+    // bidirectional k-mer table: entry (2-bit packed k-mer, first symbol in the low bits) = {lb, lbRev, len, work} of the
+    // pattern after bikmer_k extendRight steps from the whole index; work = extensions << 16 | occ lookups the reference
+    // spends on those steps (fewer than k extensions when the pattern does not occur).  Serves roots whose first part
+    // is error free: the wide-interval phase of every search becomes one lookup.
+    const uint4* bikmer;
+    uint32_t bikmer_k;
 };
 
 // children of one expanded node are described by a bit mask and re-derived when they are written:
@@ -185,6 +191,29 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         if (sp.force_left) {                                                   // Backtracking.h: right to left
                             st.qposL = (sp.partition[0] - 1) & 0xFFFF;
                             st.qposR = 0;
+                        } else if (jv.bikmer_k && sp.u[s][0] == 0 && st.pev >= jv.bikmer_k && jv.qflags[st.qidx] == 0) {
+                            // error-free first part: its first bikmer_k symbols (always searched to the right) in one lookup;
+                            // the state is the one the error-free loop would have reached (SearchNg26.h:225-250)
+                            const uint64_t bit = 2 * (qoff[st.qidx] + st.qposR);
+                            const uint32_t wi = (uint32_t)(bit >> 5);
+                            uint32_t key = __funnelshift_r(__ldg(jv.qpk + wi), __ldg(jv.qpk + wi + 1), (uint32_t)bit & 31u);
+                            key &= (1u << (2 * jv.bikmer_k)) - 1u;
+                            const uint4 e = __ldg(jv.bikmer + key);
+                            n_phys += 1;
+                            n_ext += e.w >> 16;
+                            n_look += e.w & 0xFFFFu;
+                            st.lb = e.x; st.lb_rev = e.y; st.len = e.z;
+                            st.steps = jv.bikmer_k;
+                            st.qposR = (st.qposR + jv.bikmer_k) & 0xFFFF;
+                            st.pev -= jv.bikmer_k;
+                            st.mode = MODE_NOERR;
+                            if (st.pev == 0) {                                                 // :241-249
+                                st.part = 1;
+                                st.pev = (np != 1) ? sp.partition[sp.pi[s][1]] : 0;
+                                st.mode = MODE_NEXT;
+                            }
+                            const uint32_t lastq = __ldg(qsym + qoff[st.qidx] + ((st.qposR - 1) & 0xFFFF));
+                            if (st.mode == MODE_NEXT) st.side = side_set(side_set(st.side, 1, 0, lastq), 1, 1, lastq);
                         }
                         it = pack_item(st);
                     }
@@ -307,7 +336,9 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                 is_single = false;
                 noerr_cont = false;
                 bool go_dir = true;
-                if (st.mode == MODE_POS) {                                                          // search_next_pos :119-141
+                if (st.len == 0) {
+                    go_dir = false;                                                                 // a root whose k-mer does not occur
+                } else if (st.mode == MODE_POS) {                                                   // search_next_pos :119-141
                     if (st.NextPos) {
                         if (st.Right) st.qposR = (st.qposR + 1) & 0xFFFF; else st.qposL = (st.qposL - 1) & 0xFFFF;
                         st.pev -= 1;
@@ -318,7 +349,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         }
                     }
                 }
-                if (st.mode == MODE_NEXT) {                                                         // search_next :98-117
+                if (st.len != 0 && st.mode == MODE_NEXT) {                                          // search_next :98-117
                     if (st.part == np) {
                         bool ok = !EDIT || ((st.LInfo == INFO_M || st.LInfo == INFO_I) && (st.RInfo == INFO_M || st.RInfo == INFO_I));
                         report = ok && sp.l[st.search][np - 1] <= st.e && st.e <= sp.u[st.search][np - 1];

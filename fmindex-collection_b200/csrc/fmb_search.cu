@@ -26,13 +26,14 @@ int set_device(int device) {
     return FMB_OK;
 }
 
-constexpr uint32_t kStackCap = 256;          // items per warp (8 KB)
+constexpr uint32_t kStackCapDefault = 256;   // items per warp (8 KB)
 constexpr uint32_t kWarpsPerBlock = 8;
 
 template <class OCC, bool EDIT>
 int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const SchemeParams& sp, const fmb_queries* q, uint64_t n_roots, const Item* in_items,
                     uint64_t n_in, const SchemeOut& out, cudaStream_t st) {
     static int blocks_per_sm = 0, sms = 0;
+    static const uint32_t kStackCap = getenv("FMB_SCHEME_CAP") ? (uint32_t)atoi(getenv("FMB_SCHEME_CAP")) : kStackCapDefault;
     size_t smem = (size_t)kStackCap * kWarpsPerBlock * sizeof(Item);
     auto kern = scheme_search_kernel<OCC, EDIT>;
     if (!blocks_per_sm) {
@@ -55,6 +56,8 @@ int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const Schem
         jv.jump[1] = ix->jump[1].p;
         jv.qpk = q->packed.p;
         jv.qflags = q->flags.p;
+        jv.bikmer = ix->bikmer.p;
+        jv.bikmer_k = ix->bikmer.p ? ix->bikmer_k : 0;
     }
     // a warp keeps fast-forwarding while at least ff_min of its lanes have a single child; edit distance branches
     // at almost every node, so it only pays there when most of the warp is inside error-free stretches

@@ -139,7 +139,7 @@ struct JumpView {
 constexpr unsigned long long CH_MATCH = 1ull, CH_INS = 2ull, CH_JUMP = 4ull;
 constexpr int kFastForward = 12;
 #ifndef FMB_SCHEME_MINB
-#define FMB_SCHEME_MINB 3          // 3 blocks of 256 threads per SM -> at most 85 registers
+#define FMB_SCHEME_MINB 4          // 4 blocks of 256 threads per SM -> 64 registers (a few spills beat the lower occupancy of 80)
 #endif   // consecutive single-child expansions a lane may chain in registers per pop
 
 template <class OCC, bool EDIT>

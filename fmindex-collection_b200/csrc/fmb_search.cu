@@ -26,7 +26,7 @@ int set_device(int device) {
     return FMB_OK;
 }
 
-constexpr uint32_t kStackCapDefault = 256;   // items per warp (8 KB)
+constexpr uint32_t kStackCapDefault = 160;   // items per warp (5 KB; 40 KB per block, 4 blocks per SM)
 constexpr uint32_t kWarpsPerBlock = 8;
 
 template <class OCC, bool EDIT>

@@ -133,6 +133,140 @@ struct JumpView {
     uint32_t bikmer_k;
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Window simulation of a single-row subtree (edit distance).
+// On a single-row interval the search walks the text: the row after t consumed text symbols is LF^t(row) and the symbols it
+// meets are the entries of jump[row] (16 of them in one 8-byte lookup).  So the fate of an error child can be decided here,
+// without touching the index: the subtree is expanded with exactly the rules of search_next_dir_single /
+// search_next_dir_no_errors / search_next_pos (SearchNg26.h:119-141, 225-365) on the window symbols.  If every path dies
+// inside the window the child is never created and only its extensions are counted; if some path reaches the window end, a
+// part that changes direction, or the end of the search, the simulation gives up and the child is created as usual.
+// ---------------------------------------------------------------------------------------------------------------------
+struct SimState {          // one pending node, "ready to expand" (the NextPos advance already applied)
+    uint32_t m;            // text symbols consumed inside the window: the node looks at w[m]
+    uint32_t c;            // query symbols consumed since the window started
+    uint32_t part, pev, e;
+    uint32_t T;            // info of the walking side (INFO_*)
+    uint32_t lastRank, lastQRank;
+    uint32_t noerr;        // inside the error-free loop
+};
+__device__ __forceinline__ unsigned long long sim_pack(const SimState& s) {
+    return (unsigned long long)s.m | ((unsigned long long)s.c << 5) | ((unsigned long long)s.part << 13) | ((unsigned long long)s.pev << 17) |
+           ((unsigned long long)s.e << 33) | ((unsigned long long)s.T << 37) | ((unsigned long long)s.lastRank << 39) |
+           ((unsigned long long)s.lastQRank << 42) | ((unsigned long long)s.noerr << 45);
+}
+__device__ __forceinline__ SimState sim_unpack(unsigned long long v) {
+    SimState s;
+    s.m = v & 31; s.c = (v >> 5) & 255; s.part = (v >> 13) & 15; s.pev = (v >> 17) & 0xFFFF; s.e = (v >> 33) & 15;
+    s.T = (v >> 37) & 3; s.lastRank = (v >> 39) & 7; s.lastQRank = (v >> 42) & 7; s.noerr = (v >> 45) & 1;
+    return s;
+}
+
+// returns true when the whole subtree below `root` dies inside the window; `ext` receives its number of extensions
+template <bool EDIT>
+__device__ bool sim_subtree_dies(const SchemeParams& sp, uint32_t search, uint32_t R, uint32_t window /*16 x 2 bit, w[0] in the low bits*/,
+                                 const uint8_t* __restrict__ qptr /*query symbol of c = 0*/, const SimState& root, uint32_t& ext) {
+    constexpr int kStack = 12;
+    unsigned long long stack[kStack];
+    int top = 0;
+    stack[top++] = sim_pack(root);
+    uint32_t count = 0;
+    const uint32_t np = sp.n_parts;
+    const int dirstep = R ? 1 : -1;
+    int budget = 96;                                   // node visits; beyond that the child is simply created
+    while (top > 0) {
+        SimState s = sim_unpack(stack[--top]);
+        if (--budget < 0) return false;
+        // ---- the NextPos advance of a child: returns false when the path leaves what the window can decide
+        auto advance = [&](SimState& ch) -> bool {
+            ch.c += 1;
+            ch.pev -= 1;
+            if (ch.pev == 0) {
+                ch.part += 1;
+                if (ch.part == np) return false;                                                     // leaf: may report
+                const uint32_t nr = (sp.pi[search][ch.part - 1] < sp.pi[search][ch.part]) ? 1u : 0u;
+                if (sp.force_left || nr != R) return false;                                          // the walk turns around
+                ch.pev = sp.partition[sp.pi[search][ch.part]];
+            }
+            return true;
+        };
+        if (s.m >= 16) return false;                                                                 // survives the window
+        const uint32_t sym = ((window >> (2 * s.m)) & 3u) + 1;
+        const uint32_t q = qptr[dirstep * (int)s.c];
+        const uint32_t lp = sp.l[search][s.part], up = sp.u[search][s.part];
+        if (s.noerr) {                                                                               // search_next_dir_no_errors :225-250
+            count += 1;
+            if (sym != q) continue;
+            SimState ch = s;
+            ch.m += 1;
+            ch.lastRank = q; ch.lastQRank = q;     // only read after the loop ends (set there by the reference)
+            ch.c += 1; ch.pev -= 1;
+            if (ch.pev == 0) {
+                ch.T = INFO_M;
+                ch.noerr = 0;
+                ch.part += 1;
+                if (ch.part == np) return false;
+                const uint32_t nr = (sp.pi[search][ch.part - 1] < sp.pi[search][ch.part]) ? 1u : 0u;
+                if (sp.force_left || nr != R) return false;
+                ch.pev = sp.partition[sp.pi[search][ch.part]];
+            } else {
+                // lastRank / lastQRank / T stay those of the loop's entry until the part ends (:241-249)
+                ch.lastRank = s.lastRank; ch.lastQRank = s.lastQRank;
+            }
+            if (top >= kStack) return false;
+            stack[top++] = sim_pack(ch);
+            continue;
+        }
+        // ---- search_next_dir_single :251-365
+        const bool Deletion = EDIT && s.T != INFO_S && s.T != INFO_I;
+        const bool Insertion = EDIT && s.T != INFO_S && s.T != INFO_D;
+        const bool insAllowed = (s.pev > 1 || lp <= s.e + 1) && s.e + 1 <= up;
+        const bool mismatchAllowed = s.e + 1 <= up;
+        const bool matchAllowed = (s.pev > 1 || lp <= s.e) && s.e <= up && (s.T != INFO_I || q != s.lastQRank) && (s.T != INFO_D || q != s.lastRank);
+        count += 1;
+        if (top + 3 > kStack) return false;
+        if (sym == q) {
+            if (matchAllowed) {
+                if (!mismatchAllowed) {
+                    SimState ch = s;                   // same node again inside the error-free loop (:311-315)
+                    ch.noerr = 1;
+                    stack[top++] = sim_pack(ch);
+                } else {
+                    SimState ch = s;
+                    ch.m += 1; ch.lastRank = q; ch.lastQRank = q; ch.T = INFO_M;
+                    if (!advance(ch)) return false;
+                    stack[top++] = sim_pack(ch);
+                }
+            }
+            if (Deletion && mismatchAllowed) {
+                SimState ch = s;
+                ch.m += 1; ch.e += 1; ch.lastRank = sym; ch.T = INFO_D;
+                stack[top++] = sim_pack(ch);
+            }
+        } else if (mismatchAllowed) {
+            if (insAllowed) {                          // substitution
+                SimState ch = s;
+                ch.m += 1; ch.e += 1; ch.lastRank = sym; ch.lastQRank = q; ch.T = INFO_S;
+                if (!advance(ch)) return false;
+                stack[top++] = sim_pack(ch);
+            }
+            if (Deletion) {
+                SimState ch = s;
+                ch.m += 1; ch.e += 1; ch.lastRank = sym; ch.T = INFO_D;
+                stack[top++] = sim_pack(ch);
+            }
+        }
+        if (Insertion && insAllowed) {
+            SimState ch = s;
+            ch.e += 1; ch.lastQRank = q; ch.T = INFO_I;
+            if (!advance(ch)) return false;
+            stack[top++] = sim_pack(ch);
+        }
+    }
+    ext = count;
+    return true;
+}
+
 // children of one expanded node are described by a bit mask and re-derived when they are written:
 //   bit 0 match / error-free continuation, bit 1 insertion, bit 2 sixteen-symbol jump,
 //   bits 8+c deletion(c), bits 36+c substitution(c)
@@ -158,6 +292,8 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
     bool more_roots = true;
     const uint32_t np = sp.n_parts;
     const uint32_t first_symb = 1;       // FirstSymb of delimited indices (fmindex/BiFMIndex.h:26)
+    const bool sim_all = (ff_min >> 8) & 1;      // simulate error children at every error level, not only the last one
+    ff_min &= 0xFF;
 
     for (;;) {
         // ---- refill: pull roots while fewer than 32 items are pending -------------------------------------
@@ -494,6 +630,58 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                                     } else if (mismatchAllowed) {
                                         if (insAllowed) cmask |= 1ull << (36 + single_sym);
                                         if (Deletion) cmask |= 1ull << (8 + single_sym);
+                                    }
+                                }
+                                // ---- window simulation of the error children -------------------------------------------------
+                                // (sim_subtree_dies above): children whose whole subtree dies within the next 16 text symbols are
+                                // accounted for -- their extensions are counted -- but never created.
+                                const unsigned long long err_children = cmask & ~(CH_MATCH | CH_JUMP);
+                                if (EDIT && err_children && jv.jump[R] != nullptr && single_sym >= first_symb && (sim_all || st.e + 1 == up)) {
+                                    const uint2 je = __ldg(jv.jump[R] + lo);
+                                    n_phys += 1;
+                                    if (je.x != kJumpInvalid) {
+                                        // window in walking order, w[0] (= this row's symbol) in the low bits
+                                        uint32_t window = je.y;
+                                        if (!R) {                                   // direction 0 stores the nearest symbol in the high bits
+                                            window = __brev(window);
+                                            window = ((window & 0xAAAAAAAAu) >> 1) | ((window & 0x55555555u) << 1);
+                                        }
+                                        const uint8_t* qptr = qsym + qbase + (R ? st.qposR : st.qposL);
+                                        unsigned long long rest = err_children;
+                                        while (rest) {
+                                            const uint32_t bit = __ffsll((long long)rest) - 1;
+                                            rest &= rest - 1;
+                                            SimState cs;
+                                            cs.m = 1; cs.c = 0; cs.part = st.part; cs.pev = st.pev; cs.e = st.e + 1; cs.noerr = 0;
+                                            cs.lastRank = lastRank; cs.lastQRank = lastQRank;
+                                            bool ok = true;                      // false: the child's advance already leaves the window's reach
+                                            bool adv = false;
+                                            if (bit == 1) {                      // insertion: stays on this row
+                                                cs.m = 0; cs.lastQRank = q; cs.T = INFO_I; adv = true;
+                                            } else if (bit >= 36) {              // substitution
+                                                cs.lastRank = single_sym; cs.lastQRank = q; cs.T = INFO_S; adv = true;
+                                            } else {                             // deletion: the query symbol is not consumed
+                                                cs.lastRank = single_sym; cs.T = INFO_D;
+                                            }
+                                            if (adv) {
+                                                cs.c = 1;
+                                                cs.pev -= 1;
+                                                if (cs.pev == 0) {
+                                                    cs.part += 1;
+                                                    if (cs.part == np) ok = false;
+                                                    else {
+                                                        const uint32_t nr = (sp.pi[st.search][cs.part - 1] < sp.pi[st.search][cs.part]) ? 1u : 0u;
+                                                        if (sp.force_left || nr != R) ok = false;
+                                                        else cs.pev = sp.partition[sp.pi[st.search][cs.part]];
+                                                    }
+                                                }
+                                            }
+                                            uint32_t sim_ext = 0;
+                                            if (ok && sim_subtree_dies<EDIT>(sp, st.search, R, window, qptr, cs, sim_ext)) {
+                                                cmask &= ~(1ull << bit);
+                                                n_ext += sim_ext; n_look += sim_ext;
+                                            }
+                                        }
                                     }
                                 }
                             }

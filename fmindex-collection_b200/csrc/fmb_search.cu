@@ -62,7 +62,9 @@ int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const Schem
     // a warp keeps fast-forwarding while at least ff_min of its lanes have a single child; edit distance branches
     // at almost every node, so it only pays there when most of the warp is inside error-free stretches
     static const char* ff_env = getenv("FMB_SCHEME_FFMIN");
-    const uint32_t ff_min = ff_env ? (uint32_t)atoi(ff_env) : (EDIT ? 24u : 8u);
+    static const char* sim_env = getenv("FMB_SCHEME_SIMALL");
+    const uint32_t sim_all = sim_env ? (uint32_t)atoi(sim_env) : 1u;
+    const uint32_t ff_min = (ff_env ? (uint32_t)atoi(ff_env) : (EDIT ? 16u : 8u)) | (sim_all << 8);
     kern<<<grid, 256, smem, st>>>(view, sp, q->symbols.p, q->offsets.p, jv, n_roots, in_items, n_in, out, kStackCap, ff_min);
     FMB_CUDA(cudaGetLastError());
     note_launches(1);

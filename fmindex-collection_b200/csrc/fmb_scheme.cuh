@@ -142,6 +142,13 @@ struct JumpView {
 // inside the window the child is never created and only its extensions are counted; if some path reaches the window end, a
 // part that changes direction, or the end of the search, the simulation gives up and the child is created as usual.
 // ---------------------------------------------------------------------------------------------------------------------
+// a path still alive after SIM_DEPTH window symbols counts as a survivor (measured: 8 is as good as the full 16)
+#ifndef SIM_DEPTH
+#define SIM_DEPTH 8
+#endif
+#ifndef SIM_BUDGET
+#define SIM_BUDGET 96
+#endif
 struct SimState {          // one pending node, "ready to expand" (the NextPos advance already applied)
     uint32_t m;            // text symbols consumed inside the window: the node looks at w[m]
     uint32_t c;            // query symbols consumed since the window started
@@ -173,7 +180,7 @@ __device__ bool sim_subtree_dies(const SchemeParams& sp, uint32_t search, uint32
     uint32_t count = 0;
     const uint32_t np = sp.n_parts;
     const int dirstep = R ? 1 : -1;
-    int budget = 96;                                   // node visits; beyond that the child is simply created
+    int budget = SIM_BUDGET;                           // node visits; beyond that the child is simply created
     while (top > 0) {
         SimState s = sim_unpack(stack[--top]);
         if (--budget < 0) return false;
@@ -190,7 +197,7 @@ __device__ bool sim_subtree_dies(const SchemeParams& sp, uint32_t search, uint32
             }
             return true;
         };
-        if (s.m >= 16) return false;                                                                 // survives the window
+        if (s.m >= SIM_DEPTH) return false;                                                          // survives the window
         const uint32_t sym = ((window >> (2 * s.m)) & 3u) + 1;
         const uint32_t q = qptr[dirstep * (int)s.c];
         const uint32_t lp = sp.l[search][s.part], up = sp.u[search][s.part];

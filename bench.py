@@ -204,6 +204,8 @@ def main():
     dist = None
     if world > 1 and args.impl == "ours":
         import torch.distributed as dist
+        # NCCL prints its version banner to stdout: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", device))
 
     scheme, partition, edit = workload_scheme(wl, L)

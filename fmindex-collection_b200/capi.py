@@ -46,7 +46,7 @@ SYMBOLS = [
     "fmb_results_count", "fmb_results_kind", "fmb_results_fetch_hits", "fmb_results_fetch_locs", "fmb_results_fetch_locs32",
     "fmb_results_get_stats", "fmb_results_destroy",
     "fmb_search_and_locate",
-    "fmb_index_set_exact_mode", "fmb_synth_text_device", "fmb_synth_reads_device", "fmb_synth_reads_err_device", "fmb_synth_repeat_text_device", "fmb_synth_unit_reads_device", "fmb_index_set_stream", "fmb_kernel_launch_count", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
+    "fmb_index_set_exact_mode", "fmb_index_set_locate_mode", "fmb_synth_text_device", "fmb_synth_reads_device", "fmb_synth_reads_err_device", "fmb_synth_repeat_text_device", "fmb_synth_unit_reads_device", "fmb_index_set_stream", "fmb_kernel_launch_count", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
 ]
 
 
@@ -170,6 +170,10 @@ class Index:
     def set_exact_mode(self, mode):
         """0 = auto (two-symbol steps when available), 1 = one-symbol kernel (fills the algorithmic counters), 2 = two-symbol"""
         _check(lib().fmb_index_set_exact_mode(self.h, C.c_int(mode)))
+
+    def set_locate_mode(self, mode):
+        """0 = auto (locate shortcut table when available), 1 = always walk LF steps to the nearest sample"""
+        _check(lib().fmb_index_set_locate_mode(self.h, C.c_int(mode)))
 
     # String_c
     def symbol(self, idx, dir=0):

@@ -287,6 +287,10 @@ struct IndexView {
     // u32, pad} so that one LF step of locate touches ONE line instead of two (occ block + marker word); a lane pair
     // fetches the two 32-byte halves with one request.  nullptr when not built.
     const uint4* locblocks;
+    // locate shortcut (optional): per row  sample_index << loc_step_bits | steps  -- the result of the row's LF walk to its
+    // nearest sampled row, precomputed at build time, so that locate(row) is two independent fetches (this word + the sample)
+    const uint32_t* locrow;
+    uint32_t loc_step_bits;
 };
 
 struct Cursor {             // BiFMIndexCursor{lb, lbRev, len, steps}, fmindex/BiFMIndexCursor.h:22-37

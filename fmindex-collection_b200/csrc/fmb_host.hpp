@@ -93,6 +93,9 @@ struct fmb_index {
     fmb::DevBuf<uint4> marks;
     fmb::DevBuf<uint2> samples;
     fmb::DevBuf<uint4> locblocks;        // combined occ + marker records for locate (sigma <= 5)
+    fmb::DevBuf<uint32_t> locrow;        // locate shortcut: per row sample index << loc_step_bits | LF steps
+    uint32_t loc_step_bits = 0;
+    int locate_mode = 0;                 // FMB_LOCATE_*
     uint64_t n_samples = 0;
     uint64_t C[65] = {0};
     // two-symbol table (OccDna2), sigma <= 5 only

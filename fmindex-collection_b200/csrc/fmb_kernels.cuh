@@ -819,6 +819,86 @@ __global__ void __launch_bounds__(256) locate_pair_kernel(const __grid_constant_
     }
 }
 
+// K4c: locate shortcut table.  locrow[row] = sample_index << step_bits | steps of the LF walk of `row` (built by walking every row
+// once with the lane-pair walk above); locate(row) then is locrow[row] + samples[index]: two line fetches instead of ~10.
+__global__ void __launch_bounds__(256) locrow_build_kernel(const __grid_constant__ IndexView<OccDna> ix, uint32_t step_bits, uint32_t* __restrict__ out,
+                                                           uint32_t* __restrict__ overflow) {
+    const uint64_t npairs = ((uint64_t)gridDim.x * blockDim.x) >> 1;
+    uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const uint32_t role = threadIdx.x & 1;
+    const uint32_t pmask = 3u << (threadIdx.x & 30);
+    const OccDna& occ = ix.occ[0];
+    uint32_t steps = 0;
+    row_t row = (row_t)t;
+    bool active = t < ix.n;
+    while (active) {
+        uint32_t a0, a1, a2, a3, a4, a5, a6, a7;
+        asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=r"(a4), "=r"(a5), "=r"(a6), "=r"(a7)
+                     : "l"(ix.locblocks + ((size_t)(row >> 6) * 4 + role * 2)));
+        uint32_t mine;
+        if (role) {
+            uint64_t bits = (uint64_t)a0 | ((uint64_t)a1 << 32);
+            uint32_t o = row & 63;
+            mine = ((bits >> o) & 1) ? 1u + a2 + __popcll(bits & low_mask(o)) : 0u;
+        } else {
+            DnaBlock b;
+            b.cnt[0] = a0; b.cnt[1] = a1; b.cnt[2] = a2; b.cnt[3] = a3;
+            b.p0 = (uint64_t)a4 | ((uint64_t)a5 << 32);
+            b.p1 = (uint64_t)a6 | ((uint64_t)a7 << 32);
+            uint32_t c = occ.symbol(b, row);
+            mine = ix.C[c] + occ.rank(b, row, c);
+        }
+        uint32_t other = __shfl_xor_sync(pmask, mine, 1);
+        uint32_t sampled = role ? mine : other;
+        if (sampled) {
+            if (role == 0) {
+                const uint32_t idx = sampled - 1;
+                if (steps >= (1u << step_bits) || idx >= (1u << (32 - step_bits))) atomicOr(overflow, 1u);
+                out[t] = (idx << step_bits) | steps;
+            }
+            t += npairs;
+            active = t < ix.n;
+            row = (row_t)t;
+            steps = 0;
+        } else {
+            row = role ? other : mine;
+            ++steps;
+        }
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) locate_shortcut_kernel(const __grid_constant__ IndexView<OccDna> ix, const HitRec* __restrict__ hits,
+                                                              const uint32_t* __restrict__ starts, uint32_t nh, uint32_t total,
+                                                              LocRec* __restrict__ out, unsigned long long* __restrict__ counters) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t steps = 0;
+    if (t < total) {
+        uint32_t lo = (total == nh) ? t : 0, hi = (total == nh) ? t + 1 : nh;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(starts + mid) <= t) lo = mid; else hi = mid;
+        }
+        const HitRec* h = hits + lo;
+        const row_t row = __ldg(&h->lb) + (t - __ldg(starts + lo));
+        const uint32_t w = __ldg(ix.locrow + row);
+        steps = w & ((1u << ix.loc_step_bits) - 1u);
+        const uint2 sample = __ldg(ix.samples + (w >> ix.loc_step_bits));
+        LocRec r;
+        r.qidx = __ldg(&h->qidx); r.seq = sample.x; r.pos = sample.y + steps; r.e = __ldg(&h->e);
+        out[t] = r;
+    }
+    if (COUNT) {
+        uint32_t s = steps;          // the LF steps the walk WOULD take: the algorithmic work of SURVEY.md §8d stays reported
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        if ((threadIdx.x & 31) == 0 && s) {
+            atomicAdd(counters + 2, (unsigned long long)s);
+            atomicAdd(counters + 1, (unsigned long long)s);
+        }
+    }
+}
+
 // index.locate(row) for arbitrary rows (fmindex/BiFMIndex.h:177-202): same LF walk as locate_kernel, row list input
 template <class OCC>
 __global__ void __launch_bounds__(256) locate_rows_kernel(const __grid_constant__ IndexView<OCC> ix, const uint64_t* __restrict__ rows, uint64_t count,

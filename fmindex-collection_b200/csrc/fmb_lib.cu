@@ -182,6 +182,8 @@ fmb::IndexView<fmb::OccDna> fmb_index::view_dna() const {
     v.marks = marks.p;
     v.samples = samples.p;
     v.locblocks = locblocks.p;
+    v.locrow = locrow.p;
+    v.loc_step_bits = loc_step_bits;
     return v;
 }
 
@@ -237,6 +239,7 @@ uint64_t fmb_index::device_bytes() const {
     for (int d = 0; d < 2; ++d) b += occ_dna[d].p ? occ_dna[d].bytes() : 0, b += occ_gen[d].p ? occ_gen[d].bytes() : 0, b += delim_rows[d].p ? delim_rows[d].bytes() : 0;
     b += marks.p ? marks.bytes() : 0;
     b += locblocks.p ? locblocks.bytes() : 0;
+    b += locrow.p ? locrow.bytes() : 0;
     b += samples.p ? samples.bytes() : 0;
     return b;
 }
@@ -380,6 +383,35 @@ int build_locblocks(fmb_index* ix) {
     build_locblocks_kernel<<<grid_for(nblocks, 256), 256, 0, st>>>(ix->occ_dna[0].p, ix->marks.p, nblocks, ix->locblocks.p);
     FMB_CUDA(cudaGetLastError());
     FMB_CUDA(cudaStreamSynchronize(st));
+    // locate shortcut table: walk every row once.  The word packs sample index and step count; when they do not fit 32 bits (very
+    // sparse or irregular sampling) the table is dropped and locate keeps walking.  FMB_NO_LOCROW disables it.
+    if (!getenv("FMB_NO_LOCROW")) {
+        uint32_t idx_bits = 1;
+        while (idx_bits < 32 && (uint64_t(1) << idx_bits) < ix->n_samples) ++idx_bits;
+        const uint32_t step_bits = 32 - idx_bits;
+        size_t free_b = 0, total_b = 0;
+        pool_trim();
+        FMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (step_bits >= 1 && (double)free_b > 4.0 * (double)ix->n * 1.5 + (double)(1u << 28)) {
+            FMB_TRY(ix->locrow.alloc(ix->n));
+            DevBuf<uint32_t> ovf;
+            FMB_TRY(ovf.alloc(1));
+            FMB_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(uint32_t), st));
+            int sms = 0;
+            FMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
+            ix->loc_step_bits = step_bits;
+            unsigned grid = (unsigned)std::min<uint64_t>(grid_for(ix->n * 2, 256), (uint64_t)sms * 8);
+            locrow_build_kernel<<<grid, 256, 0, st>>>(ix->view_dna(), step_bits, ix->locrow.p, ovf.p);
+            FMB_CUDA(cudaGetLastError());
+            uint32_t h_ovf = 0;
+            FMB_CUDA(cudaMemcpyAsync(&h_ovf, ovf.p, sizeof h_ovf, cudaMemcpyDeviceToHost, st));
+            FMB_CUDA(cudaStreamSynchronize(st));
+            if (h_ovf) {                 // some walk is longer than the step field allows
+                ix->locrow.release();
+                ix->loc_step_bits = 0;
+            }
+        }
+    }
     return FMB_OK;
 }
 
@@ -903,7 +935,9 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
     cudaEventCreate(&ev_m1);
     if (total) {
         cudaEventRecord(ev_m0, st);
-        if (ix->dna && ix->locblocks.p) {
+        if (ix->dna && ix->locrow.p && ix->locate_mode != FMB_LOCATE_WALK) {
+            locate_shortcut_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(ix->view_dna(), hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p);
+        } else if (ix->dna && ix->locblocks.p) {
             auto v = ix->view_dna();
             // persistent grid: every SM full of lane pairs (8 blocks x 256 threads), rows handed out with a grid stride
             static int sms = 0;
@@ -1088,6 +1122,11 @@ int fmb_index_set_exact_mode(fmb_index* ix, int mode) {
     if (!ix || mode < 0 || mode > 2) { set_error("bad argument"); return FMB_EINVAL; }
     if (mode == FMB_EXACT_TWO_SYMBOL && !ix->occ2[0].p) { set_error("index has no two-symbol table"); return FMB_EUNSUPPORTED; }
     ix->exact_mode = mode;
+    return FMB_OK;
+}
+int fmb_index_set_locate_mode(fmb_index* ix, int mode) {
+    if (!ix || mode < 0 || mode > 1) { set_error("bad argument"); return FMB_EINVAL; }
+    ix->locate_mode = mode;
     return FMB_OK;
 }
 uint64_t fmb_kernel_launch_count(void) { return fmb::g_launches.load(); }

@@ -192,6 +192,13 @@ int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uin
 #define FMB_EXACT_TWO_SYMBOL  2
 int  fmb_index_set_exact_mode(fmb_index* ix, int mode);
 
+/* Locate kernel selection.  FMB_LOCATE_AUTO (default): the locate shortcut table when the index has one (per row the
+ * sample its LF walk ends at and the walk's length, precomputed at build time: two fetches per row), else the LF walk.
+ * FMB_LOCATE_WALK: always walk (the kernel SURVEY.md §8 a13 describes).  Results are identical. */
+#define FMB_LOCATE_AUTO  0
+#define FMB_LOCATE_WALK  1
+int  fmb_index_set_locate_mode(fmb_index* ix, int mode);
+
 /* ---- synthetic data + pinned host memory helpers (bench / tests) ------------------------------------------- */
 /* T[i] = 1 + (splitmix64(seed + i) % (sigma-1)) for i < n-1, T[n-1] = 0; written to a device buffer owned by the
  * library (free with fmb_device_free).  The same generator is restated in fmb200/synth.py for the CPU side. */

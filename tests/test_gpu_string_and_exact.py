@@ -179,3 +179,43 @@ def test_larger_single_sequence(gpu):
     for r in loc:
         first.setdefault(int(r["qidx"]), set()).add(int(r["pos"]))
     assert all(int(src[q]) in first[q] for q in range(len(src)))
+
+
+def test_locate_modes_and_irregular_sampling(gpu):
+    """locate shortcut table vs LF walk, and a sparse array whose walks are too long for the shortcut word (table dropped)"""
+    from fmb200 import synth
+    from oracle.pyoracle import Oracle
+    text = synth.multi_text([6000, 500], 5, 31)
+    o, g = make_index_pair(gpu, text, 5, 16)
+    reads, _ = synth.reads_from_text(text[:6001], 400, 12, 4)
+    sym, off = synth.flatten(reads)
+    res = g.search_exact(g.upload(sym, off))
+    exp = o.locate(o.search_exact(sym, off))
+    fast = g.locate(res)
+    g.set_locate_mode(1)
+    walk = g.locate(res)
+    g.set_locate_mode(0)
+    assert locs_equal(fast.locs(), exp) and locs_equal(walk.locs(), exp)
+    assert fast.stats.lf_steps == walk.stats.lf_steps > 0
+    rows = np.arange(0, text.size, 7, dtype=np.uint64)
+    seq, pos, steps = g.locate_rows(rows)
+    for r, s, p, k in zip(rows[:200], seq, pos, steps):
+        assert o.locate_row(int(r)) == (int(s), int(p), int(k))
+    # SA-space sampling of every 97th row only: walks of up to ~100 steps, the sample of a row is no longer "pos % rate == 0"
+    bwt, rev = o.bwt, o.bwt_rev
+    sa = o.sa
+    keep = np.zeros(text.size, dtype=bool)
+    keep[::97] = True
+    delim = np.flatnonzero(text == 0)
+    seq_of = np.searchsorted(delim, sa[keep], side="left").astype(np.uint32)
+    start = np.concatenate([[0], delim + 1])
+    pos_of = (sa[keep] - start[seq_of]).astype(np.uint32)
+    bm = np.zeros((text.size + 63) // 64, dtype=np.uint64)
+    idx = np.flatnonzero(keep)
+    np.bitwise_or.at(bm, idx // 64, np.uint64(1) << (idx % 64).astype(np.uint64))
+    g2 = gpu.Index.from_bwt(5, bwt, rev, bm, seq_of, pos_of)
+    o2 = Oracle.from_bwt(5, bwt, rev, bm, seq_of, pos_of)
+    res2 = g2.search_exact(g2.upload(sym, off))
+    exp2 = o2.locate(o2.search_exact(sym, off))
+    assert locs_equal(g2.locate(res2).locs(), exp2)
+    assert locs_equal(exp2, exp)                      # text positions do not depend on the sampling

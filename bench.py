@@ -332,10 +332,14 @@ def main():
     k_ms = float(np.mean(search_ms))
     l_ms = float(np.mean(locate_ms))
     loc_lookups = n_locs * 2 + st_l.lf_steps * 2     # per row: marker test + sample fetch, per LF step: occ block + marker word
-    locate_info = {"kernel": "locate_pair_kernel", "kernel_ms": l_ms, "lf_steps_per_row": st_l.lf_steps / max(n_locs, 1),
+    tables = index.info.tables
+    shortcut = bool(tables & 32)                     # FMB_TABLE_LOCROW: the walk is precomputed, two fetches per row
+    loc_lines = 2 * n_locs if shortcut else (n_locs + st_l.lf_steps + n_locs)
+    locate_info = {"kernel": "locate_shortcut_kernel" if shortcut else ("locate_pair_kernel" if tables & 16 else "locate_kernel"),
+                   "kernel_ms": l_ms, "lf_steps_per_row": st_l.lf_steps / max(n_locs, 1),
                    "algorithmic_bytes_per_launch": loc_lookups * 32.0, "achieved": loc_lookups * 32.0 / (l_ms * 1e-3) / 1e9,
                    "frac": loc_lookups * 32.0 / (l_ms * 1e-3) / 1e9 / peak,
-                   "physical_lines_per_s": (n_locs + st_l.lf_steps + n_locs) / (l_ms * 1e-3)}
+                   "physical_lines_per_row": loc_lines / max(n_locs, 1), "physical_lines_per_s": loc_lines / (l_ms * 1e-3)}
 
     def ncu_traffic(kernel, key):
         try:
@@ -346,9 +350,10 @@ def main():
             return None
 
     if wl == "locate-heavy":
-        roofline = {"bound": "hbm", "kernel": "locate_pair_kernel", "achieved": locate_info["achieved"], "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": locate_info["kernel"], "achieved": locate_info["achieved"], "peak": peak, "unit": "GB/s",
                     "frac": locate_info["frac"], "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": loc_lookups * 32.0,
                     "kernel_ms": l_ms, "located_rows_per_s": n_locs / (l_ms * 1e-3), "lf_steps_per_row": locate_info["lf_steps_per_row"],
+                    "physical_lines_per_row": locate_info["physical_lines_per_row"], "physical_lines_per_s": locate_info["physical_lines_per_s"],
                     "search_kernel_ms": k_ms}
     elif scheme is None:
         alg_bytes = alg_lookups * 32.0
@@ -377,6 +382,7 @@ def main():
             "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload, "l2_policy": "inputs larger than L2 (index image %.1f GB, reads %.2f GB)" % (index.info.device_bytes / 1e9, nq * L / 1e9),
+                       "index_tables": [name for bit, name in ((1, "pair"), (2, "kmer"), (4, "jump"), (8, "jump_rev"), (16, "locblock"), (32, "locrow"), (64, "bikmer")) if tables & bit],
                        "hits_per_step": n_hits, "located_rows_per_step": n_locs},
             "roofline": roofline,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -6,6 +6,28 @@
 
 namespace fmb {
 
+// Work counters: one global atomic per BLOCK and counter.  (One per warp meant > 10^6 same-address atomics per launch, which
+// serialise in one L2 slice and cost more than the kernel's real work: locate went from 1.4 ms to the time of its loads.)
+// Every thread of the block must call this (it contains __syncthreads).
+__device__ __forceinline__ void block_count2(unsigned long long* counters, int slot_a, uint32_t a, int slot_b, uint32_t b) {
+    __shared__ unsigned int s_cnt[2];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+        b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(&s_cnt[0], a);
+        if (b) atomicAdd(&s_cnt[1], b);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt[0]) atomicAdd(counters + slot_a, (unsigned long long)s_cnt[0]);
+        if (slot_b >= 0 && s_cnt[1]) atomicAdd(counters + slot_b, (unsigned long long)s_cnt[1]);
+    }
+}
+
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     uint64_t z = x + 0x9e3779b97f4a7c15ull;
     z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
@@ -352,16 +374,7 @@ __global__ void __launch_bounds__(256) exact_search_kernel(const __grid_constant
         out_lb[q] = lb;
         out_len[q] = len;
     }
-    if (COUNT) {
-        for (int o = 16; o > 0; o >>= 1) {
-            ext += __shfl_xor_sync(0xFFFFFFFFu, ext, o);
-            lookups += __shfl_xor_sync(0xFFFFFFFFu, lookups, o);
-        }
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(counters + 0, (unsigned long long)ext);
-            atomicAdd(counters + 1, (unsigned long long)lookups);
-        }
-    }
+    if (COUNT) block_count2(counters, 0, ext, 1, lookups);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -646,9 +659,7 @@ __global__ void __launch_bounds__(256, MINB) exact_search2_kernel(const __grid_c
     }
     if (COUNT) {
         // [2] = line requests issued by this kernel (physical work), counted once per group
-        uint32_t v = (sub == 0) ? lines : 0;
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(counters + 2, (unsigned long long)v);
+        block_count2(counters, 2, (sub == 0) ? lines : 0, -1, 0);
     }
 }
 
@@ -720,14 +731,7 @@ __global__ void __launch_bounds__(256) locate_kernel(const __grid_constant__ Ind
         r.qidx = h.qidx; r.seq = sample.x; r.pos = sample.y + steps; r.e = h.e;
         out[t] = r;
     }
-    if (COUNT) {
-        uint32_t s = steps;
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-        if ((threadIdx.x & 31) == 0 && s) {
-            atomicAdd(counters + 2, (unsigned long long)s);
-            atomicAdd(counters + 1, (unsigned long long)s);
-        }
-    }
+    if (COUNT) block_count2(counters, 2, steps, 1, steps);
 }
 
 // K4b: locate with the combined 64-byte locate blocks.  A pair of lanes owns one SA row: the even lane fetches the
@@ -809,14 +813,7 @@ __global__ void __launch_bounds__(256) locate_pair_kernel(const __grid_constant_
             ++steps;
         }
     }
-    if (COUNT) {
-        uint32_t s = steps_total;
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-        if ((threadIdx.x & 31) == 0 && s) {
-            atomicAdd(counters + 2, (unsigned long long)s);
-            atomicAdd(counters + 1, (unsigned long long)s);
-        }
-    }
+    if (COUNT) block_count2(counters, 2, steps_total, 1, steps_total);
 }
 
 // K4c: locate shortcut table.  locrow[row] = sample_index << step_bits | steps of the LF walk of `row` (built by walking every row
@@ -889,14 +886,8 @@ __global__ void __launch_bounds__(256) locate_shortcut_kernel(const __grid_const
         r.qidx = __ldg(&h->qidx); r.seq = sample.x; r.pos = sample.y + steps; r.e = __ldg(&h->e);
         out[t] = r;
     }
-    if (COUNT) {
-        uint32_t s = steps;          // the LF steps the walk WOULD take: the algorithmic work of SURVEY.md §8d stays reported
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-        if ((threadIdx.x & 31) == 0 && s) {
-            atomicAdd(counters + 2, (unsigned long long)s);
-            atomicAdd(counters + 1, (unsigned long long)s);
-        }
-    }
+    // the LF steps the walk WOULD take: the algorithmic work of SURVEY.md §8d stays reported
+    if (COUNT) block_count2(counters, 2, steps, 1, steps);
 }
 
 // index.locate(row) for arbitrary rows (fmindex/BiFMIndex.h:177-202): same LF walk as locate_kernel, row list input

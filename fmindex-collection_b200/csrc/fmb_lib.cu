@@ -651,6 +651,9 @@ int fmb_index_get_info(const fmb_index* ix, fmb_index_info* info) {
     info->occ_block_bytes = ix->dna ? 32 : ix->gen_stride;
     info->occ_block_rows = 64;
     info->device = ix->device;
+    info->tables = (ix->occ2[0].p ? FMB_TABLE_PAIR : 0) | (ix->kmer.p ? FMB_TABLE_KMER : 0) | (ix->jump[0].p ? FMB_TABLE_JUMP : 0) |
+                   (ix->jump[1].p ? FMB_TABLE_JUMP_REV : 0) | (ix->locblocks.p ? FMB_TABLE_LOCBLOCK : 0) | (ix->locrow.p ? FMB_TABLE_LOCROW : 0) |
+                   (ix->bikmer.p ? FMB_TABLE_BIKMER : 0);
     return FMB_OK;
 }
 

@@ -64,8 +64,15 @@ typedef struct {
     uint32_t occ_block_bytes;  /* bytes fetched by one rank lookup (32 for sigma<=5)       */
     uint32_t occ_block_rows;   /* BWT rows covered by one occ block                        */
     int32_t  device;
-    uint32_t reserved;
+    uint32_t tables;           /* optional accelerating tables the image holds, FMB_TABLE_* bits  */
 } fmb_index_info;
+#define FMB_TABLE_PAIR     1u   /* two-symbol pair table (128-byte lines)          */
+#define FMB_TABLE_KMER     2u   /* k-mer interval table                            */
+#define FMB_TABLE_JUMP     4u   /* LF^16 jump table, direction 0                   */
+#define FMB_TABLE_JUMP_REV 8u   /* LF^16 jump table, direction 1                   */
+#define FMB_TABLE_LOCBLOCK 16u  /* combined occ + marker records for locate        */
+#define FMB_TABLE_LOCROW   32u  /* locate shortcut table                           */
+#define FMB_TABLE_BIKMER   64u  /* bidirectional k-mer table for scheme roots      */
 
 /* work counters of the last search/locate call on a result set (device-side counting, optional) */
 typedef struct {

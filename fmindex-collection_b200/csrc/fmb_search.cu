@@ -249,9 +249,11 @@ int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uin
     if (stats) *stats = fmb_stats{};
     if (nq == 0) return FMB_OK;
     FMB_TRY(set_device(ix->device));
-    const uint64_t chunk = n_searches ? (1u << 18) : (1u << 20);
+    static const int env_chunk = getenv("FMB_E2E_CHUNK_LOG2") ? atoi(getenv("FMB_E2E_CHUNK_LOG2")) : 0;
+    static const int env_threads = getenv("FMB_E2E_THREADS") ? atoi(getenv("FMB_E2E_THREADS")) : 0;
+    const uint64_t chunk = env_chunk ? (uint64_t(1) << env_chunk) : (1u << 20);      // measured: 2^20 beats 2^18 for the scheme searches too
     const uint64_t n_chunks = (nq + chunk - 1) / chunk;
-    const int n_threads = (int)std::min<uint64_t>(3, n_chunks);
+    const int n_threads = (int)std::min<uint64_t>(env_threads ? env_threads : 3, n_chunks);
     std::atomic<uint64_t> next_chunk{0}, written{0}, needed{0};
     std::atomic<int> err{FMB_OK};
     std::mutex mu;

@@ -158,6 +158,9 @@ static int exclusive_sum_u32(const uint32_t* in, uint32_t* out, uint64_t count, 
     return FMB_OK;
 }
 
+struct ToU64 {
+    __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; }
+};
 struct Uint4Add {
     __host__ __device__ uint4 operator()(const uint4& a, const uint4& b) const {
         return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
@@ -928,6 +931,26 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
     EventTimer tm(st);
     hit_lengths_kernel<<<grid_for(nh + 1, 256), 256, 0, st>>>(hits->hits.p, nh, starts.p);
     note_launches(1);
+    {
+        // rows are numbered with 32 bits on the device: refuse (loudly) a result set whose intervals sum to 2^32 rows or more
+        DevBuf<unsigned long long> d_sum;
+        if ((rc = d_sum.alloc(1))) return fail(rc);
+        size_t tmp_bytes = 0;
+        cub::TransformInputIterator<unsigned long long, ToU64, const uint32_t*> it(starts.p, ToU64{});
+        cub::DeviceReduce::Sum(nullptr, tmp_bytes, it, d_sum.p, (int64_t)(nh + 1), st);
+        DevBuf<uint8_t> tmp;
+        if ((rc = tmp.alloc(tmp_bytes))) return fail(rc);
+        cub::DeviceReduce::Sum(tmp.p, tmp_bytes, it, d_sum.p, (int64_t)(nh + 1), st);
+        unsigned long long h_sum = 0;
+        if (cudaMemcpyAsync(&h_sum, d_sum.p, sizeof h_sum, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+            set_error("locate: row count failed");
+            return fail(FMB_ECUDA);
+        }
+        if (h_sum >= 0xFFFFFFFFull) {
+            set_error("locate: the hits cover %llu rows; this build locates fewer than 2^32 rows per call -- split the batch", h_sum);
+            return fail(FMB_EOVERFLOW);
+        }
+    }
     if ((rc = exclusive_sum_u32(starts.p, starts.p, nh + 1, st))) return fail(rc);
     uint32_t total = 0;
     if (cudaMemcpy(&total, starts.p + nh, sizeof total, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H count failed"); return fail(FMB_ECUDA); }

@@ -113,3 +113,16 @@ def test_reads_with_planted_errors_are_found(big, k, edit):
     # the jump / k-mer accelerated kernel and the plain frontier kernel report the same multiset
     st = res.stats
     assert 0 < st.line_requests < st.occ_lookups
+
+
+def test_locate_refuses_more_than_2_32_rows(big):
+    """300 one-symbol queries cover ~4.8 G rows of the 64 Mbp index: locate must fail loudly, not wrap around"""
+    gpu, capi, index, _ = big
+    sym = np.tile(np.array([1, 2, 3, 4], dtype=np.uint8), 75)
+    off = np.arange(301, dtype=np.uint64)
+    res = index.search_exact(index.upload(sym, off))
+    hits = res.hits()
+    assert len(hits) == 300 and int(hits["len"].sum()) > 2 ** 32
+    with pytest.raises(gpu.FmbError) as ei:
+        index.locate(res)
+    assert ei.value.code == -6 and "split the batch" in str(ei.value)

@@ -569,8 +569,7 @@ __global__ void __launch_bounds__(256, MINB) exact_search2_kernel(const __grid_c
                                                                   const uint8_t* __restrict__ qflags, const uint64_t* __restrict__ qoff, uint32_t nq,
                                                                   uint32_t* __restrict__ out_lb, uint32_t* __restrict__ out_len,
                                                                   unsigned long long* __restrict__ counters) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t q = t >> 2;
+    const uint32_t q = (uint32_t)((blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 2);      // 4 lanes per query: the thread index may exceed 32 bits
     const uint32_t sub = threadIdx.x & 3;
     const uint32_t gmask = 0xFu << (threadIdx.x & 28);
     uint32_t lines = 0;

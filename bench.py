@@ -193,6 +193,15 @@ def main():
     if args.impl == "reference" and rank != 0:
         return 0
 
+    # stdout carries exactly ONE line, the JSON result: everything libraries print (NCCL's version banner goes to stdout) is
+    # sent to stderr by pointing fd 1 at fd 2 for the duration of the run; the result is written to the saved descriptor
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
+
     import torch
     import fmb200 as fmb
     from fmb200 import capi
@@ -204,8 +213,6 @@ def main():
     dist = None
     if world > 1 and args.impl == "ours":
         import torch.distributed as dist
-        # NCCL prints its version banner to stdout: keep stdout for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", device))
 
     scheme, partition, edit = workload_scheme(wl, L)
@@ -244,7 +251,7 @@ def main():
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": {"workload": workload},
                 "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "reference", "sample": sample},
                 "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------------------------------------------
@@ -413,7 +420,7 @@ def main():
         except Exception as ex:   # the baseline must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": threads, "kind": "reference", "sample": f"failed: {ex}"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0

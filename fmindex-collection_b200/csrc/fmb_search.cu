@@ -32,19 +32,25 @@ constexpr uint32_t kWarpsPerBlock = 8;
 template <class OCC, bool EDIT>
 int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const SchemeParams& sp, const fmb_queries* q, uint64_t n_roots, const Item* in_items,
                     uint64_t n_in, const SchemeOut& out, cudaStream_t st) {
-    static int blocks_per_sm = 0, sms = 0;
     static const uint32_t kStackCap = getenv("FMB_SCHEME_CAP") ? (uint32_t)atoi(getenv("FMB_SCHEME_CAP")) : kStackCapDefault;
     size_t smem = (size_t)kStackCap * kWarpsPerBlock * sizeof(Item);
     auto kern = scheme_search_kernel<OCC, EDIT>;
-    if (!blocks_per_sm) {
-        FMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int dev = 0;
-        FMB_CUDA(cudaGetDevice(&dev));
-        FMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        FMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 256, smem));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    } else {
-        FMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // launch geometry, computed once per kernel instantiation (several host threads drive one index in the pipelined path)
+    static std::mutex cfg_mu;
+    static int cfg_blocks_per_sm = 0, cfg_sms = 0;
+    int blocks_per_sm, sms;
+    {
+        std::lock_guard<std::mutex> lk(cfg_mu);
+        FMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      // per device
+        if (!cfg_blocks_per_sm) {
+            int dev = 0, bps = 0;
+            FMB_CUDA(cudaGetDevice(&dev));
+            FMB_CUDA(cudaDeviceGetAttribute(&cfg_sms, cudaDevAttrMultiProcessorCount, dev));
+            FMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 256, smem));
+            cfg_blocks_per_sm = bps < 1 ? 1 : bps;
+        }
+        blocks_per_sm = cfg_blocks_per_sm;
+        sms = cfg_sms;
     }
     uint64_t work = n_roots + n_in;
     uint64_t want_blocks = (work + 255) / 256;
@@ -238,7 +244,7 @@ int fmb_search_backtracking(const fmb_index* ix, const fmb_queries* q, uint32_t 
     return run_scheme(ix, q, sp, out);
 }
 
-// One-call path: the query batch is cut into chunks; up to three host threads each drive their own CUDA stream
+// One-call path: the query batch is cut into chunks; up to six host threads each drive their own CUDA stream
 // (upload -> search -> locate -> download of one chunk), so the H2D copy of one chunk, the kernels of another and
 // the D2H copy of a third overlap.  Rows are appended to `out` in completion order (they carry their qidx).
 int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq, int edit,
@@ -251,9 +257,9 @@ int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uin
     FMB_TRY(set_device(ix->device));
     static const int env_chunk = getenv("FMB_E2E_CHUNK_LOG2") ? atoi(getenv("FMB_E2E_CHUNK_LOG2")) : 0;
     static const int env_threads = getenv("FMB_E2E_THREADS") ? atoi(getenv("FMB_E2E_THREADS")) : 0;
-    const uint64_t chunk = env_chunk ? (uint64_t(1) << env_chunk) : (1u << 20);      // measured: 2^20 beats 2^18 for the scheme searches too
+    const uint64_t chunk = env_chunk ? (uint64_t(1) << env_chunk) : (1u << 19);      // measured with 10 M reads: 2^19 x 6 threads beats 2^20 x 3 and 2^18 x 12
     const uint64_t n_chunks = (nq + chunk - 1) / chunk;
-    const int n_threads = (int)std::min<uint64_t>(env_threads ? env_threads : 3, n_chunks);
+    const int n_threads = (int)std::min<uint64_t>(env_threads ? env_threads : 6, n_chunks);
     std::atomic<uint64_t> next_chunk{0}, written{0}, needed{0};
     std::atomic<int> err{FMB_OK};
     std::mutex mu;

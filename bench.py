@@ -202,6 +202,10 @@ def main():
     def emit(line):
         os.write(result_fd, (json.dumps(line) + "\n").encode())
 
+    # host threads of the pipelined one-call path: the library default (6) assumes the host to itself; with one rank per GPU the
+    # ranks share the host cores
+    os.environ.setdefault("FMB_E2E_THREADS", str(max(2, min(6, (os.cpu_count() or 6) // max(world, 1)))))
+
     import torch
     import fmb200 as fmb
     from fmb200 import capi

@@ -153,6 +153,7 @@ struct Occ2View {
     // farthest symbol in the low bits = text order}; .x = 0xFFFFFFFF when one of the 16 symbols is a delimiter.  Once an interval is a
     // single row, 16 backward steps are one 8-byte lookup: compare the 32-bit symbol word with the query, follow .x.
     const uint2* jump;
+    const uint2* jump4;          // the same with LF^4 and four symbols (8 bits): tails shorter than 16 symbols
 };
 constexpr uint32_t kJumpInvalid = 0xFFFFFFFFu;
 

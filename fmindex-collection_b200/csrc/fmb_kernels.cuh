@@ -621,6 +621,17 @@ __global__ void __launch_bounds__(256, MINB) exact_search2_kernel(const __grid_c
                         continue;
                     }
                 }
+                if (len == 1 && pos >= 4 && o2.jump4) {
+                    // ... and four symbols per lookup through the LF^4 table for what is left of the pattern
+                    uint2 e = __ldg(o2.jump4 + lb);
+                    lines += 1;
+                    if (e.x != kJumpInvalid) {
+                        if (e.y != field(pos - 4, 8)) { len = 0; break; }
+                        lb = e.x;
+                        pos -= 4;
+                        continue;
+                    }
+                }
                 if (pos == 1) {
                     extend_left_uni(ix, lb, len, field(0, 2) + 1, dummy);
                     lines += 1;

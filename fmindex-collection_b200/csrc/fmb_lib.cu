@@ -228,6 +228,7 @@ fmb::Occ2View fmb_index::view_occ2(int dir) const {
     v.s1 = special01[dir][1];
     for (int i = 0; i < 16; ++i) v.C2[i] = C2[dir][i];
     v.jump = jump[dir].p;
+    v.jump4 = jump4[dir].p;
     v.kmer = dir == 0 ? kmer.p : nullptr;
     v.kmer_k = dir == 0 ? kmer_k : 0;
     return v;
@@ -238,7 +239,7 @@ uint64_t fmb_index::device_bytes() const {
     for (int d = 0; d < 2; ++d) b += occ2[d].p ? occ2[d].bytes() + specials[d].bytes() : 0;
     b += kmer.p ? kmer.bytes() : 0;
     b += bikmer.p ? bikmer.bytes() : 0;
-    for (int d = 0; d < 2; ++d) b += jump[d].p ? jump[d].bytes() : 0;
+    for (int d = 0; d < 2; ++d) b += (jump[d].p ? jump[d].bytes() : 0) + (jump4[d].p ? jump4[d].bytes() : 0);
     for (int d = 0; d < 2; ++d) b += occ_dna[d].p ? occ_dna[d].bytes() : 0, b += occ_gen[d].p ? occ_gen[d].bytes() : 0, b += delim_rows[d].p ? delim_rows[d].bytes() : 0;
     b += marks.p ? marks.bytes() : 0;
     b += locblocks.p ? locblocks.bytes() : 0;
@@ -500,12 +501,19 @@ int build_jump(fmb_index* ix, int dir) {
     FMB_TRY(b.alloc(n));
     jump_init_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->view_dna(), dir, a.p);
     FMB_CUDA(cudaGetLastError());
+    // LF^4 entries (after the second round) are kept as well when memory allows: they serve the tails that are shorter than 16
+    // symbols (FMB_NO_JUMP4 disables them)
+    const bool want4 = !getenv("FMB_NO_JUMP4") && (double)free_b > 3.0 * 8.0 * (double)n * 1.25 + (double)(size_t(24) << 30);
     for (uint32_t shift = 2; shift <= 16; shift *= 2) {
         // direction 0 is compared with query symbols to the LEFT of the match (farthest symbol = lowest position = low bits),
         // direction 1 with symbols to the RIGHT (nearest symbol = lowest position = low bits): both equal the packed query order
         jump_double_kernel<<<grid_for(n, 256), 256, 0, st>>>(a.p, b.p, n, shift, dir);
         FMB_CUDA(cudaGetLastError());
         std::swap(a, b);
+        if (shift == 4 && want4) {
+            FMB_TRY(ix->jump4[dir].alloc(n));
+            FMB_CUDA(cudaMemcpyAsync(ix->jump4[dir].p, a.p, n * sizeof(uint2), cudaMemcpyDeviceToDevice, st));
+        }
     }
     FMB_CUDA(cudaStreamSynchronize(st));
     ix->jump[dir] = std::move(a);
@@ -656,7 +664,7 @@ int fmb_index_get_info(const fmb_index* ix, fmb_index_info* info) {
     info->device = ix->device;
     info->tables = (ix->occ2[0].p ? FMB_TABLE_PAIR : 0) | (ix->kmer.p ? FMB_TABLE_KMER : 0) | (ix->jump[0].p ? FMB_TABLE_JUMP : 0) |
                    (ix->jump[1].p ? FMB_TABLE_JUMP_REV : 0) | (ix->locblocks.p ? FMB_TABLE_LOCBLOCK : 0) | (ix->locrow.p ? FMB_TABLE_LOCROW : 0) |
-                   (ix->bikmer.p ? FMB_TABLE_BIKMER : 0);
+                   (ix->bikmer.p ? FMB_TABLE_BIKMER : 0) | (ix->jump4[0].p ? FMB_TABLE_JUMP4 : 0);
     return FMB_OK;
 }
 

@@ -123,6 +123,7 @@ __device__ __forceinline__ void child_cursor(const IndexView<OCC>& ix, const OCC
 // LF^16 jump tables of both directions + the 2-bit packed queries (DNA layout only; all pointers may be null)
 struct JumpView {
     const uint2* jump[2];         // [0]: farthest symbol in the low bits, [1]: nearest symbol in the low bits (= query order)
+    const uint2* jump4[2];        // LF^4 tables, same orientation, four symbols in the low 8 bits
     const uint32_t* qpk;          // packed query symbols
     const uint8_t* qflags;        // 1 = query not packable
     // bidirectional k-mer table: entry (2-bit packed k-mer, first symbol in the low bits) = {lb, lbRev, len, work} of the
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
         //      registers (fast forward) instead of a round trip through the shared-memory stack ----------------
         unsigned long long cmask = 0;
         bool report = false;
-        uint32_t q = 0, b0 = 0, b1 = 0, lo = 0, hi = 0, jrow = 0, jadd = 0, jlast = 0, jnoerr = 0;
+        uint32_t q = 0, b0 = 0, b1 = 0, lo = 0, hi = 0, jrow = 0, jadd = 0, jlast = 0, jnoerr = 0, jlen = 16;
         typename OCC::Block blk0, blk1;
         bool is_single = false, noerr_cont = false;
         uint64_t qbase = 0;
@@ -428,15 +429,15 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                 if (R) ch.RInfo = INFO_I; else ch.LInfo = INFO_I;
                 ch.NextPos = 1;
                 ch.mode = MODE_POS;
-            } else if (bit == 2) {                                                              // sixteen symbols at once (len == 1)
+            } else if (bit == 2) {                                                              // jlen symbols at once (len == 1)
                 if (R) ch.lb_rev = jrow; else ch.lb = jrow;
-                ch.steps = st.steps + 16;
+                ch.steps = st.steps + jlen;
                 ch.e = st.e + jadd;
                 ch.side = side_set(side_set(st.side, R, 0, jlast), R, 1, jlast);
                 if (st.mode == MODE_NOERR || jnoerr) {
                     // (jnoerr: a Hamming stretch that used up its error budget inside the window is in the error-free loop now)
-                    if (R) ch.qposR = (st.qposR + 16) & 0xFFFF; else ch.qposL = (st.qposL - 16) & 0xFFFF;
-                    ch.pev = st.pev - 16;
+                    if (R) ch.qposR = (st.qposR + jlen) & 0xFFFF; else ch.qposL = (st.qposL - jlen) & 0xFFFF;
+                    ch.pev = st.pev - jlen;
                     ch.NextPos = 0;
                     ch.mode = MODE_NOERR;
                     if (ch.pev == 0) {
@@ -446,9 +447,9 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         ch.mode = MODE_NEXT;
                     }
                 } else {
-                    // Hamming, errors allowed: fifteen advances now, the sixteenth is pending like after any match
-                    if (R) ch.qposR = (st.qposR + 15) & 0xFFFF; else ch.qposL = (st.qposL - 15) & 0xFFFF;
-                    ch.pev = st.pev - 15;
+                    // Hamming, errors allowed: jlen - 1 advances now, the last one is pending like after any match
+                    if (R) ch.qposR = (st.qposR + jlen - 1) & 0xFFFF; else ch.qposL = (st.qposL - (jlen - 1)) & 0xFFFF;
+                    ch.pev = st.pev - (jlen - 1);
                     if (R) ch.RInfo = INFO_M; else ch.LInfo = INFO_M;
                     ch.NextPos = 1;
                     ch.mode = MODE_POS;
@@ -511,44 +512,53 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                     b0 = lo >> 6;
                     b1 = hi >> 6;
                     const uint32_t lp = sp.l[st.search][st.part], up = sp.u[st.search][st.part];
-                    // ---- sixteen-symbol jump on a single-row interval (LF^16 table + packed query) ---------------
+                    // ---- multi-symbol jump on a single-row interval (LF^16 table, LF^4 for short stretches; packed query) ----
                     bool jumped = false;
-                    if (st.len == 1 && jv.jump[R] != nullptr && jv.qflags[st.qidx] == 0 &&
-                        ((st.mode == MODE_NOERR && st.pev >= 16) || (!EDIT && st.mode != MODE_NOERR && st.pev > 16 && st.e < up))) {
-                        const uint2 e = __ldg(jv.jump[R] + lo);
+                    uint32_t J = 0;                                   // symbols per jump
+                    if (st.len == 1 && jv.jump[R] != nullptr && jv.qflags[st.qidx] == 0) {
+                        const bool noerr = st.mode == MODE_NOERR;
+                        const bool ham = !EDIT && !noerr && st.e < up;       // Hamming with errors left: the stretch must end inside the part
+                        if (noerr ? st.pev >= 16 : (ham && st.pev > 16)) J = 16;
+                        else if (jv.jump4[R] != nullptr && (noerr ? st.pev >= 4 : (ham && st.pev > 4))) J = 4;
+                    }
+                    if (J) {
+                        const uint2 e = __ldg((J == 16 ? jv.jump[R] : jv.jump4[R]) + lo);
                         n_phys += 1;
                         if (e.x != kJumpInvalid) {
                             jumped = true;
-                            // query symbols of the next 16 positions in walking direction, packed like the table entry
-                            const uint64_t bit = 2 * (qbase + (R ? st.qposR : st.qposL - 15));
+                            const uint32_t W = 2 * J;                 // bits of the symbol word
+                            // query symbols of the next J positions in walking direction, packed like the table entry
+                            const uint64_t bit = 2 * (qbase + (R ? st.qposR : st.qposL - (J - 1)));
                             const uint32_t wi = (uint32_t)(bit >> 5);
-                            const uint32_t key = __funnelshift_r(__ldg(jv.qpk + wi), __ldg(jv.qpk + wi + 1), (uint32_t)bit & 31u);
+                            uint32_t key = __funnelshift_r(__ldg(jv.qpk + wi), __ldg(jv.qpk + wi + 1), (uint32_t)bit & 31u);
+                            if (J != 16) key &= (1u << W) - 1u;
                             const uint32_t x = e.y ^ key;
                             const uint32_t mm = (x | (x >> 1)) & 0x55555555u;               // one bit per mismatching position
                             const uint32_t budget = (st.mode == MODE_NOERR) ? 0u : up - st.e;   // mismatches this stretch may absorb (>= 1 when errors are left)
                             const uint32_t nm = __popc(mm);
-                            // index (0..15, walking order: R from the low bits up, L from the high bits down) of the j-th mismatch, j = 1..
+                            // index (0..J-1, walking order: R from the low bits up, L from the high bits down) of the j-th mismatch, j = 1..
                             auto nth = [&](uint32_t j) -> int {
                                 uint32_t m = mm;
                                 int idx = -1;
                                 for (uint32_t k = 0; k < j; ++k) {
                                     uint32_t pos = R ? (uint32_t)(__ffs(m) - 1) : 31u - (uint32_t)__clz(m);
-                                    idx = R ? (int)(pos >> 1) : (int)((31u - pos) >> 1);
+                                    idx = R ? (int)(pos >> 1) : (int)((W - 1u - pos) >> 1);
                                     m &= ~(1u << pos);
                                 }
                                 return idx;
                             };
-                            // The counters follow the reference's walk over the same 16 positions: one extension per position; once
+                            // The counters follow the reference's walk over the same J positions: one extension per position; once
                             // the error budget of a Hamming stretch is used up it switches to its error-free loop at the next
                             // matching position, which repeats that extension (SearchNg26.h:311-315).
                             if (nm <= budget) {
                                 cmask = CH_JUMP;
                                 jrow = e.x;
                                 jadd = nm;
-                                jlast = ((R ? key >> 30 : key) & 3u) + 1;                  // last query symbol consumed
+                                jlen = J;
+                                jlast = ((R ? key >> (W - 2) : key) & 3u) + 1;             // last query symbol consumed
                                 jnoerr = 0;
-                                uint32_t cnt = 16;
-                                if (st.mode != MODE_NOERR && nm == budget && nth(budget) < 15) { jnoerr = 1; cnt += 1; }
+                                uint32_t cnt = J;
+                                if (st.mode != MODE_NOERR && nm == budget && nth(budget) < (int)J - 1) { jnoerr = 1; cnt += 1; }
                                 n_ext += cnt; n_look += cnt;
                             } else {
                                 const int d = nth(budget + 1);                               // the mismatch that ends the path

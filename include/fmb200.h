@@ -73,6 +73,7 @@ typedef struct {
 #define FMB_TABLE_LOCBLOCK 16u  /* combined occ + marker records for locate        */
 #define FMB_TABLE_LOCROW   32u  /* locate shortcut table                           */
 #define FMB_TABLE_BIKMER   64u  /* bidirectional k-mer table for scheme roots      */
+#define FMB_TABLE_JUMP4    128u /* LF^4 jump tables (tails shorter than 16 symbols) */
 
 /* work counters of the last search/locate call on a result set (device-side counting, optional) */
 typedef struct {

@@ -195,6 +195,61 @@ void search(index_t const& index, queries_t&& queries, size_t maxErrors, delegat
     for (auto const& h : search_bulk<Edit>(index, queries, maxErrors)) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
 }
 
+// SearchNg26.h:448-470: search_best with a list of (scheme, partition) pairs -- per query, the first pair that yields a hit wins.
+// Device form: pair 0 runs on all queries, pair 1 on the queries still without a hit, and so on.  (No hit limit: n must be the
+// default; all queries of a call must have the length the partitions sum to.)
+template <bool Edit = true, typename index_t, Sequences queries_t, typename schemes_t, typename delegate_t>
+    requires requires(schemes_t const& ss) { std::get<0>(*std::begin(ss)); std::get<1>(*std::begin(ss)); }
+void search_best(index_t const& index, queries_t&& queries, schemes_t const& search_schemes, delegate_t&& delegate,
+                 size_t n = std::numeric_limits<size_t>::max()) {
+    if (n != std::numeric_limits<size_t>::max()) throw std::runtime_error("fmb200: the hit limit n of search_ng26::search_best is not supported");
+    size_t const Q = std::ranges::size(queries);
+    std::vector<size_t> pending(Q);
+    for (size_t i = 0; i < Q; ++i) pending[i] = i;
+    std::vector<fmb_hit> all;
+    for (auto const& entry : search_schemes) {
+        if (pending.empty()) break;
+        auto const& scheme = std::get<0>(entry);
+        auto const& partition = std::get<1>(entry);
+        std::vector<std::span<uint8_t const>> group;
+        std::vector<std::vector<uint8_t>> store;
+        store.reserve(pending.size());
+        for (auto id : pending) {
+            auto const& q = queries[id];
+            store.emplace_back(std::ranges::size(q));
+            std::ranges::copy(q, store.back().begin());
+            group.emplace_back(store.back());
+        }
+        auto hits = search_bulk<Edit>(index, group, scheme, partition);
+        std::vector<char> found(pending.size(), 0);
+        for (auto& h : hits) {
+            found[h.qidx] = 1;
+            h.qidx = pending[h.qidx];
+        }
+        all.insert(all.end(), hits.begin(), hits.end());
+        std::vector<size_t> rest;
+        for (size_t i = 0; i < pending.size(); ++i)
+            if (!found[i]) rest.push_back(pending[i]);
+        pending.swap(rest);
+    }
+    detail::sort_hits(all);
+    for (auto const& h : all) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
+}
+
+// SearchNg26.h:472-487: search_best with a maximal error count -- error levels 0 .. maxErrors-1 are tried in turn on ALL queries
+// and the first level at which any query has a hit ends the loop.  The reference's semantics are kept as they are, including
+// that the inner call is `search(index, queries, i, …)` with its default Edit = true whatever search_best's own parameter is.
+template <bool Edit = true, typename index_t, Sequences queries_t, typename delegate_t>
+void search_best(index_t const& index, queries_t&& queries, size_t maxErrors, delegate_t&& delegate, size_t n = std::numeric_limits<size_t>::max()) {
+    if (n != std::numeric_limits<size_t>::max()) throw std::runtime_error("fmb200: the hit limit n of search_ng26::search_best is not supported");
+    for (size_t i = 0; i < maxErrors; ++i) {
+        auto hits = search_bulk<true>(index, queries, i);
+        if (hits.empty()) continue;
+        for (auto const& h : hits) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
+        break;
+    }
+}
+
 }  // namespace search_ng26
 
 // =====================================================================================================================

@@ -120,6 +120,32 @@ int main() {
         CHECK(ref.cursors == gpu.cursors);
         CHECK(ref.located == gpu.located);
     }
+    // search_best: list of (scheme, partition) pairs, and the maxErrors form (SearchNg26.h:448-487)
+    {
+        using Pair = std::tuple<fmc::search_scheme::Scheme, std::vector<size_t>>;
+        std::vector<Pair> schemes;
+        for (size_t k : {0, 1, 2}) {
+            auto sch = fmc::search_scheme::generator::optimum(0, k);
+            schemes.emplace_back(sch, fmc::search_scheme::createUniformPartition(sch, 50));
+        }
+        Collector ref{index}, gpu{index};
+        fmc::search_ng26::search_best<true>(index, queries, schemes, [&](size_t q, auto c, size_t e) { ref(q, c, e); });
+        fmb200::search_ng26::search_best<true>(dev, queries, schemes, [&](size_t q, auto c, size_t e) { gpu(q, c, e); });
+        ref.sort(); gpu.sort();
+        CHECK(ref.cursors == gpu.cursors);
+        CHECK(ref.cursors.size() >= 400);
+        // a batch in which no query matches exactly: level 0 finds nothing, level 1 ends the loop
+        std::vector<std::vector<uint8_t>> damaged;
+        for (size_t i = 0; i < queries.size(); ++i)
+            if (i % 3 == 1) damaged.push_back(queries[i]);
+        for (size_t maxErrors : {1, 2, 3}) {
+            Collector r2{index}, g2{index};
+            fmc::search_ng26::search_best<true>(index, damaged, maxErrors, [&](size_t q, auto c, size_t e) { r2(q, c, e); });
+            fmb200::search_ng26::search_best<true>(dev, damaged, maxErrors, [&](size_t q, auto c, size_t e) { g2(q, c, e); });
+            r2.sort(); g2.sort();
+            CHECK(r2.cursors == g2.cursors);
+        }
+    }
     // fmc::Search functor vs fmb200::Search: reportFunc(qidx, seqId, pos + offset, errors)
     {
         std::vector<std::array<uint64_t, 4>> ref, gpu;

@@ -391,7 +391,8 @@ extern "C" int fmb_index_build(fmb_index** out, int device, uint32_t sigma, cons
     bwt.release();
     FMB_TRY(compute_C(ix));
     if (ix->dna) FMB_TRY(build_occ2(ix, 0));
-    if (ix->dna && bidirectional) FMB_TRY(build_jump(ix, 1));
+    if (!ix->dna) FMB_TRY(build_jump(ix, 0));
+    if (bidirectional) FMB_TRY(build_jump(ix, 1));
     FMB_TRY(build_bikmer(ix));
     FMB_TRY(build_locblocks(ix));
     guard.ix = nullptr;

@@ -350,7 +350,7 @@ template <bool COUNT, class OCC>
 __global__ void __launch_bounds__(256) exact_search_kernel(const __grid_constant__ IndexView<OCC> ix, const uint8_t* __restrict__ qsym,
                                                            const uint64_t* __restrict__ qoff, uint32_t nq,
                                                            uint32_t* __restrict__ out_lb, uint32_t* __restrict__ out_len,
-                                                           unsigned long long* __restrict__ counters) {
+                                                           unsigned long long* __restrict__ counters, const uint2* __restrict__ jump4) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t ext = 0, lookups = 0;
     if (q < nq) {
@@ -359,13 +359,30 @@ __global__ void __launch_bounds__(256) exact_search_kernel(const __grid_constant
         row_t lb = 0, len = ix.n;
         uint64_t cur_chunk = ~uint64_t(0);
         uint4 chunk = make_uint4(0, 0, 0, 0);
-        for (uint32_t pos = L; pos-- > 0;) {
+        auto byte_at = [&](uint32_t pos) -> uint32_t {
             uint64_t a = off + pos;
             if ((a >> 4) != cur_chunk) {
                 cur_chunk = a >> 4;
                 chunk = __ldg(reinterpret_cast<const uint4*>(qsym) + cur_chunk);
             }
-            uint32_t c = chunk_byte(chunk, (uint32_t)(a & 15));
+            return chunk_byte(chunk, (uint32_t)(a & 15));
+        };
+        for (uint32_t pos = L; pos > 0;) {
+            if (OCC::kSymbolLoad && len == 1 && pos >= 4 && jump4 != nullptr) {
+                // generic layout: four symbols per lookup on a single-row interval (LF^4 table with byte symbols, farthest symbol
+                // in the low byte = query order).  The DNA instantiation of this kernel is the exact-counting one and never jumps.
+                const uint2 e = __ldg(jump4 + lb);
+                if (e.x != kJumpInvalid) {
+                    const uint32_t key = byte_at(pos - 4) | (byte_at(pos - 3) << 8) | (byte_at(pos - 2) << 16) | (byte_at(pos - 1) << 24);
+                    ext += 4; lookups += 4;
+                    if (e.y != key) { len = 0; break; }
+                    lb = e.x;
+                    pos -= 4;
+                    continue;
+                }
+            }
+            --pos;
+            uint32_t c = byte_at(pos);
             if (c >= ix.sigma) { len = 0; break; }
             extend_left_uni(ix, lb, len, c, lookups);
             ++ext;
@@ -534,13 +551,17 @@ __global__ void __launch_bounds__(256) pack_queries_kernel(const uint8_t* __rest
 
 // LF^16 jump table by pointer doubling: J1[row] = {LF(row), BWT[row]-1};  J2k[row] = {J_k[J_k[row].x].x, syms << 2k | syms'}
 // (the farthest symbol ends up in the low bits: the order of the 2-bit packed query stream)
-__global__ void __launch_bounds__(256) jump_init_kernel(const __grid_constant__ IndexView<OccDna> ix, int dir, uint2* __restrict__ out) {
+// DNA layout: 2-bit codes (symbol - 1); generic layout: the symbol itself in 8 bits (compared with the raw query bytes)
+template <class OCC>
+__global__ void __launch_bounds__(256) jump_init_kernel(const __grid_constant__ IndexView<OCC> ix, int dir, uint2* __restrict__ out) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= ix.n) return;
-    const OccDna& occ = ix.occ[dir];
-    DnaBlock b = occ.load((uint32_t)(i >> 6));
+    const OCC& occ = ix.occ[dir];
+    typename OCC::Block b = occ.load((uint32_t)(i >> 6), 0);
     uint32_t y = occ.symbol(b, (row_t)i);
-    out[i] = y ? make_uint2(ix.C[y] + occ.rank(b, (row_t)i, y), y - 1) : make_uint2(kJumpInvalid, 0);
+    if (y == 0) { out[i] = make_uint2(kJumpInvalid, 0); return; }
+    if (OCC::kSymbolLoad) b = occ.load((uint32_t)(i >> 6), y);
+    out[i] = make_uint2(ix.C[y] + occ.rank(b, (row_t)i, y), OCC::kSymbolLoad ? y : y - 1);
 }
 __global__ void __launch_bounds__(256) jump_double_kernel(const uint2* __restrict__ in, uint2* __restrict__ out, uint64_t n, uint32_t shift, int nearest_low) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;

@@ -499,6 +499,19 @@ int build_jump(fmb_index* ix, int dir) {
     DevBuf<uint2> a, b;
     FMB_TRY(a.alloc(n));
     FMB_TRY(b.alloc(n));
+    if (!ix->dna) {
+        // generic layout: LF^4 with the four symbols as bytes (two doubling rounds); compared with the raw query bytes
+        jump_init_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->view_gen(), dir, a.p);
+        FMB_CUDA(cudaGetLastError());
+        for (uint32_t shift = 8; shift <= 16; shift *= 2) {
+            jump_double_kernel<<<grid_for(n, 256), 256, 0, st>>>(a.p, b.p, n, shift, dir);
+            FMB_CUDA(cudaGetLastError());
+            std::swap(a, b);
+        }
+        FMB_CUDA(cudaStreamSynchronize(st));
+        ix->jump4[dir] = std::move(a);
+        return FMB_OK;
+    }
     jump_init_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->view_dna(), dir, a.p);
     FMB_CUDA(cudaGetLastError());
     // LF^4 entries (after the second round) are kept as well when memory allows: they serve the tails that are shorter than 16
@@ -616,7 +629,9 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, co
     if (rc) return fail(rc);
     if (ix->dna) rc = build_occ2(ix, 0);
     if (rc) return fail(rc);
-    if (ix->dna && ix->bidirectional) rc = build_jump(ix, 1);
+    if (!ix->dna) rc = build_jump(ix, 0);
+    if (rc) return fail(rc);
+    if (ix->bidirectional) rc = build_jump(ix, 1);
     if (rc) return fail(rc);
     rc = build_bikmer(ix);
     if (rc) return fail(rc);
@@ -881,7 +896,8 @@ int fmb_search_exact(const fmb_index* ix, const fmb_queries* q, fmb_results** ou
         static const bool minb8 = getenv("FMB_EXACT2_MINB1") == nullptr;      // 32 registers -> 2048 resident threads per SM
         if (two && minb8) exact_search2_kernel<true, 8><<<grid_for(nq * 4, 256), 256, 0, st>>>(ix->view_dna(), ix->view_occ2(0), q->symbols.p, q->packed.p, q->flags.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
         else if (two) exact_search2_kernel<true, 1><<<grid_for(nq * 4, 256), 256, 0, st>>>(ix->view_dna(), ix->view_occ2(0), q->symbols.p, q->packed.p, q->flags.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
-        else FMB_DISPATCH(ix, v, exact_search_kernel<true><<<grid_for(nq, 256), 256, 0, st>>>(v, q->symbols.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p));
+        else FMB_DISPATCH(ix, v, exact_search_kernel<true><<<grid_for(nq, 256), 256, 0, st>>>(v, q->symbols.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p,
+                                                                                              ix->dna ? nullptr : ix->jump4[0].p));
         cudaEventRecord(ev_main, st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("exact_search_kernel: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }

@@ -512,13 +512,16 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                     b0 = lo >> 6;
                     b1 = hi >> 6;
                     const uint32_t lp = sp.l[st.search][st.part], up = sp.u[st.search][st.part];
-                    // ---- multi-symbol jump on a single-row interval (LF^16 table, LF^4 for short stretches; packed query) ----
+                    // ---- multi-symbol jump on a single-row interval.  DNA layout: LF^16 table, LF^4 for short stretches, 2-bit symbols
+                    //      compared with the packed query; generic layout: LF^4 table with byte symbols compared with the raw query bytes ----
                     bool jumped = false;
                     uint32_t J = 0;                                   // symbols per jump
-                    if (st.len == 1 && jv.jump[R] != nullptr && jv.qflags[st.qidx] == 0) {
+                    constexpr bool kBytes = OCC::kSymbolLoad;
+                    constexpr uint32_t B = kBytes ? 8u : 2u;          // bits per symbol in a table entry
+                    if (st.len == 1 && (kBytes ? jv.jump4[R] != nullptr : (jv.jump[R] != nullptr && jv.qflags[st.qidx] == 0))) {
                         const bool noerr = st.mode == MODE_NOERR;
                         const bool ham = !EDIT && !noerr && st.e < up;       // Hamming with errors left: the stretch must end inside the part
-                        if (noerr ? st.pev >= 16 : (ham && st.pev > 16)) J = 16;
+                        if (!kBytes && (noerr ? st.pev >= 16 : (ham && st.pev > 16))) J = 16;
                         else if (jv.jump4[R] != nullptr && (noerr ? st.pev >= 4 : (ham && st.pev > 4))) J = 4;
                     }
                     if (J) {
@@ -526,23 +529,37 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         n_phys += 1;
                         if (e.x != kJumpInvalid) {
                             jumped = true;
-                            const uint32_t W = 2 * J;                 // bits of the symbol word
-                            // query symbols of the next J positions in walking direction, packed like the table entry
-                            const uint64_t bit = 2 * (qbase + (R ? st.qposR : st.qposL - (J - 1)));
-                            const uint32_t wi = (uint32_t)(bit >> 5);
-                            uint32_t key = __funnelshift_r(__ldg(jv.qpk + wi), __ldg(jv.qpk + wi + 1), (uint32_t)bit & 31u);
-                            if (J != 16) key &= (1u << W) - 1u;
+                            const uint32_t W = B * J;                 // bits of the symbol word
+                            // query symbols of the next J positions in walking direction, laid out like the table entry
+                            uint32_t key;
+                            if (kBytes) {
+                                const uint8_t* qp = qsym + qbase + (R ? st.qposR : st.qposL - 3);
+                                key = (uint32_t)__ldg(qp) | ((uint32_t)__ldg(qp + 1) << 8) | ((uint32_t)__ldg(qp + 2) << 16) | ((uint32_t)__ldg(qp + 3) << 24);
+                            } else {
+                                const uint64_t bit = 2 * (qbase + (R ? st.qposR : st.qposL - (J - 1)));
+                                const uint32_t wi = (uint32_t)(bit >> 5);
+                                key = __funnelshift_r(__ldg(jv.qpk + wi), __ldg(jv.qpk + wi + 1), (uint32_t)bit & 31u);
+                                if (J != 16) key &= (1u << W) - 1u;
+                            }
                             const uint32_t x = e.y ^ key;
-                            const uint32_t mm = (x | (x >> 1)) & 0x55555555u;               // one bit per mismatching position
+                            uint32_t mm;                               // one bit per mismatching position, at the lowest bit of its field
+                            if (kBytes) {
+                                uint32_t y = x | (x >> 4);
+                                y |= y >> 2;
+                                y |= y >> 1;
+                                mm = y & 0x01010101u;
+                            } else {
+                                mm = (x | (x >> 1)) & 0x55555555u;
+                            }
                             const uint32_t budget = (st.mode == MODE_NOERR) ? 0u : up - st.e;   // mismatches this stretch may absorb (>= 1 when errors are left)
                             const uint32_t nm = __popc(mm);
-                            // index (0..J-1, walking order: R from the low bits up, L from the high bits down) of the j-th mismatch, j = 1..
+                            // index (0..J-1, walking order: R from the low fields up, L from the high fields down) of the j-th mismatch, j = 1..
                             auto nth = [&](uint32_t j) -> int {
                                 uint32_t m = mm;
                                 int idx = -1;
                                 for (uint32_t k = 0; k < j; ++k) {
                                     uint32_t pos = R ? (uint32_t)(__ffs(m) - 1) : 31u - (uint32_t)__clz(m);
-                                    idx = R ? (int)(pos >> 1) : (int)((W - 1u - pos) >> 1);
+                                    idx = R ? (int)(pos / B) : (int)(J - 1u - pos / B);
                                     m &= ~(1u << pos);
                                 }
                                 return idx;
@@ -555,7 +572,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                                 jrow = e.x;
                                 jadd = nm;
                                 jlen = J;
-                                jlast = ((R ? key >> (W - 2) : key) & 3u) + 1;             // last query symbol consumed
+                                jlast = ((R ? key >> (W - B) : key) & ((1u << B) - 1u)) + (kBytes ? 0u : 1u);   // last query symbol consumed
                                 jnoerr = 0;
                                 uint32_t cnt = J;
                                 if (st.mode != MODE_NOERR && nm == budget && nth(budget) < (int)J - 1) { jnoerr = 1; cnt += 1; }

@@ -57,6 +57,10 @@ int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const Schem
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * blocks_per_sm, want_blocks));
     JumpView jv{};
     static const bool no_jump = getenv("FMB_NO_SCHEME_JUMP") != nullptr;
+    if (!ix->dna && !no_jump) {
+        jv.jump4[0] = ix->jump4[0].p;         // byte-symbol LF^4 tables of the generic layout
+        jv.jump4[1] = ix->jump4[1].p;
+    }
     if (ix->dna && q->packed.p && !no_jump) {
         jv.jump[0] = ix->jump[0].p;
         jv.jump[1] = ix->jump[1].p;

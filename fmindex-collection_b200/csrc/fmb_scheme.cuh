@@ -159,20 +159,21 @@ struct SimState {          // one pending node, "ready to expand" (the NextPos a
     uint32_t noerr;        // inside the error-free loop
 };
 __device__ __forceinline__ unsigned long long sim_pack(const SimState& s) {
+    // m:5 c:8 part:4 pev:16 e:4 T:2 lastRank:8 lastQRank:8 noerr:1  (symbols up to 255: the generic layout has sigma <= 32)
     return (unsigned long long)s.m | ((unsigned long long)s.c << 5) | ((unsigned long long)s.part << 13) | ((unsigned long long)s.pev << 17) |
            ((unsigned long long)s.e << 33) | ((unsigned long long)s.T << 37) | ((unsigned long long)s.lastRank << 39) |
-           ((unsigned long long)s.lastQRank << 42) | ((unsigned long long)s.noerr << 45);
+           ((unsigned long long)s.lastQRank << 47) | ((unsigned long long)s.noerr << 55);
 }
 __device__ __forceinline__ SimState sim_unpack(unsigned long long v) {
     SimState s;
     s.m = v & 31; s.c = (v >> 5) & 255; s.part = (v >> 13) & 15; s.pev = (v >> 17) & 0xFFFF; s.e = (v >> 33) & 15;
-    s.T = (v >> 37) & 3; s.lastRank = (v >> 39) & 7; s.lastQRank = (v >> 42) & 7; s.noerr = (v >> 45) & 1;
+    s.T = (v >> 37) & 3; s.lastRank = (v >> 39) & 255; s.lastQRank = (v >> 47) & 255; s.noerr = (v >> 55) & 1;
     return s;
 }
 
-// returns true when the whole subtree below `root` dies inside the window; `ext` receives its number of extensions
-template <bool EDIT>
-__device__ bool sim_subtree_dies(const SchemeParams& sp, uint32_t search, uint32_t R, uint32_t window /*16 x 2 bit, w[0] in the low bits*/,
+// BYTES: the window holds 4 symbols of 8 bits (generic layout, LF^4 table) instead of 16 codes of 2 bits (symbol - 1)
+template <bool EDIT, bool BYTES>
+__device__ bool sim_subtree_dies(const SchemeParams& sp, uint32_t search, uint32_t R, uint32_t window /*w[0] in the low bits*/,
                                  const uint8_t* __restrict__ qptr /*query symbol of c = 0*/, const SimState& root, uint32_t& ext) {
     constexpr int kStack = 12;
     unsigned long long stack[kStack];
@@ -198,8 +199,8 @@ __device__ bool sim_subtree_dies(const SchemeParams& sp, uint32_t search, uint32
             }
             return true;
         };
-        if (s.m >= SIM_DEPTH) return false;                                                          // survives the window
-        const uint32_t sym = ((window >> (2 * s.m)) & 3u) + 1;
+        if (s.m >= (BYTES ? 4u : (uint32_t)SIM_DEPTH)) return false;                                 // survives the window
+        const uint32_t sym = BYTES ? ((window >> (8 * s.m)) & 0xFFu) : ((window >> (2 * s.m)) & 3u) + 1;
         const uint32_t q = qptr[dirstep * (int)s.c];
         const uint32_t lp = sp.l[search][s.part], up = sp.u[search][s.part];
         if (s.noerr) {                                                                               // search_next_dir_no_errors :225-250
@@ -670,15 +671,20 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                                 // (sim_subtree_dies above): children whose whole subtree dies within the next 16 text symbols are
                                 // accounted for -- their extensions are counted -- but never created.
                                 const unsigned long long err_children = cmask & ~(CH_MATCH | CH_JUMP);
-                                if (EDIT && err_children && jv.jump[R] != nullptr && single_sym >= first_symb && (sim_all || st.e + 1 == up)) {
-                                    const uint2 je = __ldg(jv.jump[R] + lo);
+                                const uint2* sim_table = OCC::kSymbolLoad ? jv.jump4[R] : jv.jump[R];
+                                if (EDIT && err_children && sim_table != nullptr && single_sym >= first_symb && (sim_all || st.e + 1 == up)) {
+                                    const uint2 je = __ldg(sim_table + lo);
                                     n_phys += 1;
                                     if (je.x != kJumpInvalid) {
                                         // window in walking order, w[0] (= this row's symbol) in the low bits
                                         uint32_t window = je.y;
                                         if (!R) {                                   // direction 0 stores the nearest symbol in the high bits
-                                            window = __brev(window);
-                                            window = ((window & 0xAAAAAAAAu) >> 1) | ((window & 0x55555555u) << 1);
+                                            if (OCC::kSymbolLoad) {
+                                                window = __byte_perm(window, 0, 0x0123);
+                                            } else {
+                                                window = __brev(window);
+                                                window = ((window & 0xAAAAAAAAu) >> 1) | ((window & 0x55555555u) << 1);
+                                            }
                                         }
                                         const uint8_t* qptr = qsym + qbase + (R ? st.qposR : st.qposL);
                                         unsigned long long rest = err_children;
@@ -711,7 +717,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                                                 }
                                             }
                                             uint32_t sim_ext = 0;
-                                            if (ok && sim_subtree_dies<EDIT>(sp, st.search, R, window, qptr, cs, sim_ext)) {
+                                            if (ok && sim_subtree_dies<EDIT, OCC::kSymbolLoad>(sp, st.search, R, window, qptr, cs, sim_ext)) {
                                                 cmask &= ~(1ull << bit);
                                                 n_ext += sim_ext; n_look += sim_ext;
                                             }

@@ -378,6 +378,7 @@ typedef struct {                   /* SearchNg26.h:41-52 */
     uint64_t e, part, partitionEntryValue, queryPosL, queryPosR;
     char LInfo, RInfo;
     int Right, NextPos;
+    uint64_t key;                  /* discovery-order key of the path (test aid, see ng26_key_edge) */
 } state_t;
 
 typedef struct {
@@ -392,12 +393,48 @@ typedef struct {
     uint64_t qidx, ct, max_hits;
     hitvec* hv;
     fmo_counters* ctr;
+    /* discovery-order keys (fmo_search_ng26_keys) */
+    uint32_t search_idx, key_slots, key_bits, key_maxd, key_ords;
+    uint64_t *keys, keys_n, keys_cap;
+    int want_keys;
 } ng26_ctx;
 
-static int ng26_delegate(ng26_ctx* cx, cursor_t cur, uint64_t e) {
+/* Discovery-order key -- TEST AID for the device's hit-limited search (fmb_search_scheme_n).
+ * The device enumerates the search tree in an arbitrary order and must afterwards put the hits of a query into
+ * the order this depth-first search finds them in.  Two paths of one search split at ONE node, so their order is
+ * decided by the order in which that node visits its children:
+ *   search_next_dir        (:170-218)  match, then for every symbol c: deletion(c), substitution(c), then insertion
+ *   search_next_dir_single (:286-363)  insertion, then match / deletion  or  substitution / deletion
+ * A path is therefore identified by its error edges.  Slot `e` of the key (e = errors before the edge) holds a code
+ * for the edge taken at depth d = steps + e (strictly increasing along a path):
+ *   insertion at a single-row node ("before the match child")   code = d
+ *   no (further) error edge                                        code = MID = maxd
+ *   every other error edge ("after the match child")               code = MID + 1 + (maxd-1-d) * ords + ord
+ * with ord = 0 substitution / 1 deletion at a single-row node and 2c deletion(c) / 2c+1 substitution(c) /
+ * 2 sigma + 1 insertion at a wide node.  Comparing the slots from e = 0 upwards (after the search number in the top
+ * byte) reproduces the depth-first order; fmo_search_ng26_keys returns the keys so that tests can check that they
+ * ascend in the order the hits are reported. */
+static uint64_t ng26_key_edge(const ng26_ctx* cx, const state_t* st, int single, int before, uint32_t ord) {
+    if (!cx->want_keys) return st->key;
+    uint64_t d = st->cur.steps + st->e;
+    uint64_t code = before ? d : (uint64_t)cx->key_maxd + 1 + ((uint64_t)cx->key_maxd - 1 - d) * cx->key_ords + ord;
+    (void)single;
+    uint32_t sh = 56 - (uint32_t)(st->e + 1) * cx->key_bits;
+    uint64_t mask = ((1ull << cx->key_bits) - 1) << sh;
+    return (st->key & ~mask) | (code << sh);
+}
+
+static int ng26_delegate(ng26_ctx* cx, cursor_t cur, uint64_t e, uint64_t key) {
     if (cur.len + cx->ct > cx->max_hits) cur.len = cx->max_hits - cx->ct;    /* :415-417 */
     cx->ct += cur.len;
     hit_push(cx->hv, cx->qidx, cur, e);
+    if (cx->want_keys) {
+        if (cx->keys_n == cx->keys_cap) {
+            cx->keys_cap = cx->keys_cap ? cx->keys_cap * 2 : 1024;
+            cx->keys = (uint64_t*)realloc(cx->keys, cx->keys_cap * sizeof(uint64_t));
+        }
+        cx->keys[cx->keys_n++] = key;
+    }
     return cx->ct == cx->max_hits;                                             /* :420 */
 }
 
@@ -430,7 +467,7 @@ static int ng26_search_next(ng26_ctx* cx, const state_t* state) {              /
     if (state->part == cx->n_parts) {
         if (!cx->edit || ((state->LInfo == 'M' || state->LInfo == 'I') && (state->RInfo == 'M' || state->RInfo == 'I'))) {
             if (cx->l[cx->n_parts - 1] <= state->e && state->e <= cx->u[cx->n_parts - 1])
-                return ng26_delegate(cx, state->cur, state->e);
+                return ng26_delegate(cx, state->cur, state->e, state->key);
         }
         return 0;
     }
@@ -500,6 +537,7 @@ static int ng26_search_next_dir(ng26_ctx* cx, const state_t* state) {          /
             if (Deletion) {
                 ns.LInfo = OnDeletionL; ns.RInfo = OnDeletionR;
                 ns.NextPos = 0;
+                ns.key = ng26_key_edge(cx, state, 0, 0, (uint32_t)(2 * i));
                 if (ng26_search_next_pos(cx, ns)) return 1;
             }
             if (!substitutionAllowed) continue;
@@ -507,6 +545,7 @@ static int ng26_search_next_dir(ng26_ctx* cx, const state_t* state) {          /
             ns.side[R].lastQRank = nextSymb;
             ns.LInfo = OnSubstituteL; ns.RInfo = OnSubstituteR;
             ns.NextPos = 1;
+            ns.key = ng26_key_edge(cx, state, 0, 0, (uint32_t)(2 * i + 1));
             if (ng26_search_next_pos(cx, ns)) return 1;
         }
         if (Insertion && insertionAllowed) {                                    /* :207-218 */
@@ -515,6 +554,7 @@ static int ng26_search_next_dir(ng26_ctx* cx, const state_t* state) {          /
             ns.side[R].lastQRank = nextSymb;
             ns.LInfo = OnInsertionL; ns.RInfo = OnInsertionR;
             ns.NextPos = 1;
+            ns.key = ng26_key_edge(cx, state, 0, 0, 2 * cx->ix->sigma + 1);
             if (ng26_search_next_pos(cx, ns)) return 1;
         }
     } else if (matchAllowed) {
@@ -550,6 +590,7 @@ static int ng26_search_next_dir_single(ng26_ctx* cx, const state_t* state) {   /
         ns.side[R].lastQRank = curQSymb;
         ns.LInfo = OnInsertionL; ns.RInfo = OnInsertionR;
         ns.NextPos = 1;
+        ns.key = ng26_key_edge(cx, state, 1, 1, 0);
         if (ng26_search_next_pos(cx, ns)) return 1;
     }
     if (curISymb < cx->first_symb) return 0;                                    /* :300-302 */
@@ -577,6 +618,7 @@ static int ng26_search_next_dir_single(ng26_ctx* cx, const state_t* state) {   /
             ns.cur = icursorNext;
             ns.LInfo = OnDeletionL; ns.RInfo = OnDeletionR;
             ns.NextPos = 0;
+            ns.key = ng26_key_edge(cx, state, 1, 0, 1);
             if (ng26_search_next_pos(cx, ns)) return 1;
         }
     } else if (mismatchAllowed) {                                               /* :339-363 */
@@ -589,6 +631,7 @@ static int ng26_search_next_dir_single(ng26_ctx* cx, const state_t* state) {   /
             ns.side[R].lastQRank = curQSymb;
             ns.LInfo = OnSubstituteL; ns.RInfo = OnSubstituteR;
             ns.NextPos = 1;
+            ns.key = ng26_key_edge(cx, state, 1, 0, 0);
             int f = ng26_search_next_pos(cx, ns);
             ns.side[R].lastQRank = saved;
             if (f) return 1;
@@ -596,6 +639,7 @@ static int ng26_search_next_dir_single(ng26_ctx* cx, const state_t* state) {   /
         if (Deletion) {
             ns.LInfo = OnDeletionL; ns.RInfo = OnDeletionR;
             ns.NextPos = 0;
+            ns.key = ng26_key_edge(cx, state, 1, 0, 1);
             if (ng26_search_next_pos(cx, ns)) return 1;
         }
     }
@@ -613,30 +657,65 @@ static int ng26_run(ng26_ctx* cx) {                                             
     st.partitionEntryValue = cx->partition[cx->pi[0]];
     st.cur.lb = 0; st.cur.lb_rev = 0; st.cur.len = cx->ix->n; st.cur.steps = 0;   /* BiFMIndexCursor.h:28-30 */
     st.LInfo = 'M'; st.RInfo = 'M';
+    if (cx->want_keys) {                     /* search number, then every slot = "no error edge" */
+        st.key = (uint64_t)cx->search_idx << 56;
+        for (uint32_t i = 0; i < cx->key_slots; ++i) st.key |= (uint64_t)cx->key_maxd << (56 - (i + 1) * cx->key_bits);
+    }
     return ng26_search_next(cx, &st);
 }
 
-uint64_t fmo_search_ng26(const fmo_index* ix, const uint8_t* qsym, const uint64_t* qoff, uint64_t nq, int edit,
-                         uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l, const uint32_t* u,
-                         const uint32_t* partition, uint64_t max_hits, fmo_hit** out, fmo_counters* ctr) {
+int fmo_ng26_key_layout(uint32_t sigma, uint32_t n_searches, uint32_t n_parts, const uint32_t* u, const uint32_t* partition,
+                        uint32_t* slots, uint32_t* bits, uint32_t* maxd, uint32_t* ords) {
+    uint32_t K = 0, total = 0;
+    for (uint32_t i = 0; i < n_searches * n_parts; ++i) K = u[i] > K ? u[i] : K;
+    for (uint32_t p = 0; p < n_parts; ++p) total += partition[p];
+    *slots = K;
+    *maxd = total + 2 * K + 2;
+    *ords = 2 * sigma + 2;
+    uint64_t range = (uint64_t)*maxd + 1 + (uint64_t)*maxd * *ords;
+    uint32_t b = 1;
+    while ((1ull << b) < range) ++b;
+    *bits = b;
+    return K * b <= 56;
+}
+
+uint64_t fmo_search_ng26_keys(const fmo_index* ix, const uint8_t* qsym, const uint64_t* qoff, uint64_t nq, int edit,
+                              uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l, const uint32_t* u,
+                              const uint32_t* partition, uint64_t max_hits, fmo_hit** out, uint64_t** keys_out, fmo_counters* ctr) {
     hitvec hv = {0, 0, 0};
+    uint64_t *keys = NULL, keys_n = 0, keys_cap = 0;
     *out = NULL;
+    if (keys_out) *keys_out = NULL;
     if (nq == 0 || max_hits == 0) return 0;                                     /* :409-410 */
+    uint32_t slots = 0, bits = 0, maxd = 0, ords = 0;
+    if (keys_out && !fmo_ng26_key_layout(ix->sigma, n_searches, n_parts, u, partition, &slots, &bits, &maxd, &ords)) return 0;
     for (uint64_t q = 0; q < nq; ++q) {                                         /* :411-422 */
         ng26_ctx cx;
         memset(&cx, 0, sizeof cx);
         cx.ix = ix; cx.edit = edit; cx.query = qsym + qoff[q];
         cx.n_parts = n_parts; cx.partition = partition; cx.first_symb = 1;
         cx.qidx = q; cx.ct = 0; cx.max_hits = max_hits; cx.hv = &hv; cx.ctr = ctr;
+        cx.want_keys = keys_out != NULL;
+        cx.key_slots = slots; cx.key_bits = bits; cx.key_maxd = maxd; cx.key_ords = ords;
+        cx.keys = keys; cx.keys_n = keys_n; cx.keys_cap = keys_cap;
         for (uint32_t s = 0; s < n_searches; ++s) {                             /* search_impl :385-390 */
             cx.pi = pi + (size_t)s * n_parts;
             cx.l = l + (size_t)s * n_parts;
             cx.u = u + (size_t)s * n_parts;
+            cx.search_idx = s;
             if (ng26_run(&cx)) break;
         }
+        keys = cx.keys; keys_n = cx.keys_n; keys_cap = cx.keys_cap;
     }
     *out = hv.v;
+    if (keys_out) *keys_out = keys;
     return hv.n;
+}
+
+uint64_t fmo_search_ng26(const fmo_index* ix, const uint8_t* qsym, const uint64_t* qoff, uint64_t nq, int edit,
+                         uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l, const uint32_t* u,
+                         const uint32_t* partition, uint64_t max_hits, fmo_hit** out, fmo_counters* ctr) {
+    return fmo_search_ng26_keys(ix, qsym, qoff, nq, edit, n_searches, n_parts, pi, l, u, partition, max_hits, out, NULL, ctr);
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -91,6 +91,14 @@ uint64_t fmo_search_exact(const fmo_index* ix, const uint8_t* qsym, const uint64
 uint64_t fmo_search_ng26(const fmo_index* ix, const uint8_t* qsym, const uint64_t* qoff, uint64_t nq, int edit,
                          uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l, const uint32_t* u,
                          const uint32_t* partition, uint64_t max_hits, fmo_hit** out, fmo_counters* ctr);
+/* The same search; additionally *keys_out receives one discovery-order key per hit (see ng26_key_edge in fm_oracle.c):
+ * a test aid for the device's hit-limited search, whose post-sort by this key must reproduce the order of this
+ * depth-first search.  fmo_ng26_key_layout returns the field widths (0 = the keys do not fit 64 bits). */
+uint64_t fmo_search_ng26_keys(const fmo_index* ix, const uint8_t* qsym, const uint64_t* qoff, uint64_t nq, int edit,
+                              uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l, const uint32_t* u,
+                              const uint32_t* partition, uint64_t max_hits, fmo_hit** out, uint64_t** keys_out, fmo_counters* ctr);
+int fmo_ng26_key_layout(uint32_t sigma, uint32_t n_searches, uint32_t n_parts, const uint32_t* u, const uint32_t* partition,
+                        uint32_t* slots, uint32_t* bits, uint32_t* maxd, uint32_t* ords);
 /* search/Backtracking.h:85-88 (Hamming, works on unidirectional indices too) */
 uint64_t fmo_search_backtracking(const fmo_index* ix, const uint8_t* qsym, const uint64_t* qoff, uint64_t nq,
                                  uint32_t max_errors, fmo_hit** out, fmo_counters* ctr);

@@ -197,6 +197,18 @@ class Oracle:
                                        C.c_uint64(max_hits), C.byref(out), C.byref(counters) if counters is not None else None)
         return _take(self.lib().fmo_free, out.value, n, HIT_DTYPE)
 
+    def search_ng26_keys(self, symbols, offsets, scheme, partition, edit, max_hits=UINT64_MAX):
+        """hits in the order the depth-first search reports them + their discovery-order keys (fm_oracle.c ng26_key_edge)"""
+        symbols, offsets = _u8(symbols), _u64(offsets)
+        pi, l, u, part = _scheme_args(scheme, partition)
+        out, keys = C.c_void_p(), C.c_void_p()
+        f = self.lib().fmo_search_ng26_keys
+        f.restype = C.c_uint64
+        n = f(self.h, _p(symbols), _p(offsets), C.c_uint64(offsets.size - 1), C.c_int(int(edit)),
+              C.c_uint32(pi.shape[0]), C.c_uint32(pi.shape[1]), _p(pi), _p(l), _p(u), _p(part),
+              C.c_uint64(max_hits), C.byref(out), C.byref(keys), None)
+        return _take(self.lib().fmo_free, out.value, n, HIT_DTYPE), _take(self.lib().fmo_free, keys.value, n, np.dtype(np.uint64))
+
     def search_backtracking(self, symbols, offsets, max_errors, counters=None):
         symbols, offsets = _u8(symbols), _u64(offsets)
         out = C.c_void_p()

@@ -245,3 +245,46 @@ def test_oracle_vs_reference_library(seed):
     sch = schemes.optimum(0, 1)
     part = schemes.uniform_partition(2, 32)
     assert np.array_equal(sort_hits(r.search_ng26(sym, off, sch, part, True, threads=3)), sort_hits(r.search_ng26(sym, off, sch, part, True)))
+
+
+# ---- discovery-order keys (test aid for the device's hit-limited search) -----------------------------------
+@pytest.mark.parametrize("kind", ["random", "repeats", "protein"])
+def test_discovery_order_keys_ascend_in_report_order(kind):
+    """The device enumerates a search tree in its own order and sorts the hits by a sparse key afterwards; the key (defined in
+    fm_oracle.c, ng26_key_edge) must therefore ascend strictly in the order the reference's depth-first search reports hits
+    (SearchNg26.h:170-218 wide nodes, :286-363 single-row nodes; searches in scheme order :385-390)."""
+    from fmb200 import schemes, synth
+    rng = np.random.default_rng(11)
+    if kind == "random":
+        sigma, L = 5, 24
+        text = synth.multi_text([1500, 700], sigma, 5)
+    elif kind == "repeats":
+        sigma, L = 5, 20
+        unit = rng.integers(1, 5, 40).astype(np.uint8)
+        chunks = []
+        for _ in range(40):
+            u = unit.copy()
+            u[rng.integers(0, 40, 2)] = rng.integers(1, 5, 2)
+            chunks.append(u)
+        text = np.concatenate(chunks + [np.zeros(1, np.uint8)])
+    else:
+        sigma, L = 21, 12
+        text = synth.multi_text([900, 300], sigma, 9)
+    o = Oracle.build(text, sigma, 4)
+    body = text[: 700 if kind != "repeats" else len(text) - 1]
+    reads, _ = synth.reads_from_text(body, 60, L, 3)
+    reads = synth.plant_errors(reads, sigma, 2, True, 4)
+    sym, off = synth.flatten(reads)
+    total = 0
+    for k in (1, 2, 3):
+        for edit in (False, True):
+            for sch in (schemes.optimum(0, k) if k < 3 else schemes.h2(k + 2, 0, k), schemes.h2(k + 1, 0, k), schemes.backtracking(k + 1, 0, k)):
+                if not edit:
+                    sch = schemes.limit_to_hamming(sch)
+                part = schemes.uniform_partition(sch[0].shape[1], L)
+                hits, keys = o.search_ng26_keys(sym, off, sch, part, edit)
+                assert np.array_equal(hits, o.search_ng26(sym, off, sch, part, edit))
+                same_q = hits["qidx"][1:] == hits["qidx"][:-1]
+                assert np.all(keys[1:][same_q] > keys[:-1][same_q]), (kind, k, edit)
+                total += hits.size
+    assert total > 500

@@ -32,6 +32,8 @@ struct SchemeParams {
     uint8_t u[kMaxSearches][kMaxParts];
     uint16_t partition[kMaxParts];
     uint16_t start[kMaxSearches];      // sum of partition[0 .. pi[s][0])          (SearchNg26.h:65-68)
+    // ordered mode (hit limit n, SearchNg26.h:408-423): layout of the discovery-order key, see order_key_edge
+    uint32_t key_slots, key_bits, key_maxd, key_ords;
 };
 
 enum : uint32_t { INFO_M = 0, INFO_S = 1, INFO_D = 2, INFO_I = 3 };
@@ -52,6 +54,7 @@ struct State {
     uint32_t qposL, qposR, pev, steps;
     uint32_t e, part, search, mode, LInfo, RInfo, Right, NextPos;
     uint32_t side;
+    unsigned long long key;   // ordered mode only (not part of Item: kept in a parallel stack)
 };
 
 __device__ __forceinline__ Item pack_item(const State& s) {
@@ -82,6 +85,37 @@ __device__ __forceinline__ uint32_t side_set(uint32_t side, uint32_t right, uint
     return (side & ~(0xFFu << sh)) | (v << sh);
 }
 
+// Discovery-order key (ordered mode).  With a hit limit the reference stops a query after its first n rows IN THE ORDER ITS
+// DEPTH-FIRST SEARCH FINDS THEM (search_n_impl, SearchNg26.h:408-423).  The kernel enumerates the tree in its own order, so every
+// item carries a sparse key from which that order is recovered afterwards by sorting.  Two paths of one search split at one node
+// and their order is the order in which that node visits the two children:
+//   search_next_dir        (:170-218)  match, then for every symbol c: deletion(c), substitution(c), then insertion
+//   search_next_dir_single (:286-363)  insertion, then match / deletion  or  substitution / deletion
+// so a path is identified by its error edges.  Slot e of the key (e = errors before the edge; top byte = search number, slots
+// follow from the high bits down) holds a code for the error edge leaving a node of depth d = steps + e (strictly increasing
+// along a path):
+//   insertion at a single-row node (visited before the match child)     code = d
+//   no further error edge                                                 code = MID = key_maxd
+//   any other error edge (visited after the match child)                  code = MID + 1 + (key_maxd - 1 - d) * key_ords + ord
+// ord = 0 substitution / 1 deletion at a single-row node; 2c deletion(c) / 2c + 1 substitution(c) / 2 sigma + 1 insertion at a
+// wide node.  Mismatches absorbed by a multi-symbol jump (Hamming) lie on single-row nodes with exactly one child and need no
+// entry.  Unsigned comparison of two keys = order of discovery (the tests check the definition against the report order of
+// the reference's depth-first search).
+__device__ __forceinline__ unsigned long long order_key_edge(const SchemeParams& sp, unsigned long long key, uint32_t steps, uint32_t e,
+                                                             bool before, uint32_t ord) {
+    const uint32_t d = steps + e;
+    const unsigned long long code = before ? (unsigned long long)d
+                                           : (unsigned long long)sp.key_maxd + 1 + (unsigned long long)(sp.key_maxd - 1 - d) * sp.key_ords + ord;
+    const uint32_t sh = 56 - (e + 1) * sp.key_bits;
+    const unsigned long long mask = ((1ull << sp.key_bits) - 1) << sh;
+    return (key & ~mask) | (code << sh);
+}
+__device__ __forceinline__ unsigned long long order_key_root(const SchemeParams& sp, uint32_t search) {
+    unsigned long long key = (unsigned long long)search << 56;
+    for (uint32_t i = 0; i < sp.key_slots; ++i) key |= (unsigned long long)sp.key_maxd << (56 - (i + 1) * sp.key_bits);
+    return key;
+}
+
 struct SchemeOut {
     HitRec* hits;
     unsigned long long* hit_count;     // total hits found (may exceed capacity)
@@ -92,6 +126,10 @@ struct SchemeOut {
     unsigned long long* counters;      // [0] extensions, [1] occ lookups, [3] peak items per warp
     unsigned long long* root_counter;
     uint32_t qidx_base;                // added to the reported qidx (chunked query batches)
+    // ordered mode: keys of the hits / the spilled items / the items fed in
+    unsigned long long* hit_keys;
+    unsigned long long* overflow_keys;
+    const unsigned long long* in_keys;
 };
 
 // one cursor extension by `symb` in direction `right` from two loaded blocks (DNA: blocks are symbol independent)
@@ -285,7 +323,7 @@ constexpr int kFastForward = 12;
 #define FMB_SCHEME_MINB 4          // 4 blocks of 256 threads per SM -> 64 registers (a few spills beat the lower occupancy of 80)
 #endif   // consecutive single-child expansions a lane may chain in registers per pop
 
-template <class OCC, bool EDIT>
+template <class OCC, bool EDIT, bool ORDERED>
 __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(const __grid_constant__ IndexView<OCC> ix, const __grid_constant__ SchemeParams sp,
                                                             const uint8_t* __restrict__ qsym, const uint64_t* __restrict__ qoff,
                                                             const __grid_constant__ JumpView jv, uint64_t n_roots,
@@ -295,6 +333,8 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = threadIdx.x >> 5;
     Item* stack = reinterpret_cast<Item*>(smem_raw) + (size_t)warp * cap;
+    // ordered mode: the keys of the stacked items, behind the item stacks of all warps
+    unsigned long long* kstack = reinterpret_cast<unsigned long long*>(reinterpret_cast<Item*>(smem_raw) + (size_t)(blockDim.x >> 5) * cap) + (size_t)warp * cap;
     const uint64_t total_roots = n_roots + n_in;
     uint32_t top = 0;
     uint32_t n_ext = 0, n_look = 0, n_phys = 0, peak = 0;
@@ -320,8 +360,10 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                 if (lane < got) {
                     uint64_t r = base + lane;
                     Item it;
+                    unsigned long long rkey = 0;
                     if (r < n_in) {
                         it = in_items[r];
+                        if constexpr (ORDERED) rkey = out.in_keys[r];
                     } else {
                         r -= n_in;
                         uint32_t s = (uint32_t)(r % sp.n_searches);
@@ -361,8 +403,10 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                             if (st.mode == MODE_NEXT) st.side = side_set(side_set(st.side, 1, 0, lastq), 1, 1, lastq);
                         }
                         it = pack_item(st);
+                        if constexpr (ORDERED) rkey = order_key_root(sp, s);
                     }
                     stack[top + lane] = it;
+                    if constexpr (ORDERED) kstack[top + lane] = rkey;
                 }
                 top += got;
                 __syncwarp();
@@ -377,7 +421,10 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
         const uint32_t nact = top < 32 ? top : 32;
         const bool active = lane < nact;
         State st;
-        if (active) st = unpack_item(stack[top - 1 - lane]);
+        if (active) {
+            st = unpack_item(stack[top - 1 - lane]);
+            if constexpr (ORDERED) st.key = kstack[top - 1 - lane];
+        }
         top -= nact;
         __syncwarp();
 
@@ -425,6 +472,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                     ch.mode = MODE_POS;
                 }
             } else if (bit == 1) {                                                              // insertion: no index step
+                if constexpr (ORDERED) ch.key = order_key_edge(sp, st.key, st.steps, st.e, is_single, 2 * ix.sigma + 1);
                 ch.e = st.e + 1;
                 ch.side = side_set(st.side, R, 1, q);
                 if (R) ch.RInfo = INFO_I; else ch.LInfo = INFO_I;
@@ -458,6 +506,8 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
             } else {
                 const bool is_sub = bit >= 36;
                 const uint32_t c = is_sub ? bit - 36 : bit - 8;
+                if constexpr (ORDERED)
+                    ch.key = order_key_edge(sp, st.key, st.steps, st.e, false, is_single ? (is_sub ? 0u : 1u) : 2 * c + (is_sub ? 1u : 0u));
                 stepped(c);
                 ch.e = st.e + 1;
                 ch.side = side_set(st.side, R, 0, c);
@@ -750,6 +800,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         HitRec h;
                         h.qidx = st.qidx + out.qidx_base; h.lb = st.lb; h.lb_rev = sp.zero_lb_rev ? 0 : st.lb_rev; h.len = st.len; h.steps = st.steps; h.e = st.e;
                         out.hits[idx] = h;
+                        if constexpr (ORDERED) out.hit_keys[idx] = st.key;
                     }
                 }
             }
@@ -766,15 +817,18 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
         if (total == 0) continue;
         uint32_t slot = incl - nchild;
         Item* dst;
+        unsigned long long* kdst = nullptr;
         bool drop = false;
         if (top + total <= cap) {
             dst = stack + top;
+            if constexpr (ORDERED) kdst = kstack + top;
             top += total;
         } else {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(out.overflow_count, (unsigned long long)total);
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
             dst = out.overflow + base;
+            if constexpr (ORDERED) kdst = out.overflow_keys + base;
             drop = base + total > out.overflow_capacity;      // host sees overflow_count > capacity and fails loudly
         }
         if (cmask && !drop) {
@@ -782,7 +836,9 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
             while (rest) {
                 uint32_t bit = __ffsll((long long)rest) - 1;
                 rest &= rest - 1;
-                dst[slot++] = pack_item(make_child(bit));
+                const State c = make_child(bit);
+                if constexpr (ORDERED) kdst[slot] = c.key;
+                dst[slot++] = pack_item(c);
             }
         }
         __syncwarp();

@@ -9,6 +9,8 @@
 #include <thread>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 #include "fmb_host.hpp"
 #include "fmb_scheme.cuh"
 
@@ -29,12 +31,12 @@ int set_device(int device) {
 constexpr uint32_t kStackCapDefault = 160;   // items per warp (5 KB; 40 KB per block, 4 blocks per SM)
 constexpr uint32_t kWarpsPerBlock = 8;
 
-template <class OCC, bool EDIT>
+template <class OCC, bool EDIT, bool ORDERED>
 int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const SchemeParams& sp, const fmb_queries* q, uint64_t n_roots, const Item* in_items,
                     uint64_t n_in, const SchemeOut& out, cudaStream_t st) {
     static const uint32_t kStackCap = getenv("FMB_SCHEME_CAP") ? (uint32_t)atoi(getenv("FMB_SCHEME_CAP")) : kStackCapDefault;
-    size_t smem = (size_t)kStackCap * kWarpsPerBlock * sizeof(Item);
-    auto kern = scheme_search_kernel<OCC, EDIT>;
+    size_t smem = (size_t)kStackCap * kWarpsPerBlock * (sizeof(Item) + (ORDERED ? sizeof(unsigned long long) : 0));
+    auto kern = scheme_search_kernel<OCC, EDIT, ORDERED>;
     // launch geometry, computed once per kernel instantiation (several host threads drive one index in the pipelined path)
     static std::mutex cfg_mu;
     static int cfg_blocks_per_sm = 0, cfg_sms = 0;
@@ -82,14 +84,107 @@ int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const Schem
     note_launches(1);
     return FMB_OK;
 }
-template <bool EDIT>
+template <bool EDIT, bool ORDERED>
 int launch_scheme(const fmb_index* ix, const SchemeParams& sp, const fmb_queries* q, uint64_t n_roots, const Item* in_items,
                   uint64_t n_in, const SchemeOut& out, cudaStream_t st) {
-    if (ix->dna) return launch_scheme_t<OccDna, EDIT>(ix, ix->view_dna(), sp, q, n_roots, in_items, n_in, out, st);
-    return launch_scheme_t<OccGen, EDIT>(ix, ix->view_gen(), sp, q, n_roots, in_items, n_in, out, st);
+    if (ix->dna) return launch_scheme_t<OccDna, EDIT, ORDERED>(ix, ix->view_dna(), sp, q, n_roots, in_items, n_in, out, st);
+    return launch_scheme_t<OccGen, EDIT, ORDERED>(ix, ix->view_gen(), sp, q, n_roots, in_items, n_in, out, st);
 }
 
-int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp, fmb_results** out_res) {
+// ---- hit limit: put the hits into the reference's discovery order and cut every query off after n rows ----------------------
+__global__ void iota_kernel(uint32_t* out, uint64_t count) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (uint32_t)i;
+}
+__global__ void gather_qidx_kernel(const HitRec* __restrict__ hits, const uint32_t* __restrict__ perm, uint32_t* __restrict__ out, uint64_t count) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < count) out[i] = hits[perm[i]].qidx;
+}
+__global__ void gather_hits_kernel(const HitRec* __restrict__ hits, const uint32_t* __restrict__ perm, HitRec* __restrict__ out, uint64_t count) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < count) out[i] = hits[perm[i]];
+}
+// search_n_impl's delegate (SearchNg26.h:414-421): `ct` rows reported so far; a cursor that would exceed n is clipped to n - ct rows,
+// and the query ends when ct == n.  hits are sorted by (qidx, discovery order); the thread at the first hit of a query walks
+// that query's hits (flags are zero beforehand).
+__global__ void limit_rows_kernel(HitRec* __restrict__ hits, uint32_t* __restrict__ keep, uint64_t count, unsigned long long n) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t q = hits[i].qidx;
+    if (i > 0 && hits[i - 1].qidx == q) return;
+    unsigned long long ct = 0;
+    for (uint64_t j = i; j < count && hits[j].qidx == q; ++j) {
+        unsigned long long len = hits[j].len;
+        if (len + ct > n) {
+            len = n - ct;
+            hits[j].len = (uint32_t)len;
+        }
+        ct += len;
+        keep[j] = 1;
+        if (ct == n) break;
+    }
+}
+__global__ void scatter_kept_kernel(const HitRec* __restrict__ hits, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos,
+                                    HitRec* __restrict__ out, uint64_t count) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < count && keep[i]) out[pos[i]] = hits[i];
+}
+
+int order_and_limit(fmb_results* res, DevBuf<unsigned long long>& keys, uint64_t n_limit, cudaStream_t st) {
+    const uint64_t count = res->count;
+    if (count == 0) return FMB_OK;
+    if (count >= 0xFFFFFFFFull) { set_error("hit-limited search: %llu hits before the limit is applied, split the query batch", (unsigned long long)count); return FMB_EOVERFLOW; }
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    DevBuf<uint32_t> perm_a, perm_b, qk_a, qk_b;
+    DevBuf<unsigned long long> keys_b;
+    DevBuf<HitRec> sorted;
+    FMB_TRY(perm_a.alloc(count)); FMB_TRY(perm_b.alloc(count)); FMB_TRY(qk_a.alloc(count + 1)); FMB_TRY(qk_b.alloc(count + 1));
+    FMB_TRY(keys_b.alloc(count)); FMB_TRY(sorted.alloc(count));
+    iota_kernel<<<grid, 256, 0, st>>>(perm_a.p, count);
+    size_t tmp_bytes = 0, tmp_bytes2 = 0, tmp_bytes3 = 0;
+    FMB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_b.p, perm_a.p, perm_b.p, (int64_t)count, 0, 64, st));
+    FMB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes2, qk_a.p, qk_b.p, perm_b.p, perm_a.p, (int64_t)count, 0, 32, st));
+    FMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes3, qk_a.p, qk_b.p, (int64_t)(count + 1), st));
+    DevBuf<uint8_t> tmp;
+    FMB_TRY(tmp.alloc(std::max(tmp_bytes, std::max(tmp_bytes2, tmp_bytes3))));
+    FMB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_b.p, perm_a.p, perm_b.p, (int64_t)count, 0, 64, st));     // discovery order ...
+    gather_qidx_kernel<<<grid, 256, 0, st>>>(res->hits.p, perm_b.p, qk_a.p, count);
+    FMB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes2, qk_a.p, qk_b.p, perm_b.p, perm_a.p, (int64_t)count, 0, 32, st));      // ... within ascending qidx (stable)
+    gather_hits_kernel<<<grid, 256, 0, st>>>(res->hits.p, perm_a.p, sorted.p, count);
+    // qk_a: keep flags (+ one trailing zero), qk_b: their exclusive sum -- qk_b[count] = number of hits kept
+    FMB_CUDA(cudaMemsetAsync(qk_a.p, 0, (count + 1) * sizeof(uint32_t), st));
+    limit_rows_kernel<<<grid, 256, 0, st>>>(sorted.p, qk_a.p, count, (unsigned long long)n_limit);
+    FMB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes3, qk_a.p, qk_b.p, (int64_t)(count + 1), st));
+    scatter_kept_kernel<<<grid, 256, 0, st>>>(sorted.p, qk_a.p, qk_b.p, res->hits.p, count);
+    uint32_t kept = 0;
+    FMB_CUDA(cudaMemcpyAsync(&kept, qk_b.p + count, sizeof kept, cudaMemcpyDeviceToHost, st));
+    FMB_CUDA(cudaStreamSynchronize(st));
+    FMB_CUDA(cudaGetLastError());
+    note_launches(9);
+    res->count = kept;
+    return FMB_OK;
+}
+
+// n_limit = UINT64_MAX: every hit, in no particular order; else the reference's search_n semantics (SearchNg26.h:408-423)
+int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp_in, fmb_results** out_res, uint64_t n_limit = UINT64_MAX) {
+    SchemeParams sp = sp_in;
+    const bool ordered = n_limit != UINT64_MAX;
+    if (ordered) {
+        uint32_t K = 0, total = 0;
+        for (uint32_t s = 0; s < sp.n_searches; ++s)
+            for (uint32_t p = 0; p < sp.n_parts; ++p) K = std::max<uint32_t>(K, sp.u[s][p]);
+        for (uint32_t p = 0; p < sp.n_parts; ++p) total += sp.partition[p];
+        sp.key_slots = K;
+        sp.key_maxd = total + 2 * K + 2;
+        sp.key_ords = 2 * ix->sigma + 2;
+        const uint64_t range = (uint64_t)sp.key_maxd + 1 + (uint64_t)sp.key_maxd * sp.key_ords;
+        sp.key_bits = 1;
+        while ((1ull << sp.key_bits) < range) ++sp.key_bits;
+        if (K * sp.key_bits > 56) {
+            set_error("hit-limited search: %u errors on %u-symbol queries need %u key bits (56 available)", K, total, K * sp.key_bits);
+            return FMB_EUNSUPPORTED;
+        }
+    }
     FMB_TRY(set_device(ix->device));
     cudaStream_t st = active_stream(ix);
     auto res = new fmb_results();
@@ -102,9 +197,14 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     uint64_t hit_cap = std::max<uint64_t>(1u << 20, nq * 8);
     const uint64_t ovf_cap = 1u << 22;       // 4 M items = 128 MB per buffer
     DevBuf<Item> ovf[2];
+    DevBuf<unsigned long long> ovf_keys[2], hit_keys;
     DevBuf<unsigned long long> ctr;          // [0..3] counters, [4] hit_count, [5] overflow_count, [6] root_counter
     FMB_TRY(ovf[0].alloc(ovf_cap));
     FMB_TRY(ovf[1].alloc(ovf_cap));
+    if (ordered) {
+        FMB_TRY(ovf_keys[0].alloc(ovf_cap));
+        FMB_TRY(ovf_keys[1].alloc(ovf_cap));
+    }
     FMB_TRY(ctr.alloc(8));
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0);
@@ -113,8 +213,10 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     unsigned long long h_ctr[8];
     for (int attempt = 0; attempt < 2; ++attempt) {
         FMB_TRY(res->hits.alloc(hit_cap));
+        if (ordered) FMB_TRY(hit_keys.alloc(hit_cap));
         FMB_CUDA(cudaMemsetAsync(ctr.p, 0, 8 * sizeof(unsigned long long), st));
-        SchemeOut so;
+        SchemeOut so{};
+        so.hit_keys = hit_keys.p;
         so.hits = res->hits.p;
         so.hit_count = ctr.p + 4;
         so.hit_capacity = hit_cap;
@@ -128,10 +230,14 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
         cudaEventRecord(ev0, st);
         for (int pass = 0;; ++pass) {
             so.overflow = ovf[cur].p;
+            so.overflow_keys = ovf_keys[cur].p;
+            so.in_keys = pass ? ovf_keys[cur ^ 1].p : nullptr;
             const Item* in_items = pass ? ovf[cur ^ 1].p : nullptr;
             if (roots + n_in > 0) {
-                int rc = sp.edit ? launch_scheme<true>(ix, sp, q, roots, in_items, n_in, so, st)
-                                 : launch_scheme<false>(ix, sp, q, roots, in_items, n_in, so, st);
+                int rc = ordered ? (sp.edit ? launch_scheme<true, true>(ix, sp, q, roots, in_items, n_in, so, st)
+                                            : launch_scheme<false, true>(ix, sp, q, roots, in_items, n_in, so, st))
+                                 : (sp.edit ? launch_scheme<true, false>(ix, sp, q, roots, in_items, n_in, so, st)
+                                            : launch_scheme<false, false>(ix, sp, q, roots, in_items, n_in, so, st));
                 if (rc) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
             }
             FMB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
@@ -166,6 +272,7 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     res->stats.line_requests = h_ctr[2];
     res->stats.kernel_ms = total_ms;
     res->stats.main_kernel_ms = total_ms;
+    if (ordered) FMB_TRY(order_and_limit(res, hit_keys, n_limit, st));
     guard.r = nullptr;
     *out_res = res;
     return FMB_OK;
@@ -177,6 +284,11 @@ extern "C" {
 
 int fmb_search_scheme(const fmb_index* ix, const fmb_queries* q, int edit, uint32_t n_searches, uint32_t n_parts,
                       const uint32_t* pi, const uint32_t* l, const uint32_t* u, const uint32_t* partition, fmb_results** out) {
+    return fmb_search_scheme_n(ix, q, edit, n_searches, n_parts, pi, l, u, partition, UINT64_MAX, out);
+}
+
+int fmb_search_scheme_n(const fmb_index* ix, const fmb_queries* q, int edit, uint32_t n_searches, uint32_t n_parts,
+                        const uint32_t* pi, const uint32_t* l, const uint32_t* u, const uint32_t* partition, uint64_t n, fmb_results** out) {
     if (!ix || !q || !out || !pi || !l || !u || !partition) { set_error("NULL argument"); return FMB_EINVAL; }
     *out = nullptr;
     if (!ix->bidirectional) { set_error("search schemes need a bidirectional index (extendRight)"); return FMB_EINVAL; }
@@ -225,7 +337,14 @@ int fmb_search_scheme(const fmb_index* ix, const fmb_queries* q, int edit, uint3
         for (uint32_t i = 0; i < sp.pi[s][0]; ++i) start += sp.partition[i];
         sp.start[s] = (uint16_t)start;
     }
-    return run_scheme(ix, q, sp, out);
+    if (n == 0) {                                   // search_n_impl returns at once (SearchNg26.h:410)
+        auto res = new fmb_results();
+        res->device = ix->device;
+        res->kind = 0;
+        *out = res;
+        return FMB_OK;
+    }
+    return run_scheme(ix, q, sp, out, n);
 }
 
 int fmb_search_backtracking(const fmb_index* ix, const fmb_queries* q, uint32_t max_errors, fmb_results** out) {

@@ -1,0 +1,133 @@
+"""GPU parity: hit-limited search (search_n: search_ng26::search(..., n), SearchNg26.h:408-433; fmc::search_n, search/search.h:37-45).
+
+With a limit the reference reports, per query, the first n ROWS in the order its depth-first search finds them, clipping the
+cursor that crosses the limit.  fmb_search_scheme_n must return exactly that list -- hits are compared IN ORDER, not as sets:
+the oracle (and the reference) emit them by ascending qidx, then discovery order."""
+import numpy as np
+import pytest
+
+from helpers import make_index_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _remap(s):
+    return np.array([{"A": 1, "B": 2, "C": 3, "D": 4}[c] for c in s], dtype=np.uint8)
+
+
+def _located(g, res):
+    return sorted((int(r["qidx"]), int(r["seq"]), int(r["pos"])) for r in g.locate(res).locs())
+
+
+def _same_list(got, exp):
+    got, exp = np.asarray(got), np.asarray(exp)
+    if got.shape != exp.shape:
+        return False
+    return all(np.array_equal(got[f].astype(np.uint64), exp[f].astype(np.uint64)) for f in ("qidx", "lb", "lb_rev", "len", "steps", "e"))
+
+
+def test_golden_search_n(gpu):
+    """search/checkSearches.cpp:1148-1172 (ng26, n = 3) and :1446-1466 (fmc::search_n<true>, n = 3)"""
+    from fmb200 import schemes, synth
+    text = np.concatenate([_remap("AAACAAABAAA"), [0], _remap("AAABAAACAAA"), [0]]).astype(np.uint8)
+    o, g = make_index_pair(gpu, text, 5, 1)
+    q = synth.flatten([_remap("CC"), _remap("BB")])
+    pigeon_opt = (np.array([[0, 1], [1, 0]]), np.array([[0, 0], [0, 1]]), np.array([[0, 1], [0, 1]]))
+    part = schemes.uniform_partition(2, 2)
+    exp_n3 = [(0, 0, 3), (0, 1, 7), (0, 1, 7), (1, 0, 7), (1, 0, 7), (1, 1, 3)]
+    assert _located(g, g.search_scheme(g.upload(*q), pigeon_opt, part, True, n=3)) == exp_n3
+    sch, p = schemes.facade_scheme(True, 1, 2)
+    assert _located(g, g.search_scheme(g.upload(*q), sch, p, True, n=3)) == exp_n3
+    assert len(g.search_scheme(g.upload(*q), sch, p, True, n=0)) == 0                       # SearchNg26.h:410
+
+
+@pytest.fixture(scope="module")
+def pair(gpu):
+    from fmb200 import synth
+    text = synth.multi_text([6000, 3000, 700, 5], 5, 21)
+    o, g = make_index_pair(gpu, text, 5, 8)
+    return text, o, g
+
+
+@pytest.mark.parametrize("k", [1, 2])
+@pytest.mark.parametrize("edit", [False, True])
+def test_search_n_random_text(pair, k, edit):
+    from fmb200 import schemes, synth
+    text, o, g = pair
+    L = 40
+    reads, _ = synth.reads_from_text(text[:6000], 300, L, 77)
+    reads = synth.plant_errors(reads, 5, 1, edit, 7 + k)
+    sym, off = synth.flatten(reads)
+    q = g.upload(sym, off)
+    for sch in (schemes.optimum(0, k), schemes.facade_scheme(edit, k, L)[0]):
+        part = schemes.uniform_partition(sch[0].shape[1], L)
+        for n in (1, 2, 3, 7, 10**9):
+            exp = o.search_ng26(sym, off, sch, part, edit, max_hits=n)
+            got = g.search_scheme(q, sch, part, edit, n=n).hits()
+            assert _same_list(got, exp), (k, edit, n)
+
+
+@pytest.mark.parametrize("edit", [False, True])
+def test_search_n_repetitive_text(gpu, edit):
+    """wide intervals: the order of the children of search_next_dir (match, deletion(c) / substitution(c) by symbol, insertion) and
+    clipping of cursors with many rows"""
+    from fmb200 import schemes, synth
+    rng = np.random.default_rng(3)
+    unit = rng.integers(1, 5, size=50).astype(np.uint8)
+    seqs = []
+    for _ in range(40):
+        u = unit.copy()
+        for p in rng.integers(0, 50, size=2):
+            u[p] = rng.integers(1, 5)
+        seqs.append(u)
+    text = np.concatenate([np.concatenate([s, [0]]) for s in seqs]).astype(np.uint8)
+    o, g = make_index_pair(gpu, text, 5, 4)
+    reads = np.array([seqs[i % 40][5:35] for i in range(60)], dtype=np.uint8)
+    reads = synth.plant_errors(reads, 5, 1, edit, 4)
+    sym, off = synth.flatten(reads)
+    q = g.upload(sym, off)
+    for k in (1, 2, 3):
+        sch = schemes.optimum(0, k) if k < 3 else schemes.h2(5, 0, 3)
+        if not edit:
+            sch = schemes.limit_to_hamming(sch)
+        part = schemes.uniform_partition(sch[0].shape[1], 30)
+        for n in (1, 4, 25, 26, 1000, 10**7):
+            exp = o.search_ng26(sym, off, sch, part, edit, max_hits=n)
+            got = g.search_scheme(q, sch, part, edit, n=n).hits()
+            assert _same_list(got, exp), (k, edit, n)
+            assert int(got["len"].astype(np.int64).sum()) <= n * 60
+        assert len(o.search_ng26(sym, off, sch, part, edit)) > len(o.search_ng26(sym, off, sch, part, edit, max_hits=4))   # the limit cuts
+
+
+def test_search_n_protein(gpu):
+    """generic layout (sigma = 21): byte-symbol jump tables, 42 + 2 child ranks per node"""
+    from fmb200 import schemes, synth
+    text = synth.multi_text([5000, 1200], 21, 9)
+    o, g = make_index_pair(gpu, text, 21, 4)
+    L = 20
+    reads, _ = synth.reads_from_text(text[:5000], 200, L, 3)
+    reads = synth.plant_errors(reads, 21, 1, True, 4)
+    sym, off = synth.flatten(reads)
+    q = g.upload(sym, off)
+    for k, edit in ((1, False), (1, True), (2, True)):
+        sch = schemes.optimum(0, k)
+        part = schemes.uniform_partition(sch[0].shape[1], L)
+        for n in (1, 2, 5):
+            exp = o.search_ng26(sym, off, sch, part, edit, max_hits=n)
+            assert _same_list(g.search_scheme(q, sch, part, edit, n=n).hits(), exp), (k, edit, n)
+
+
+def test_search_n_refuses_keys_that_do_not_fit(pair):
+    from fmb200 import schemes, synth
+    text, o, g = pair
+    L = 40
+    reads, _ = synth.reads_from_text(text[:6000], 4, L, 1)
+    sym, off = synth.flatten(reads)
+    sch = schemes.backtracking(1, 0, 6)              # 6 errors x 11 bits > 56
+    with pytest.raises(gpu_error()):
+        g.search_scheme(g.upload(sym, off), sch, [L], True, n=5)
+
+
+def gpu_error():
+    import fmb200
+    return fmb200.FmbError

@@ -9,9 +9,11 @@
 //   search/search.h:14-75                 fmc::search<Edit>(index, queries, errors, delegate), fmc::Search{...}()
 //   locate.h:15-57                        LocateLinear{index, cursor}
 // Differences a caller can observe: delegates are invoked after the device finished, grouped by
-// ascending qidx (the reference's batched exact search retires queries out of order; tests compare sorted); the
-// hit limit `n` of search_n / search_best is not supported (it depends on the reference's DFS order) -- any n other
-// than the default throws.  `*_bulk` variants return the raw records without per-hit callbacks.
+// ascending qidx (the reference's batched exact search retires queries out of order; tests compare sorted).  With a hit
+// limit `n` (search_ng26::search(..., n), search_best(..., n), fmc::search_n, Search::maxResults) the delegate sees exactly
+// the reference's calls in the reference's order: ascending qidx, within a query the order of its depth-first search,
+// the cursor that crosses the limit clipped (SearchNg26.h:408-423).  `*_bulk` variants return the raw records without
+// per-hit callbacks.
 #pragma once
 #include <algorithm>
 #include <limits>
@@ -40,6 +42,11 @@ inline std::vector<fmb_hit> fetch_hits(fmb_results* r) {
     std::vector<fmb_hit> hits(fmb_results_count(r));
     check(fmb_results_fetch_hits(r, hits.data(), hits.size()));
     return hits;
+}
+constexpr size_t kNoLimit = std::numeric_limits<size_t>::max();
+// hit-limited results keep the discovery order inside a query: only group them by ascending qidx
+inline void group_hits_by_query(std::vector<fmb_hit>& hits) {
+    std::stable_sort(hits.begin(), hits.end(), [](fmb_hit const& a, fmb_hit const& b) { return a.qidx < b.qidx; });
 }
 inline void sort_hits(std::vector<fmb_hit>& hits) {
     std::sort(hits.begin(), hits.end(), [](fmb_hit const& a, fmb_hit const& b) {
@@ -139,17 +146,18 @@ namespace search_ng26 {
 
 template <bool Edit = true, typename index_t, Sequences queries_t, detail::SchemeLike scheme_t>
 std::vector<fmb_hit> search_bulk(index_t const& index, queries_t const& queries, scheme_t const& scheme,
-                                 std::vector<size_t> const& partition, fmb_stats* stats = nullptr) {
+                                 std::vector<size_t> const& partition, fmb_stats* stats = nullptr, size_t n = detail::kNoLimit) {
     static_assert(detail::is_bidirectional<index_t>, "search schemes need a bidirectional index (extendRight)");
     auto fs = detail::flatten(scheme, partition);
     auto flat = flatten(queries);
     auto q = detail::upload(index.handle(), flat);
     fmb_results* r{};
-    check(fmb_search_scheme(index.handle(), q.get(), Edit ? 1 : 0, fs.n_searches, fs.n_parts, fs.pi.data(), fs.l.data(), fs.u.data(), fs.partition.data(), &r));
+    if (n == detail::kNoLimit) check(fmb_search_scheme(index.handle(), q.get(), Edit ? 1 : 0, fs.n_searches, fs.n_parts, fs.pi.data(), fs.l.data(), fs.u.data(), fs.partition.data(), &r));
+    else check(fmb_search_scheme_n(index.handle(), q.get(), Edit ? 1 : 0, fs.n_searches, fs.n_parts, fs.pi.data(), fs.l.data(), fs.u.data(), fs.partition.data(), n, &r));
     detail::ResultsHandle res{r};
     if (stats) check(fmb_results_get_stats(r, stats));
     auto hits = detail::fetch_hits(r);
-    detail::sort_hits(hits);
+    if (n == detail::kNoLimit) detail::sort_hits(hits);      // with a limit the device returns (qidx, discovery order)
     return hits;
 }
 
@@ -157,14 +165,14 @@ std::vector<fmb_hit> search_bulk(index_t const& index, queries_t const& queries,
 template <bool Edit = true, typename index_t, Sequences queries_t, detail::SchemeLike scheme_t, typename delegate_t>
 void search(index_t const& index, queries_t&& queries, scheme_t const& scheme, std::vector<size_t> const& partition,
             delegate_t&& delegate, size_t n = std::numeric_limits<size_t>::max()) {
-    if (n != std::numeric_limits<size_t>::max()) throw std::runtime_error("fmb200: the hit limit n of search_ng26::search is not supported");
-    for (auto const& h : search_bulk<Edit>(index, queries, scheme, partition)) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
+    if (n == 0) return;                                       // SearchNg26.h:410
+    for (auto const& h : search_bulk<Edit>(index, queries, scheme, partition, nullptr, n)) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
 }
 
 // SearchNg26.h:436-444: scheme selected per query length (h2 with maxErrors+2 parts, CachedSearchScheme.h:15-36).
 // Queries are grouped by length; every group is one device call.
 template <bool Edit = true, typename index_t, Sequences queries_t>
-std::vector<fmb_hit> search_bulk(index_t const& index, queries_t const& queries, size_t maxErrors) {
+std::vector<fmb_hit> search_bulk(index_t const& index, queries_t const& queries, size_t maxErrors, size_t n = detail::kNoLimit) {
     std::map<size_t, std::vector<size_t>> by_len;
     size_t qidx = 0;
     for (auto const& q : queries) by_len[std::ranges::size(q)].push_back(qidx++);
@@ -182,27 +190,29 @@ std::vector<fmb_hit> search_bulk(index_t const& index, queries_t const& queries,
             std::ranges::copy(q, store.back().begin());
             group.emplace_back(store.back());
         }
-        auto hits = search_bulk<Edit>(index, group, scheme, partition);
+        auto hits = search_bulk<Edit>(index, group, scheme, partition, nullptr, n);
         for (auto& h : hits) h.qidx = ids[h.qidx];
         all.insert(all.end(), hits.begin(), hits.end());
     }
-    detail::sort_hits(all);
+    if (n == detail::kNoLimit) detail::sort_hits(all);
+    else detail::group_hits_by_query(all);
     return all;
 }
 template <bool Edit = true, typename index_t, Sequences queries_t, typename delegate_t>
 void search(index_t const& index, queries_t&& queries, size_t maxErrors, delegate_t&& delegate, size_t n = std::numeric_limits<size_t>::max()) {
-    if (n != std::numeric_limits<size_t>::max()) throw std::runtime_error("fmb200: the hit limit n of search_ng26::search is not supported");
-    for (auto const& h : search_bulk<Edit>(index, queries, maxErrors)) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
+    if (n == 0) return;
+    for (auto const& h : search_bulk<Edit>(index, queries, maxErrors, n)) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
 }
 
 // SearchNg26.h:448-470: search_best with a list of (scheme, partition) pairs -- per query, the first pair that yields a hit wins.
-// Device form: pair 0 runs on all queries, pair 1 on the queries still without a hit, and so on.  (No hit limit: n must be the
-// default; all queries of a call must have the length the partitions sum to.)
+// Device form: pair 0 runs on all queries, pair 1 on the queries still without a hit, and so on.  The hit limit n counts per
+// pair (`ct` is reset for every pair, :453).  All queries of a call must have the length the partitions sum to.
 template <bool Edit = true, typename index_t, Sequences queries_t, typename schemes_t, typename delegate_t>
     requires requires(schemes_t const& ss) { std::get<0>(*std::begin(ss)); std::get<1>(*std::begin(ss)); }
 void search_best(index_t const& index, queries_t&& queries, schemes_t const& search_schemes, delegate_t&& delegate,
                  size_t n = std::numeric_limits<size_t>::max()) {
-    if (n != std::numeric_limits<size_t>::max()) throw std::runtime_error("fmb200: the hit limit n of search_ng26::search_best is not supported");
+    // n == 0: `ct == n` never holds and `cur.len = n - ct` wraps in the reference -- nothing sensible to mirror
+    if (n == 0) throw std::invalid_argument("fmb200: search_best with n == 0");
     size_t const Q = std::ranges::size(queries);
     std::vector<size_t> pending(Q);
     for (size_t i = 0; i < Q; ++i) pending[i] = i;
@@ -220,7 +230,7 @@ void search_best(index_t const& index, queries_t&& queries, schemes_t const& sea
             std::ranges::copy(q, store.back().begin());
             group.emplace_back(store.back());
         }
-        auto hits = search_bulk<Edit>(index, group, scheme, partition);
+        auto hits = search_bulk<Edit>(index, group, scheme, partition, nullptr, n);
         std::vector<char> found(pending.size(), 0);
         for (auto& h : hits) {
             found[h.qidx] = 1;
@@ -232,7 +242,8 @@ void search_best(index_t const& index, queries_t&& queries, schemes_t const& sea
             if (!found[i]) rest.push_back(pending[i]);
         pending.swap(rest);
     }
-    detail::sort_hits(all);
+    if (n == detail::kNoLimit) detail::sort_hits(all);
+    else detail::group_hits_by_query(all);
     for (auto const& h : all) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
 }
 
@@ -241,9 +252,9 @@ void search_best(index_t const& index, queries_t&& queries, schemes_t const& sea
 // that the inner call is `search(index, queries, i, …)` with its default Edit = true whatever search_best's own parameter is.
 template <bool Edit = true, typename index_t, Sequences queries_t, typename delegate_t>
 void search_best(index_t const& index, queries_t&& queries, size_t maxErrors, delegate_t&& delegate, size_t n = std::numeric_limits<size_t>::max()) {
-    if (n != std::numeric_limits<size_t>::max()) throw std::runtime_error("fmb200: the hit limit n of search_ng26::search_best is not supported");
+    if (n == 0) return;                                       // every inner search returns at once (:410)
     for (size_t i = 0; i < maxErrors; ++i) {
-        auto hits = search_bulk<true>(index, queries, i);
+        auto hits = search_bulk<true>(index, queries, i, n);
         if (hits.empty()) continue;
         for (auto const& h : hits) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
         break;
@@ -327,6 +338,13 @@ void search(index_t const& index, queries_t const& queries, size_t errors, deleg
     }
 }
 
+// search/search.h:37-45: at most n rows per query, in the order the reference finds them (always through search_ng26, also for
+// errors == 0: the h2 scheme with two error-free parts)
+template <bool EditDistance, typename index_t, Sequences queries_t, typename delegate_t>
+void search_n(index_t const& index, queries_t const& queries, size_t errors, size_t n, delegate_t&& delegate) {
+    search_ng26::search<EditDistance>(index, queries, errors, std::forward<delegate_t>(delegate), n);
+}
+
 // search/search.h:47-75: search + locate, reportFunc(qidx, seqId, pos + offset, errors).  One device pass
 // (fmb_search_and_locate for explicit schemes is used by search_and_locate_bulk below).
 template <typename index_t, Sequences queries_t, typename delegate_t>
@@ -338,9 +356,11 @@ struct Search {
     std::optional<size_t> maxResults{};
     delegate_t const& reportFunc;
     void operator()() {
-        if (maxResults) throw std::runtime_error("fmb200: Search::maxResults (search_n) is not supported");
         std::vector<fmb_hit> hits;
-        if (errors == 0) hits = search_no_errors::search_bulk(index, queries);
+        if (maxResults) {
+            if (*maxResults == 0) return;
+            hits = editDistance ? search_ng26::search_bulk<true>(index, queries, errors, *maxResults) : search_ng26::search_bulk<false>(index, queries, errors, *maxResults);
+        } else if (errors == 0) hits = search_no_errors::search_bulk(index, queries);
         else hits = editDistance ? search_ng26::search_bulk<true>(index, queries, errors) : search_ng26::search_bulk<false>(index, queries, errors);
         // locate all rows of all hits in one launch
         std::vector<uint64_t> rows;

@@ -146,6 +146,49 @@ int main() {
             CHECK(r2.cursors == g2.cursors);
         }
     }
+    // hit limit n (search_n): the delegate must see the reference's calls IN THE REFERENCE'S ORDER -- nothing is sorted here.
+    // search_ng26::search(..., n) with an explicit scheme and with maxErrors (SearchNg26.h:426-444), fmc::search_n
+    // (search/search.h:37-45), search_best(..., n) (:448-470) and fmc::Search{... maxResults ...} (:47-75)
+    for (size_t n : {1, 3, 8, 100000}) {
+        for (size_t k : {1, 2}) {
+            auto scheme = fmc::search_scheme::generator::optimum(0, k);
+            auto partition = fmc::search_scheme::createUniformPartition(scheme, 50);
+            Collector ref{index}, gpu{index}, refh{index}, gpuh{index}, reff{index}, gpuf{index};
+            fmc::search_ng26::search<true>(index, queries, scheme, partition, [&](size_t q, auto c, size_t e) { ref(q, c, e); }, n);
+            fmb200::search_ng26::search<true>(dev, queries, scheme, partition, [&](size_t q, auto c, size_t e) { gpu(q, c, e); }, n);
+            CHECK(ref.cursors == gpu.cursors);
+            CHECK(ref.located == gpu.located);
+            fmc::search_ng26::search<false>(index, queries, scheme, partition, [&](size_t q, auto c, size_t e) { refh(q, c, e); }, n);
+            fmb200::search_ng26::search<false>(dev, queries, scheme, partition, [&](size_t q, auto c, size_t e) { gpuh(q, c, e); }, n);
+            CHECK(refh.cursors == gpuh.cursors);
+            fmc::search_n<true>(index, queries, k, n, [&](size_t q, auto c, size_t e) { reff(q, c, e); });
+            fmb200::search_n<true>(dev, queries, k, n, [&](size_t q, auto c, size_t e) { gpuf(q, c, e); });
+            CHECK(reff.cursors == gpuf.cursors);
+            CHECK(reff.located == gpuf.located);
+            if (n == 1) CHECK(reff.located.size() <= queries.size());
+        }
+        {
+            using Pair = std::tuple<fmc::search_scheme::Scheme, std::vector<size_t>>;
+            std::vector<Pair> schemes;
+            for (size_t k : {0, 1, 2}) {
+                auto sch = fmc::search_scheme::generator::optimum(0, k);
+                schemes.emplace_back(sch, fmc::search_scheme::createUniformPartition(sch, 50));
+            }
+            Collector ref{index}, gpu{index};
+            fmc::search_ng26::search_best<true>(index, queries, schemes, [&](size_t q, auto c, size_t e) { ref(q, c, e); }, n);
+            fmb200::search_ng26::search_best<true>(dev, queries, schemes, [&](size_t q, auto c, size_t e) { gpu(q, c, e); }, n);
+            CHECK(ref.cursors == gpu.cursors);
+        }
+        {
+            std::vector<std::array<uint64_t, 4>> ref, gpu;
+            auto r1 = [&](size_t q, size_t sid, size_t pos, size_t e) { ref.push_back({q, sid, pos, e}); };
+            auto r2 = [&](size_t q, size_t sid, size_t pos, size_t e) { gpu.push_back({q, sid, pos, e}); };
+            fmc::Search{index, queries, true, size_t{2}, std::optional<size_t>{n}, r1}();
+            fmb200::Search{dev, queries, true, size_t{2}, std::optional<size_t>{n}, r2}();
+            CHECK(ref == gpu);
+            CHECK(!ref.empty());
+        }
+    }
     // fmc::Search functor vs fmb200::Search: reportFunc(qidx, seqId, pos + offset, errors)
     {
         std::vector<std::array<uint64_t, 4>> ref, gpu;

@@ -6,6 +6,8 @@
 //   search/SearchNg26.h:426-444           search_ng26::search<Edit>(index, queries, scheme, partition, delegate(qidx, cursor, e))
 //                                         search_ng26::search<Edit>(index, queries, maxErrors, delegate)
 //   search/Backtracking.h:85-98           search_backtracking::search(index, queries, maxError, delegate(qidx, cursor, e))
+//   search/SearchOneError.h:126-145       search_one_error::search(index, queries, delegate(qidx, cursor, e))
+//   search/SearchPseudo.h:171-186         search_pseudo::search<false>(index, queries, expanded scheme, delegate(qidx, cursor, e))
 //   search/search.h:14-75                 fmc::search<Edit>(index, queries, errors, delegate), fmc::Search{...}()
 //   locate.h:15-57                        LocateLinear{index, cursor}
 // Differences a caller can observe: delegates are invoked after the device finished, grouped by
@@ -262,6 +264,130 @@ void search_best(index_t const& index, queries_t&& queries, size_t maxErrors, de
 }
 
 }  // namespace search_ng26
+
+// =====================================================================================================================
+// search/SearchOneError.h:126-145: at most one substitution.  The reference hard-codes a two-search scheme: left half exact then
+// right half with <= 1 mismatch (reports e = 0 and e = 1), right half exact then left half with exactly one mismatch -- i.e.
+// {pi 01, l 00, u 01}, {pi 10, l 01, u 01} over the partition {L - L/2, L/2} (:27,73), searched with Hamming distance.
+namespace search_one_error {
+
+template <typename index_t, Sequences queries_t>
+std::vector<fmb_hit> search_bulk(index_t const& index, queries_t const& queries) {
+    std::map<size_t, std::vector<size_t>> by_len;
+    size_t qidx = 0;
+    for (auto const& q : queries) by_len[std::ranges::size(q)].push_back(qidx++);
+    std::vector<fmb_hit> all;
+    for (auto const& [len, ids] : by_len) {
+        if (len == 0) {
+            // no symbol to search: search_left_to_right reports the cursor of the whole index with 0 errors (:24-37, 53)
+            for (auto id : ids) all.push_back(fmb_hit{id, 0, 0, index.size(), 0, 0});
+            continue;
+        }
+        search_scheme::Scheme scheme;
+        std::vector<size_t> partition;
+        if (len == 1) {
+            // the right-to-left search has an empty exact half: every symbol other than the query's is a one-error hit (:86-100)
+            scheme = {search_scheme::Search{{0}, {0}, {1}}};
+            partition = {1};
+        } else {
+            scheme = {search_scheme::Search{{0, 1}, {0, 0}, {0, 1}}, search_scheme::Search{{1, 0}, {0, 1}, {0, 1}}};
+            partition = {len - len / 2, len / 2};
+        }
+        std::vector<std::span<uint8_t const>> group;
+        std::vector<std::vector<uint8_t>> store;
+        store.reserve(ids.size());
+        for (auto id : ids) {
+            auto const& q = queries[id];
+            store.emplace_back(std::ranges::size(q));
+            std::ranges::copy(q, store.back().begin());
+            group.emplace_back(store.back());
+        }
+        auto hits = search_ng26::search_bulk<false>(index, group, scheme, partition);
+        for (auto& h : hits) h.qidx = ids[h.qidx];
+        all.insert(all.end(), hits.begin(), hits.end());
+    }
+    detail::sort_hits(all);
+    return all;
+}
+
+template <typename index_t, Sequences queries_t, typename delegate_t>
+void search(index_t const& index, queries_t const& queries, delegate_t&& delegate) {
+    for (auto const& h : search_bulk(index, queries)) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
+}
+
+}  // namespace search_one_error
+
+// =====================================================================================================================
+// search/SearchPseudo.h:171-186: search with an EXPANDED scheme (one pi / l / u entry per query symbol, search_scheme/expand.h:146-165),
+// Hamming distance.  The device kernel works on parts, so the expanded searches are folded back: a part ends where the walk
+// changes direction, where u changes, and at every position whose lower bound is not already implied by an earlier part end
+// (e never decreases, so `l[pos] <= e` holds once a part end with the same or a larger bound was passed -- the argument that makes
+// expand()'s own lower bounds, SearchNg26's per-part check and this per-symbol check agree).  All searches are cut at the union of
+// those boundaries.  The edit-distance form of search_pseudo enumerates alignments without the redundancy filter of search_ng26
+// (different duplicates) and is not provided.
+namespace search_pseudo {
+
+namespace detail_pseudo {
+template <fmb200::detail::SchemeLike scheme_t>
+std::tuple<search_scheme::Scheme, std::vector<size_t>> fold(scheme_t const& expanded) {
+    size_t const L = std::ranges::begin(expanded)->pi.size();
+    if (L == 0) throw std::invalid_argument("fmb200: empty expanded search");
+    std::vector<char> cut(L + 1, 0);          // cut[t]: a part boundary between text positions t-1 and t
+    for (auto const& s : expanded) {
+        if (s.pi.size() != L || s.l.size() != L || s.u.size() != L) throw std::invalid_argument("fmb200: ragged expanded search scheme");
+        size_t implied = 0;                   // largest lower bound checked at a part end so far
+        for (size_t pos = 0; pos + 1 < L; ++pos) {
+            bool const right = pos == 0 ? s.pi[1] > s.pi[0] : s.pi[pos] > s.pi[pos - 1];
+            bool const next_right = s.pi[pos + 1] > s.pi[pos];
+            bool const adjacent = next_right ? s.pi[pos + 1] == s.pi[pos] + 1 : s.pi[pos + 1] + 1 == s.pi[pos];
+            bool end = !adjacent || right != next_right || s.u[pos + 1] != s.u[pos] || s.l[pos] > implied;
+            if (!end) continue;
+            implied = std::max<size_t>(implied, s.l[pos]);
+            cut[next_right ? s.pi[pos + 1] : s.pi[pos + 1] + 1] = 1;
+        }
+    }
+    std::vector<size_t> partition, part_of(L);
+    size_t start = 0;
+    for (size_t t = 1; t <= L; ++t)
+        if (t == L || cut[t]) {
+            for (size_t i = start; i < t; ++i) part_of[i] = partition.size();
+            partition.push_back(t - start);
+            start = t;
+        }
+    search_scheme::Scheme folded;
+    for (auto const& s : expanded) {
+        search_scheme::Search f;
+        for (size_t pos = 0; pos < L; ++pos) {
+            size_t const part = part_of[s.pi[pos]];
+            if (f.pi.empty() || f.pi.back() != part) {
+                if (std::find(f.pi.begin(), f.pi.end(), part) != f.pi.end()) throw std::invalid_argument("fmb200: expanded search visits a part twice");
+                f.pi.push_back(part);
+                f.l.push_back(s.l[pos]);
+                f.u.push_back(s.u[pos]);
+            } else {
+                if (s.u[pos] != f.u.back()) throw std::invalid_argument("fmb200: upper bound changes inside a part");
+                f.l.back() = s.l[pos];       // the bound of the part's last symbol
+            }
+        }
+        folded.push_back(std::move(f));
+    }
+    return {std::move(folded), std::move(partition)};
+}
+}  // namespace detail_pseudo
+
+template <bool EditDistance, typename index_t, Sequences queries_t, fmb200::detail::SchemeLike scheme_t>
+std::vector<fmb_hit> search_bulk(index_t const& index, queries_t const& queries, scheme_t const& expanded) {
+    static_assert(!EditDistance, "fmb200::search_pseudo: only the Hamming-distance form maps onto the device kernels");
+    auto [scheme, partition] = detail_pseudo::fold(expanded);
+    return search_ng26::search_bulk<false>(index, queries, scheme, partition);
+}
+
+template <bool EditDistance, typename index_t, Sequences queries_t, fmb200::detail::SchemeLike scheme_t, typename delegate_t>
+void search(index_t const& index, queries_t&& queries, scheme_t const& expanded, delegate_t&& delegate) {
+    for (auto const& h : search_bulk<EditDistance>(index, queries, expanded)) delegate(static_cast<size_t>(h.qidx), fmb200::detail::make_cursor(index, h), static_cast<size_t>(h.e));
+}
+
+}  // namespace search_pseudo
 
 // =====================================================================================================================
 namespace search_backtracking {

@@ -9,6 +9,8 @@
 #include <fmindex-collection/search/Backtracking.h>
 #include <fmindex-collection/search/SearchNg26.h>
 #include <fmindex-collection/search/SearchNoErrors.h>
+#include <fmindex-collection/search/SearchOneError.h>
+#include <fmindex-collection/search/SearchPseudo.h>
 #include <fmindex-collection/search/search.h>
 #include <fmindex-collection/search_scheme/expand.h>
 #include <fmindex-collection/search_scheme/generator/all.h>
@@ -187,6 +189,34 @@ int main() {
             fmb200::Search{dev, queries, true, size_t{2}, std::optional<size_t>{n}, r2}();
             CHECK(ref == gpu);
             CHECK(!ref.empty());
+        }
+    }
+    // search_one_error (SearchOneError.h:126-145): queries of mixed lengths, including the degenerate lengths 0, 1, 2 and 3
+    {
+        std::vector<std::vector<uint8_t>> mixed(queries.begin(), queries.begin() + 120);
+        for (size_t i = 0; i < mixed.size(); ++i) mixed[i].resize(i < 8 ? i % 4 : 12 + i % 30);
+        Collector ref{index}, gpu{index};
+        fmc::search_one_error::search(index, mixed, [&](size_t q, auto c, size_t e) { ref.cursors.push_back({q, c.lb, c.lbRev, c.len, c.steps, e}); });
+        fmb200::search_one_error::search(dev, mixed, [&](size_t q, auto c, size_t e) {
+            static_assert(std::same_as<decltype(c), fmc::BiFMIndexCursor<RefIndex>>);
+            gpu.cursors.push_back({q, c.lb, c.lbRev, c.len, c.steps, e});
+        });
+        ref.sort(); gpu.sort();
+        CHECK(ref.cursors == gpu.cursors);
+        CHECK(ref.cursors.size() > 100);
+    }
+    // search_pseudo<false> (SearchPseudo.h:171-186) with the reference's expanded schemes (expand.h:146-165)
+    for (size_t k : {1, 2, 3}) {
+        for (int kind = 0; kind < 2; ++kind) {
+            auto scheme = kind == 0 ? fmc::search_scheme::generator::optimum(0, std::min<size_t>(k, 2)) : fmc::search_scheme::generator::h2(k + 2, 0, k);
+            auto expanded = fmc::search_scheme::expand(scheme, 50);
+            Collector ref{index}, gpu{index};
+            fmc::search_pseudo::search<false>(index, queries, expanded, [&](size_t q, auto c, size_t e) { ref(q, c, e); });
+            fmb200::search_pseudo::search<false>(dev, queries, expanded, [&](size_t q, auto c, size_t e) { gpu(q, c, e); });
+            ref.sort(); gpu.sort();
+            CHECK(ref.cursors == gpu.cursors);
+            CHECK(ref.located == gpu.located);
+            CHECK(ref.cursors.size() > 300);
         }
     }
     // fmc::Search functor vs fmb200::Search: reportFunc(qidx, seqId, pos + offset, errors)

@@ -45,7 +45,7 @@ SYMBOLS = [
     "fmb_search_exact", "fmb_search_scheme", "fmb_search_scheme_n", "fmb_search_backtracking", "fmb_locate", "fmb_locate_rows", "fmb_sample_value",
     "fmb_results_count", "fmb_results_kind", "fmb_results_fetch_hits", "fmb_results_fetch_locs", "fmb_results_fetch_locs32",
     "fmb_results_get_stats", "fmb_results_destroy",
-    "fmb_search_and_locate",
+    "fmb_search_and_locate", "fmb_index_save", "fmb_index_load", "fmb_checksum64",
     "fmb_index_set_exact_mode", "fmb_index_set_locate_mode", "fmb_synth_text_device", "fmb_synth_reads_device", "fmb_synth_reads_err_device", "fmb_synth_repeat_text_device", "fmb_synth_unit_reads_device", "fmb_index_set_stream", "fmb_kernel_launch_count", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
 ]
 
@@ -65,6 +65,8 @@ def lib():
     L.fmb_results_count.restype = C.c_uint64
     L.fmb_queries_count.restype = C.c_uint64
     L.fmb_kernel_launch_count.restype = C.c_uint64
+    L.fmb_checksum64.restype = C.c_uint64
+    L.fmb_checksum64.argtypes = [C.c_void_p, C.c_uint64]
     L.fmb_host_alloc_pinned.restype = C.c_void_p
     L.fmb_host_alloc_pinned.argtypes = [C.c_uint64]
     L.fmb_host_free_pinned.argtypes = [C.c_void_p]
@@ -117,6 +119,17 @@ class Index:
         _check(lib().fmb_index_create(C.byref(h), C.c_int(device), C.c_uint32(sigma), C.c_uint64(bwt.size), _ptr(bwt),
                                       _ptr(bwt_rev), _ptr(bm), _ptr(sq), _ptr(sp), C.c_uint64(sq.size)))
         return cls(h)
+
+    @classmethod
+    def load(cls, path, device=0):
+        """loadIndex (fmindex/diskStorage.h:20-27): read the flat index file written by save() and rebuild the device tables"""
+        h = C.c_void_p()
+        _check(lib().fmb_index_load(C.byref(h), C.c_int(device), os.fsencode(path)))
+        return cls(h)
+
+    def save(self, path):
+        """saveIndex (fmindex/diskStorage.h:13-18)"""
+        _check(lib().fmb_index_save(self.h, os.fsencode(path)))
 
     @classmethod
     def build(cls, sigma, text, sampling_rate=16, bidirectional=True, device=0):

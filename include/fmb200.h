@@ -111,6 +111,17 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n,
 int fmb_index_build(fmb_index** out, int device, uint32_t sigma, const uint8_t* text, uint64_t n,
                     uint32_t sampling_rate, int bidirectional, int text_on_device);
 
+/* On-disk form of an index, replacing saveIndex / loadIndex (fmindex/diskStorage.h:13-27; cereal archive of
+ * (bwt, bwtRev, C, annotatedArray), fmindex/BiFMIndex.h:209-215).  The file holds the same content in a flat versioned
+ * layout -- BWT bytes of both directions, sample marker bitmap, samples in row order, each section with a checksum
+ * (layout in csrc/fmb_io.cu) -- and every device table is rebuilt on the GPU when it is loaded.  fmb_index_load
+ * validates magic, version, section sizes and checksums BEFORE it touches the device and fails with FMB_EINVAL on any
+ * mismatch. */
+int fmb_index_save(const fmb_index* ix, const char* path);
+int fmb_index_load(fmb_index** out, int device, const char* path);
+/* the section checksum of the file format (64-bit FNV-style over little-endian 8-byte words, tail zero padded) */
+uint64_t fmb_checksum64(const void* data, uint64_t bytes);
+
 void fmb_index_destroy(fmb_index* ix);
 int  fmb_index_get_info(const fmb_index* ix, fmb_index_info* info);
 int  fmb_index_get_C(const fmb_index* ix, uint64_t* C /* sigma+1 */);           /* member C, BiFMIndex.h:34 */

@@ -10,6 +10,7 @@
 // Errors: every non-zero C-ABI status becomes std::runtime_error (the reference throws std::runtime_error on
 // construction failures, BiFMIndex.h:48-50, utils.h:110,127).  There is no CPU fallback.
 #pragma once
+#include <filesystem>
 #include <algorithm>
 #include <array>
 #include <cstdint>
@@ -292,6 +293,26 @@ struct FMIndex : detail::IndexBase<TSigma, false> {
     }
     explicit FMIndex(fmb_index* raw) { Base::adopt(raw); }
 };
+
+// ---- persistence (fmindex/diskStorage.h:13-27) -------------------------------------------------------------------------
+// saveIndex(index, path) / loadIndex<Index>(path): the flat file of fmb_index_save (BWT bytes + sampled suffix array; the device
+// tables are rebuilt when the file is loaded).  Index = fmb200::BiFMIndex<Sigma> or fmb200::FMIndex<Sigma>; a file of the other
+// kind or another alphabet size is refused.
+template <typename Index>
+void saveIndex(Index const& index, std::filesystem::path const& fileName) {
+    check(fmb_index_save(index.handle(), fileName.c_str()));
+}
+template <typename Index>
+auto loadIndex(std::filesystem::path const& fileName, int device = 0) -> Index {
+    fmb_index* raw{};
+    check(fmb_index_load(&raw, device, fileName.c_str()));
+    detail::IndexHandle guard{raw};
+    fmb_index_info info{};
+    check(fmb_index_get_info(raw, &info));
+    constexpr bool wantBi = requires(Index const& ix) { ix.bwtRev; };
+    if (info.sigma != Index::Sigma || (info.bidirectional != 0) != wantBi) throw std::runtime_error("fmb200::loadIndex: " + fileName.string() + " holds a different index type");
+    return Index{guard.release()};
+}
 
 // ---- cursors -------------------------------------------------------------------------------------------------------
 // BiFMIndexCursor (fmindex/BiFMIndexCursor.h:13-200): value type {index*, lb, lbRev, len, steps}

@@ -3,6 +3,8 @@
 // sequences, run every search entry point with a collecting delegate, compare as sorted multisets.
 // Built by tests/cpp/build.sh, run by tests/test_gpu_cpp_shim.py on the GPU box.  Needs a CUDA device.
 #include <algorithm>
+#include <filesystem>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -256,6 +258,38 @@ int main() {
         CHECK(ss::createUniformPartition(2, 150) == (std::vector<size_t>{75, 75}));
         auto bt = ss::generator::backtracking(3, 1, 2);
         CHECK(bt[0].l == (std::vector<size_t>{0, 0, 1}) && bt[0].u == (std::vector<size_t>{2, 2, 2}));
+    }
+    // ---- saveIndex / loadIndex (fmindex/diskStorage.h:13-27) + hit limit through the shim ---------------------------------------
+    {
+        auto path = std::filesystem::temp_directory_path() / ("fmb200_shim_test_" + std::to_string(::getpid()) + ".fmb");
+        fmb200::saveIndex(index, path);
+        auto loaded = fmb200::loadIndex<fmb200::BiFMIndex<5>>(path);
+        CHECK(loaded.size() == index.size());
+        CHECK(loaded.C == index.C);
+        std::vector<std::array<uint64_t, 3>> a, b;
+        fmb200::search_no_errors::search(index, queries, [&](size_t q, auto const& c) { a.push_back({q, c.lb, c.len}); });
+        fmb200::search_no_errors::search(loaded, queries, [&](size_t q, auto const& c) { b.push_back({q, c.lb, c.len}); });
+        std::sort(a.begin(), a.end());
+        std::sort(b.begin(), b.end());
+        CHECK(a == b && !a.empty());
+        bool refused = false;
+        try { (void)fmb200::loadIndex<fmb200::FMIndex<5>>(path); } catch (std::runtime_error const&) { refused = true; }
+        CHECK(refused);                                          // a BiFMIndex file is not an FMIndex
+        std::filesystem::remove(path);
+        // search_n: the oracle's list, in order
+        for (size_t n : {1, 2, 5}) {
+            auto [scheme, partition] = ss::facadeScheme<true>(2, 40);
+            auto fs = fmb200::detail::flatten(scheme, partition);
+            std::vector<std::array<uint64_t, 6>> got;
+            fmb200::search_n<true>(index, queries, 2, n, [&](size_t q, auto const& c, size_t e) { got.push_back({q, c.lb, c.lbRev, c.len, c.steps, e}); });
+            fmo_hit* h{};
+            uint64_t cnt = fmo_search_ng26(o, flat.symbols.data(), flat.offsets.data(), queries.size(), 1, fs.n_searches, fs.n_parts, fs.pi.data(), fs.l.data(), fs.u.data(),
+                                           fs.partition.data(), n, &h, nullptr);
+            std::vector<std::array<uint64_t, 6>> exp;
+            for (uint64_t i = 0; i < cnt; ++i) exp.push_back({h[i].qidx, h[i].lb, h[i].lb_rev, h[i].len, h[i].steps, h[i].e});
+            CHECK(got == exp);
+            fmo_free(h);
+        }
     }
     // ---- multi-GPU host logic: replicas + contiguous shards (every visible device) -------------------------------------------
     {

@@ -41,7 +41,7 @@ SYMBOLS = [
     "fmb_index_create", "fmb_index_build", "fmb_index_destroy", "fmb_index_get_info", "fmb_index_get_C", "fmb_index_export",
     "fmb_string_symbol", "fmb_string_rank", "fmb_string_prefix_rank", "fmb_string_all_ranks",
     "fmb_cursor_extend", "fmb_cursor_extend_all",
-    "fmb_queries_upload", "fmb_queries_destroy", "fmb_queries_count",
+    "fmb_queries_upload", "fmb_queries_upload_revcomp", "fmb_queries_destroy", "fmb_queries_count",
     "fmb_search_exact", "fmb_search_scheme", "fmb_search_scheme_n", "fmb_search_backtracking", "fmb_locate", "fmb_locate_rows", "fmb_sample_value",
     "fmb_results_count", "fmb_results_kind", "fmb_results_fetch_hits", "fmb_results_fetch_locs", "fmb_results_fetch_locs32",
     "fmb_results_get_stats", "fmb_results_destroy",
@@ -229,8 +229,10 @@ class Index:
         return out
 
     # searches
-    def upload(self, symbols, offsets):
-        return Queries(self, symbols, offsets)
+    def upload(self, symbols, offsets, complement=None):
+        """complement: table of sigma symbols (DNA: [0, 4, 3, 2, 1]) -> the device batch holds every query followed by its reverse
+        complement (2 nq queries, example/utils.h:62-74), built on the device"""
+        return Queries(self, symbols, offsets, complement)
 
     def search_exact(self, queries):
         r = C.c_void_p()
@@ -301,10 +303,14 @@ class Index:
 
 
 class Queries:
-    def __init__(self, index, symbols, offsets):
+    def __init__(self, index, symbols, offsets, complement=None):
         symbols, offsets = _u8(symbols), _u64(offsets)
         self.h = C.c_void_p()
-        _check(lib().fmb_queries_upload(C.byref(self.h), index.h, _ptr(symbols), _ptr(offsets), C.c_uint64(offsets.size - 1)))
+        if complement is None:
+            _check(lib().fmb_queries_upload(C.byref(self.h), index.h, _ptr(symbols), _ptr(offsets), C.c_uint64(offsets.size - 1)))
+        else:
+            comp = _u8(complement)
+            _check(lib().fmb_queries_upload_revcomp(C.byref(self.h), index.h, _ptr(symbols), _ptr(offsets), C.c_uint64(offsets.size - 1), _ptr(comp)))
 
     def __len__(self):
         return lib().fmb_queries_count(self.h)

@@ -498,6 +498,29 @@ __global__ void rebase_offsets_kernel(uint64_t* __restrict__ off, uint64_t count
     if (i < count) off[i] -= base;
 }
 
+// Reverse-complement doubling of a query batch on the device (the example's loadQueries pushes every read followed by its reverse
+// complement, example/utils.h:62-74): query i of the uploaded batch becomes query 2i (unchanged) and query 2i+1 (reversed, every
+// symbol mapped through `comp`).  One warp per uploaded query; offsets are relative to the first symbol of the batch.
+struct ComplementTable { uint8_t map[32]; };
+__global__ void __launch_bounds__(256) revcomp_double_kernel(const uint8_t* __restrict__ fwd, const uint64_t* __restrict__ foff, uint64_t nq,
+                                                             const __grid_constant__ ComplementTable comp, uint8_t* __restrict__ out,
+                                                             uint64_t* __restrict__ ooff) {
+    const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (w >= nq) return;
+    const uint64_t b = foff[w], e = foff[w + 1], L = e - b;
+    if (lane == 0) {
+        ooff[2 * w] = 2 * b;
+        ooff[2 * w + 1] = 2 * b + L;
+        if (w + 1 == nq) ooff[2 * nq] = 2 * e;
+    }
+    for (uint64_t j = lane; j < L; j += 32) {
+        const uint8_t c = fwd[b + j];
+        out[2 * b + j] = c;
+        out[2 * b + L + (L - 1 - j)] = c < 32 ? comp.map[c] : c;
+    }
+}
+
 // bidirectional k-mer table (fmb_scheme.cuh JumpView::bikmer): k extendRight steps per pattern, with the work the
 // reference's error-free loop spends on them
 __global__ void __launch_bounds__(256) bikmer_table_kernel(const __grid_constant__ IndexView<OccDna> ix, uint32_t k, uint64_t count, uint4* __restrict__ out) {

@@ -802,24 +802,33 @@ int fmb_cursor_extend_all(const fmb_index* ix, int right, const uint64_t* cur, u
 }
 
 // ---- queries ------------------------------------------------------------------------------------------------
-int fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq) {
+// complement == nullptr: the batch as given; else reverse-complement doubling on the device (2 nq queries, only nq cross PCIe)
+static int upload_queries(fmb_queries** out, const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq, const uint8_t* complement) {
     if (!out || !ix || !offsets) { set_error("NULL argument"); return FMB_EINVAL; }
     *out = nullptr;
-    if (nq >= 0xFFFFFFFFull) { set_error("too many queries in one batch"); return FMB_EUNSUPPORTED; }
+    const uint64_t mult = complement ? 2 : 1;
+    if (nq * mult >= 0xFFFFFFFFull) { set_error("too many queries in one batch"); return FMB_EUNSUPPORTED; }
     FMB_TRY(use_device(ix->device));
-    uint64_t total = offsets[nq] - offsets[0];
-    if (total && !symbols) { set_error("symbols is NULL"); return FMB_EINVAL; }
+    if (offsets[nq] < offsets[0]) { set_error("offsets not monotone"); return FMB_EINVAL; }
+    const uint64_t in_total = offsets[nq] - offsets[0];
+    if (in_total && !symbols) { set_error("symbols is NULL"); return FMB_EINVAL; }
+    const uint64_t total = in_total * mult, nq_out = nq * mult;
     auto q = new fmb_queries();
     q->device = ix->device;
-    q->nq = nq;
+    q->nq = nq_out;
     q->total_symbols = total;
-    if (offsets[nq] < offsets[0]) { set_error("offsets not monotone"); delete q; return FMB_EINVAL; }
     cudaStream_t st = active_stream(ix);
+    DevBuf<uint8_t> stage_sym;
+    DevBuf<uint64_t> stage_off;
     int rc = q->symbols.alloc(total + 32);
-    if (!rc) rc = q->offsets.alloc(nq + 1);
+    if (!rc) rc = q->offsets.alloc(nq_out + 1);
+    if (!rc && complement) rc = stage_sym.alloc(in_total);
+    if (!rc && complement) rc = stage_off.alloc(nq + 1);
     if (rc) { delete q; return rc; }
+    uint8_t* sym_dst = complement ? stage_sym.p : q->symbols.p;
+    uint64_t* off_dst = complement ? stage_off.p : q->offsets.p;
     cudaError_t e = cudaSuccess;
-    if (total) e = cudaMemcpyAsync(q->symbols.p, symbols + offsets[0], total, cudaMemcpyHostToDevice, st);
+    if (in_total) e = cudaMemcpyAsync(sym_dst, symbols + offsets[0], in_total, cudaMemcpyHostToDevice, st);
     // validate the offsets while the symbols are in flight
     uint32_t mx = 0, mn = 0xFFFFFFFFu;
     for (uint64_t i = 0; i < nq; ++i) {
@@ -836,23 +845,34 @@ int fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* sy
     q->max_len = mx;
     q->min_len = nq ? mn : 0;
     if (e == cudaSuccess) e = cudaMemsetAsync(q->symbols.p + total, 0xFF, 32, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(q->offsets.p, offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(off_dst, offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && offsets[0] != 0) {
         // a slice of a larger batch: make the offsets relative to the first symbol of the slice, on the device
-        rebase_offsets_kernel<<<grid_for(nq + 1, 256), 256, 0, st>>>(q->offsets.p, nq + 1, offsets[0]);
+        rebase_offsets_kernel<<<grid_for(nq + 1, 256), 256, 0, st>>>(off_dst, nq + 1, offsets[0]);
         e = cudaGetLastError();
         note_launches(1);
+    }
+    if (e == cudaSuccess && complement) {
+        ComplementTable ct;
+        for (uint32_t c = 0; c < 32; ++c) ct.map[c] = c < ix->sigma ? complement[c] : (uint8_t)c;
+        if (nq) {
+            revcomp_double_kernel<<<grid_for(nq * 32, 256), 256, 0, st>>>(stage_sym.p, stage_off.p, nq, ct, q->symbols.p, q->offsets.p);
+            e = cudaGetLastError();
+            note_launches(1);
+        } else {
+            e = cudaMemsetAsync(q->offsets.p, 0, 8, st);
+        }
     }
     if (e == cudaSuccess && ix->dna) {
         // 2-bit packed copy for the two-symbol / jump kernels
         const uint64_t words = (total + 15) / 16;
         rc = q->packed.alloc(words + 2);
-        if (!rc) rc = q->flags.alloc(nq + 1);
-        if (rc) { delete q; return rc; }
-        e = cudaMemsetAsync(q->flags.p, 0, nq + 1, st);
+        if (!rc) rc = q->flags.alloc(nq_out + 1);
+        if (rc) { cudaStreamSynchronize(st); delete q; return rc; }
+        e = cudaMemsetAsync(q->flags.p, 0, nq_out + 1, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(q->packed.p + words, 0, 2 * sizeof(uint32_t), st);
         if (e == cudaSuccess && words) {
-            pack_queries_kernel<<<grid_for(words, 256), 256, 0, st>>>(q->symbols.p, total, q->offsets.p, nq, ix->sigma, q->packed.p, words, q->flags.p);
+            pack_queries_kernel<<<grid_for(words, 256), 256, 0, st>>>(q->symbols.p, total, q->offsets.p, nq_out, ix->sigma, q->packed.p, words, q->flags.p);
             e = cudaGetLastError();
             note_launches(1);
         }
@@ -861,6 +881,13 @@ int fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* sy
     if (e != cudaSuccess) { set_error("query upload: %s", cudaGetErrorString(e)); delete q; return FMB_ECUDA; }
     *out = q;
     return FMB_OK;
+}
+int fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq) {
+    return upload_queries(out, ix, symbols, offsets, nq, nullptr);
+}
+int fmb_queries_upload_revcomp(fmb_queries** out, const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq, const uint8_t* complement) {
+    if (!complement) { set_error("NULL complement table"); return FMB_EINVAL; }
+    return upload_queries(out, ix, symbols, offsets, nq, complement);
 }
 void fmb_queries_destroy(fmb_queries* q) {
     if (!q) return;

@@ -150,6 +150,11 @@ int fmb_cursor_extend_all(const fmb_index* ix, int right, const uint64_t* cur, u
 /* `Sequences queries` of the reference (concepts.h:12-24), flattened: symbols of all queries back to back and
  * offsets[nq+1].  Host pointers (pinned memory is copied faster).  The batch is bound to the device of `ix`. */
 int  fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq);
+/* Reverse-complement doubling (the example's loadQueries with reverse = true, example/utils.h:62-74; main.cpp:71): the device
+ * batch holds 2 nq queries -- uploaded query i as query 2i and its reverse complement (reversed, every symbol c < sigma
+ * replaced by complement[c]; DNA: {0,4,3,2,1}) as query 2i+1 -- but only the nq forward reads cross PCIe. */
+int  fmb_queries_upload_revcomp(fmb_queries** out, const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq,
+                                const uint8_t* complement /* sigma entries */);
 void fmb_queries_destroy(fmb_queries* q);
 uint64_t fmb_queries_count(const fmb_queries* q);
 

@@ -5,3 +5,4 @@
 #include "multi.hpp"
 #include "search.hpp"
 #include "search_scheme.hpp"
+#include "io.hpp"

@@ -93,3 +93,45 @@ def test_dropin_against_reference_headers(gpu):
     r = subprocess.run([path], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 failed" in r.stdout
+
+
+def test_fasta_front_end(tmp_path):
+    """include/fmb200/io.hpp: loadQueries / reverse-complement doubling / result writer (example/utils.h:26-105, main.cpp:260-266)"""
+    fa = tmp_path / "reads.fa"
+    fa.write_text(">r0 first\nACGT\nTTA\n> r1\nacgtn$\n>r2\n\n>r3\nGGC")          # multi-line record, lower case, empty record, no final newline
+    src = tmp_path / "io.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include "fmb200/fmb200.hpp"
+#include "fmb200/io.hpp"
+int main(int argc, char** argv) {
+    auto [q, info] = fmb200::io::loadQueries<6>(argv[1], true, false);
+    for (size_t i = 0; i < q.size(); ++i) {
+        std::printf("%s|%d|", info[i].name.c_str(), int(info[i].reverse));
+        for (auto c : q[i]) std::printf("%d", int(c));
+        std::printf("\n");
+    }
+    auto [q5, i5] = fmb200::io::loadQueries<5>(argv[1], false, true);               // N -> 1 for Sigma == 5
+    for (auto c : q5[1]) std::printf("%d", int(c));
+    std::printf("\n");
+    bool threw = false;
+    try { fmb200::io::loadQueries<5>(argv[1], false, false); } catch (std::runtime_error const&) { threw = true; }
+    std::printf("threw=%d missing=%zu\n", int(threw), std::get<0>(fmb200::io::loadQueries<5>("/nonexistent.fa", true, true)).size());
+    std::vector<std::tuple<size_t, size_t, size_t, size_t>> res{{3, 0, 17, 1}, {4, 1, 2, 0}};
+    fmb200::io::saveResults(argv[2], res);
+    std::vector<fmb_loc32> res2{{7, 1, 99, 2}};
+    fmb200::io::saveResults(std::string(argv[2]) + "2", res2);
+}
+''')
+    exe = tmp_path / "io"
+    lib = os.path.join(ROOT, "fmindex-collection_b200")
+    import fmb200  # noqa: F401
+    from fmb200 import build as b
+    b.build()
+    subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", "-Wno-comment", "-I", os.path.join(ROOT, "include"), str(src), "-L", lib, "-lfmb200",
+                    f"-Wl,-rpath,{lib}", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe), str(fa), str(tmp_path / "out.txt")], check=True, capture_output=True, text=True).stdout.splitlines()
+    assert out == ["r0 first|0|1234441", "r0 first|1|4111234", "r1|0|123450", "r1|1|051234", "r2|0|", "r2|1|", "r3|0|332", "r3|1|322",
+                   "123410", "threw=1 missing=0"]
+    assert (tmp_path / "out.txt").read_text() == "3 0 17\n4 1 2\n"
+    assert (tmp_path / "out.txt2").read_text() == "7 1 99\n"

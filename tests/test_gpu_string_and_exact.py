@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from helpers import hits_equal, locs_equal, make_index_pair
+from helpers import hits_equal, locs_equal, make_index_pair, strip_lb_rev
 
 pytestmark = pytest.mark.gpu
 
@@ -220,3 +220,44 @@ def test_locate_modes_and_irregular_sampling(gpu):
     assert locs_equal(g2.locate(res2).locs(), exp2)
     # (with SA-space sampling a walk may cross a delimiter, where the reference's pos + steps arithmetic leaves the sequence: the
     #  device reproduces the reference, the positions are not comparable with the text-order sampling above)
+
+
+def test_reverse_complement_doubling_on_the_device(gpu):
+    """fmb_queries_upload_revcomp: the device batch = every read followed by its reverse complement (example/utils.h:62-74),
+    compared with the same doubling done on the host; ragged lengths, an empty read, a read holding a delimiter"""
+    from fmb200 import schemes, synth
+    text = synth.multi_text([5000, 800], 5, 13)
+    o, g = make_index_pair(gpu, text, 5, 4)
+    comp = np.array([0, 4, 3, 2, 1], dtype=np.uint8)
+    rng = np.random.default_rng(5)
+    reads = []
+    for i in range(400):
+        L = int(rng.integers(1, 60)) if i % 50 else 0
+        p = int(rng.integers(0, 5000 - 60))
+        r = text[p:p + L].copy()
+        if i % 3 == 0 and L:
+            r = comp[r[::-1]]                     # a read from the other strand: its reverse complement is the one that matches
+        reads.append(r)
+    reads[7] = np.array([1, 2, 0, 3, 4, 4, 1], dtype=np.uint8)
+    doubled = []
+    for r in reads:
+        doubled += [r, comp[r[::-1]]]
+    sym, off = synth.flatten(reads)
+    dsym, doff = synth.flatten(doubled)
+    q = g.upload(sym, off, complement=comp)
+    assert len(q) == 2 * len(reads)
+    exp = o.search_exact(dsym, doff)
+    got = g.search_exact(q).hits()
+    assert hits_equal(strip_lb_rev(got), strip_lb_rev(exp)) and len(exp) > 400
+    assert hits_equal(strip_lb_rev(g.search_exact(g.upload(dsym, doff)).hits()), strip_lb_rev(exp))
+    # equal-length batch through a scheme search
+    eq = [text[p:p + 30].copy() for p in rng.integers(0, 4900, 100)]
+    eq = [comp[r[::-1]] if i % 2 else r for i, r in enumerate(eq)]
+    eq = list(synth.plant_errors(np.array(eq, dtype=np.uint8), 5, 1, True, 3))
+    d2 = []
+    for r in eq:
+        d2 += [r, comp[r[::-1]]]
+    sch = schemes.optimum(0, 1)
+    part = schemes.uniform_partition(2, 30)
+    es, eo = synth.flatten(d2)
+    assert hits_equal(g.search_scheme(g.upload(*synth.flatten(eq), complement=comp), sch, part, True).hits(), o.search_ng26(es, eo, sch, part, True))

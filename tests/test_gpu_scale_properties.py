@@ -115,6 +115,40 @@ def test_reads_with_planted_errors_are_found(big, k, edit):
     assert 0 < st.line_requests < st.occ_lookups
 
 
+@pytest.mark.parametrize("k,edit", [(1, False), (2, True)])
+def test_hit_limit_properties_at_scale(big, k, edit):
+    """search_n at 10^6 reads: the limited lists nest (the list for n is a prefix, per query, of the list for a larger n, the last
+    cursor possibly clipped), every query with a hit keeps one, no query exceeds n rows, and the unlimited search reports the
+    same multiset as the ordered one with n = infinity"""
+    from fmb200 import schemes
+    gpu, capi, index, d_text = big
+    sym, off = _reads(capi, d_text, "err", k, edit)
+    q = index.upload(sym, off)
+    sch = schemes.optimum(0, k)
+    part = schemes.uniform_partition(sch[0].shape[1], L)
+    full = index.search_scheme(q, sch, part, edit).hits()
+    order = ["qidx", "e", "lb", "len", "steps", "lb_rev"]
+    big_n = index.search_scheme(q, sch, part, edit, n=10**12).hits()
+    assert np.array_equal(np.sort(full, order=order), np.sort(big_n, order=order))
+    assert np.all(np.diff(big_n["qidx"].astype(np.int64)) >= 0)                   # grouped by ascending qidx
+    prev = big_n
+    for n in (3, 1):
+        lim = index.search_scheme(q, sch, part, edit, n=n).hits()
+        rows = np.bincount(lim["qidx"].astype(np.int64), weights=lim["len"].astype(np.float64), minlength=NQ)
+        rows_full = np.bincount(full["qidx"].astype(np.int64), weights=full["len"].astype(np.float64), minlength=NQ)
+        assert np.array_equal(rows, np.minimum(rows_full, n))                      # exactly min(n, all rows) rows per query
+        # prefix property: the j-th hit of a query in `lim` is the j-th hit of that query in `prev` (len possibly clipped)
+        def rank_in_query(h):
+            first = np.searchsorted(h["qidx"], h["qidx"], side="left")
+            return np.arange(len(h)) - first
+        pos_prev = np.searchsorted(prev["qidx"], lim["qidx"], side="left") + rank_in_query(lim)
+        same = prev[pos_prev]
+        for f in ("qidx", "lb", "lb_rev", "steps", "e"):
+            assert np.array_equal(lim[f], same[f]), (n, f)
+        assert np.all(lim["len"] <= same["len"])
+        prev = lim
+
+
 def test_locate_refuses_more_than_2_32_rows(big):
     """300 one-symbol queries cover ~4.8 G rows of the 64 Mbp index: locate must fail loudly, not wrap around"""
     gpu, capi, index, _ = big

@@ -131,3 +131,16 @@ def test_search_n_refuses_keys_that_do_not_fit(pair):
 def gpu_error():
     import fmb200
     return fmb200.FmbError
+
+
+def test_search_n_with_spilled_frontier(gpu):
+    """a 40-item stack per warp (FMB_SCHEME_CAP, read once per process) makes the frontier spill to the global overflow list, whose
+    items carry their keys to the next launch: the repetitive-text cases again, in a fresh process"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FMB_SCHEME_CAP="40")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_search_n.py"), "-q", "-x", "-k", "repetitive or random_text"],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -22,6 +22,7 @@ int compute_C(fmb_index* ix);
 int build_occ2(fmb_index* ix, int dir);
 int build_locblocks(fmb_index* ix);
 int build_jump(fmb_index* ix, int dir);
+int widen_jump0(fmb_index* ix);
 int build_bikmer(fmb_index* ix);
 int new_index(fmb_index** out, int device, uint32_t sigma, uint64_t n, bool bidirectional);
 
@@ -393,6 +394,7 @@ extern "C" int fmb_index_build(fmb_index** out, int device, uint32_t sigma, cons
     if (ix->dna) FMB_TRY(build_occ2(ix, 0));
     if (!ix->dna) FMB_TRY(build_jump(ix, 0));
     if (bidirectional) FMB_TRY(build_jump(ix, 1));
+    FMB_TRY(widen_jump0(ix));
     FMB_TRY(build_bikmer(ix));
     FMB_TRY(build_locblocks(ix));
     guard.ix = nullptr;

@@ -154,6 +154,9 @@ struct Occ2View {
     // single row, 16 backward steps are one 8-byte lookup: compare the 32-bit symbol word with the query, follow .x.
     const uint2* jump;
     const uint2* jump4;          // the same with LF^4 and four symbols (8 bits): tails shorter than 16 symbols
+    // jump_wide != 0: `jump` holds 16-byte entries {LF^16(row), symbols 1..16, LF^32(row), symbols 17..32} -- one lookup serves a
+    // 16- or a 32-symbol jump (.z = 0xFFFFFFFF when one of symbols 17..32 is a delimiter)
+    uint32_t jump_wide;
 };
 constexpr uint32_t kJumpInvalid = 0xFFFFFFFFu;
 

@@ -105,6 +105,7 @@ struct fmb_index {
     uint32_t special01[2][2] = {{0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu}};
     uint32_t C2[2][16] = {};
     fmb::DevBuf<uint2> jump[2];          // LF^16 jump tables
+    uint32_t jump_shift[2] = {0, 0};     // 1: the table holds 16-byte entries {LF^16, 16 symbols, LF^32, 16 more symbols} (two uint2 per row)
     fmb::DevBuf<uint2> jump4[2];         // LF^4 jump tables (same entry format, 4 symbols in the low 8 bits)
     fmb::DevBuf<uint2> kmer;             // k-mer interval table of direction 0
     uint32_t kmer_k = 0;

@@ -599,6 +599,16 @@ __global__ void __launch_bounds__(256) jump_double_kernel(const uint2* __restric
     out[i] = r;
 }
 
+// merged LF^16 / LF^32 table: out[row] = {J16[row], J16[J16[row].x]} (16 bytes per row)
+__global__ void __launch_bounds__(256) jump_widen_kernel(const uint2* __restrict__ in, uint4* __restrict__ out, uint64_t n) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 a = in[i];
+    uint2 b = make_uint2(kJumpInvalid, 0);
+    if (a.x != kJumpInvalid) b = __ldg(in + a.x);
+    out[i] = make_uint4(a.x, a.y, b.x, b.y);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K2b: exact backward search with two-symbol steps.  A group of 4 lanes owns one query: every lane fetches one
 // 32-byte quarter of the 128-byte line (ONE request per line for the memory system), computes its share of the
@@ -655,11 +665,25 @@ __global__ void __launch_bounds__(256, MINB) exact_search2_kernel(const __grid_c
             }
             while (pos > 0 && len > 0) {
                 if (len == 1 && pos >= 16 && o2.jump) {
-                    // single-row interval: 16 symbols per lookup through the LF^16 jump table
-                    uint2 e = __ldg(o2.jump + lb);
+                    // single-row interval: 16 symbols per lookup through the LF^16 jump table -- or 32 when the table holds the merged
+                    // 16-byte entries and the next 32 symbols stay inside one sequence
+                    uint2 e, f = make_uint2(kJumpInvalid, 0);
+                    if (o2.jump_wide) {
+                        const uint4 w = __ldg(reinterpret_cast<const uint4*>(o2.jump) + lb);
+                        e = make_uint2(w.x, w.y);
+                        f = make_uint2(w.z, w.w);
+                    } else {
+                        e = __ldg(o2.jump + lb);
+                    }
                     lines += 1;
                     if (e.x != kJumpInvalid) {
                         if (e.y != field(pos - 16, 32)) { len = 0; break; }
+                        if (pos >= 32 && f.x != kJumpInvalid) {
+                            if (f.y != field(pos - 32, 32)) { len = 0; break; }
+                            lb = f.x;
+                            pos -= 32;
+                            continue;
+                        }
                         lb = e.x;
                         pos -= 16;
                         continue;

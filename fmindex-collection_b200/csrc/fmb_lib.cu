@@ -42,13 +42,15 @@ Pool& pool() {
     static Pool* p = new Pool();     // intentionally leaked: must outlive static destructors that free buffers
     return *p;
 }
+constexpr size_t kMaxCachedBlock = size_t(1) << 34;      // blocks above 16 GB go straight back to CUDA
 size_t size_class(size_t bytes) {
     if (bytes <= 4096) return 4096;
+    // blocks that are never cached need no size class: 2 MB granularity instead of up to 12.5 % slack (3 GB per 24 GB jump table)
+    if (bytes > kMaxCachedBlock) return (bytes + (size_t(2) << 20) - 1) / (size_t(2) << 20) * (size_t(2) << 20);
     int top = 63 - __builtin_clzll((unsigned long long)bytes);
     size_t step = size_t(1) << (top - 3);
     return (bytes + step - 1) / step * step;
 }
-constexpr size_t kMaxCachedBlock = size_t(1) << 34;      // blocks above 16 GB go straight back to CUDA
 constexpr size_t kMaxCachedTotal = size_t(40) << 30;     // ... and so does anything that would push the cache above 40 GB
 }  // namespace
 
@@ -228,6 +230,7 @@ fmb::Occ2View fmb_index::view_occ2(int dir) const {
     v.s1 = special01[dir][1];
     for (int i = 0; i < 16; ++i) v.C2[i] = C2[dir][i];
     v.jump = jump[dir].p;
+    v.jump_wide = jump_shift[dir];
     v.jump4 = jump4[dir].p;
     v.kmer = dir == 0 ? kmer.p : nullptr;
     v.kmer_k = dir == 0 ? kmer_k : 0;
@@ -254,6 +257,7 @@ uint64_t fmb_index::device_bytes() const {
 namespace fmb {
 
 int build_jump(fmb_index* ix, int dir);
+int widen_jump0(fmb_index* ix);
 
 // Builds occ table `dir` of `ix` from n BWT bytes at d_bwt (device).  Fails when a symbol is >= sigma.
 int build_occ_from_device_bwt(fmb_index* ix, int dir, const uint8_t* d_bwt) {
@@ -533,6 +537,31 @@ int build_jump(fmb_index* ix, int dir) {
     return FMB_OK;
 }
 
+// Merged LF^16 / LF^32 table of direction 0 (16 bytes per row instead of 8): exact search then covers 32 symbols of a single-row
+// interval per lookup.  Built after both LF^16 tables exist; skipped (the 8-byte table stays) when the device cannot hold the wide
+// copy next to the narrow one plus what the remaining tables need, or when FMB_NO_JUMP32 is set.
+int widen_jump0(fmb_index* ix) {
+    if (!ix->dna || !ix->jump[0].p || ix->jump_shift[0] || getenv("FMB_NO_JUMP32")) return FMB_OK;
+    const uint64_t n = ix->n;
+    size_t free_b = 0, total_b = 0;
+    pool_trim();
+    FMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    // the wide table (16 n) next to the narrow one; the 8 n released afterwards cover the tables still to come (locate shortcut 4 n,
+    // locate blocks n, marks, samples, bidirectional k-mer table)
+    if ((double)free_b < 16.0 * (double)n * 1.125 + (double)(size_t(2) << 30)) return FMB_OK;
+    cudaStream_t st = active_stream(ix);
+    DevBuf<uint2> wide;
+    FMB_TRY(wide.alloc(2 * n));
+    jump_widen_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->jump[0].p, reinterpret_cast<uint4*>(wide.p), n);
+    FMB_CUDA(cudaGetLastError());
+    FMB_CUDA(cudaStreamSynchronize(st));
+    note_launches(1);
+    ix->jump[0] = std::move(wide);
+    ix->jump_shift[0] = 1;
+    pool_trim();
+    return FMB_OK;
+}
+
 // sample tables from a device bitmap ((n+63)/64 words; rows >= n clear) and device sample arrays
 int build_marks_from_device(fmb_index* ix, const uint64_t* d_bitmap, const uint32_t* d_seq, const uint32_t* d_pos, uint64_t n_samples) {
     const uint64_t words = ix->n / 64 + 1;
@@ -633,6 +662,8 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, co
     if (rc) return fail(rc);
     if (ix->bidirectional) rc = build_jump(ix, 1);
     if (rc) return fail(rc);
+    rc = widen_jump0(ix);
+    if (rc) return fail(rc);
     rc = build_bikmer(ix);
     if (rc) return fail(rc);
     {
@@ -679,7 +710,7 @@ int fmb_index_get_info(const fmb_index* ix, fmb_index_info* info) {
     info->device = ix->device;
     info->tables = (ix->occ2[0].p ? FMB_TABLE_PAIR : 0) | (ix->kmer.p ? FMB_TABLE_KMER : 0) | (ix->jump[0].p ? FMB_TABLE_JUMP : 0) |
                    (ix->jump[1].p ? FMB_TABLE_JUMP_REV : 0) | (ix->locblocks.p ? FMB_TABLE_LOCBLOCK : 0) | (ix->locrow.p ? FMB_TABLE_LOCROW : 0) |
-                   (ix->bikmer.p ? FMB_TABLE_BIKMER : 0) | (ix->jump4[0].p ? FMB_TABLE_JUMP4 : 0);
+                   (ix->bikmer.p ? FMB_TABLE_BIKMER : 0) | (ix->jump4[0].p ? FMB_TABLE_JUMP4 : 0) | (ix->jump_shift[0] ? FMB_TABLE_JUMP32 : 0);
     return FMB_OK;
 }
 

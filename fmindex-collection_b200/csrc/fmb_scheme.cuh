@@ -162,6 +162,7 @@ __device__ __forceinline__ void child_cursor(const IndexView<OCC>& ix, const OCC
 struct JumpView {
     const uint2* jump[2];         // [0]: farthest symbol in the low bits, [1]: nearest symbol in the low bits (= query order)
     const uint2* jump4[2];        // LF^4 tables, same orientation, four symbols in the low 8 bits
+    uint32_t jshift[2];           // 1: jump[d] holds 16-byte merged LF^16 / LF^32 entries, the LF^16 part first (row r at jump[d] + 2 r)
     const uint32_t* qpk;          // packed query symbols
     const uint8_t* qflags;        // 1 = query not packable
     // bidirectional k-mer table: entry (2-bit packed k-mer, first symbol in the low bits) = {lb, lbRev, len, work} of the
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         else if (jv.jump4[R] != nullptr && (noerr ? st.pev >= 4 : (ham && st.pev > 4))) J = 4;
                     }
                     if (J) {
-                        const uint2 e = __ldg((J == 16 ? jv.jump[R] : jv.jump4[R]) + lo);
+                        const uint2 e = __ldg(J == 16 ? jv.jump[R] + ((size_t)lo << jv.jshift[R]) : jv.jump4[R] + lo);
                         n_phys += 1;
                         if (e.x != kJumpInvalid) {
                             jumped = true;
@@ -723,7 +724,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                                 const unsigned long long err_children = cmask & ~(CH_MATCH | CH_JUMP);
                                 const uint2* sim_table = OCC::kSymbolLoad ? jv.jump4[R] : jv.jump[R];
                                 if (EDIT && err_children && sim_table != nullptr && single_sym >= first_symb && (sim_all || st.e + 1 == up)) {
-                                    const uint2 je = __ldg(sim_table + lo);
+                                    const uint2 je = __ldg(sim_table + (OCC::kSymbolLoad ? (size_t)lo : ((size_t)lo << jv.jshift[R])));
                                     n_phys += 1;
                                     if (je.x != kJumpInvalid) {
                                         // window in walking order, w[0] (= this row's symbol) in the low bits

@@ -66,6 +66,8 @@ int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const Schem
     if (ix->dna && q->packed.p && !no_jump) {
         jv.jump[0] = ix->jump[0].p;
         jv.jump[1] = ix->jump[1].p;
+        jv.jshift[0] = ix->jump_shift[0];
+        jv.jshift[1] = ix->jump_shift[1];
         jv.jump4[0] = ix->jump4[0].p;
         jv.jump4[1] = ix->jump4[1].p;
         jv.qpk = q->packed.p;

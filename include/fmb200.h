@@ -74,6 +74,7 @@ typedef struct {
 #define FMB_TABLE_LOCROW   32u  /* locate shortcut table                           */
 #define FMB_TABLE_BIKMER   64u  /* bidirectional k-mer table for scheme roots      */
 #define FMB_TABLE_JUMP4    128u /* LF^4 jump tables (tails shorter than 16 symbols) */
+#define FMB_TABLE_JUMP32   256u /* direction 0 holds merged LF^16 / LF^32 entries (32 symbols per lookup in exact search) */
 
 /* work counters of the last search/locate call on a result set (device-side counting, optional) */
 typedef struct {

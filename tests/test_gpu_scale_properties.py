@@ -57,6 +57,20 @@ def _has_deletion(k):
 def test_tables_present(big):
     gpu, capi, index, _ = big
     assert index.info.tables & 0x7F == 0x7F          # pair, kmer, jump, jump_rev, locblock, locrow, bikmer
+    assert index.info.tables & 0x180 == 0x180        # LF^4 tables, merged LF^16 / LF^32 entries in direction 0
+
+
+def test_narrow_jump_table_gives_the_same_answers(gpu):
+    """FMB_NO_JUMP32 (read when an index is built) keeps the 8-byte LF^16 entries: the exact-search and scheme parity tests again
+    in a fresh process"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FMB_NO_JUMP32="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_string_and_exact.py"),
+                        os.path.join(root, "tests", "test_gpu_scheme_and_build.py"), "-q", "-x"], env=env, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_exact_reads_are_found_where_they_came_from(big):

@@ -21,7 +21,9 @@
 //         120  sections, back to back, in that order (little endian, u8 / u8 / u64 / u32 / u32 elements)
 #include <cstdio>
 #include <cstring>
+#include <filesystem>
 #include <memory>
+#include <new>
 #include <vector>
 
 #include "fmb_host.hpp"
@@ -71,7 +73,34 @@ extern "C" {
 
 uint64_t fmb_checksum64(const void* data, uint64_t bytes) { return checksum64(data, bytes); }
 
+static int save_impl(const fmb_index* ix, const char* path);
+static int load_impl(fmb_index** out, int device, const char* path);
+
+// no C++ exception may cross the C boundary: the host buffers of a 3 Gbp index are 8 GB
 int fmb_index_save(const fmb_index* ix, const char* path) {
+    try {
+        return save_impl(ix, path);
+    } catch (const std::bad_alloc&) {
+        set_error("fmb_index_save: out of host memory");
+        return FMB_ENOMEM;
+    } catch (const std::exception& e) {
+        set_error("fmb_index_save: %s", e.what());
+        return FMB_EINVAL;
+    }
+}
+int fmb_index_load(fmb_index** out, int device, const char* path) {
+    try {
+        return load_impl(out, device, path);
+    } catch (const std::bad_alloc&) {
+        set_error("fmb_index_load: out of host memory");
+        return FMB_ENOMEM;
+    } catch (const std::exception& e) {
+        set_error("fmb_index_load: %s", e.what());
+        return FMB_EINVAL;
+    }
+}
+
+static int save_impl(const fmb_index* ix, const char* path) {
     if (!ix || !path) { set_error("NULL argument"); return FMB_EINVAL; }
     const uint64_t n = ix->n, ns = ix->n_samples, words = (n + 63) / 64;
     std::vector<uint8_t> bwt(n), bwt_rev(ix->bidirectional ? n : 0);
@@ -97,7 +126,7 @@ int fmb_index_save(const fmb_index* ix, const char* path) {
     return FMB_OK;
 }
 
-int fmb_index_load(fmb_index** out, int device, const char* path) {
+static int load_impl(fmb_index** out, int device, const char* path) {
     if (!out || !path) { set_error("NULL argument"); return FMB_EINVAL; }
     *out = nullptr;
     File f(fopen(path, "rb"));
@@ -111,6 +140,14 @@ int fmb_index_load(fmb_index** out, int device, const char* path) {
     if (h.sigma < 2 || h.sigma > 32 || h.n == 0 || h.bidirectional > 1 || h.n_samples > h.n) { set_error("%s: implausible header (sigma %u, n %llu)", path, h.sigma, (unsigned long long)h.n); return FMB_EINVAL; }
     for (int s = 0; s < 5; ++s)
         if (h.bytes[s] != want[s]) { set_error("%s: section %d holds %llu bytes, the header implies %llu", path, s, (unsigned long long)h.bytes[s], (unsigned long long)want[s]); return FMB_EINVAL; }
+    {
+        // the sizes the header implies must be the size of the file: nothing is allocated for a header that lies
+        std::error_code ec;
+        const uint64_t have = (uint64_t)std::filesystem::file_size(path, ec);
+        uint64_t need = sizeof h;
+        for (int s = 0; s < 5; ++s) need += want[s];
+        if (!ec && have < need) { set_error("%s: truncated (%llu bytes, the header implies %llu)", path, (unsigned long long)have, (unsigned long long)need); return FMB_EINVAL; }
+    }
     std::vector<uint8_t> bwt(h.n), bwt_rev(h.bytes[1]);
     std::vector<uint64_t> bitmap(words);
     std::vector<uint32_t> seq(h.n_samples), pos(h.n_samples);

@@ -291,6 +291,27 @@ int main() {
             fmo_free(h);
         }
     }
+    // ---- io::uploadQueries(reverse = true): the device doubles the batch (read, reverse complement, read, ...) ------------------
+    {
+        std::vector<std::vector<uint8_t>> doubled;
+        for (auto const& q : queries) {
+            doubled.push_back(q);
+            doubled.push_back(fmb200::io::reverseComplement(q));
+        }
+        auto dev = fmb200::io::uploadQueries(index, queries, /*reverse*/ true);
+        CHECK(fmb_queries_count(dev.get()) == doubled.size());
+        fmb_results* r{};
+        fmb200::check(fmb_search_exact(index.handle(), dev.get(), &r));
+        fmb200::detail::ResultsHandle res{r};
+        auto got = fmb200::detail::fetch_hits(r);
+        auto exp = fmb200::search_no_errors::search_bulk(index, doubled);
+        fmb200::detail::sort_hits(got);
+        fmb200::detail::sort_hits(exp);
+        CHECK(got.size() == exp.size() && !got.empty());
+        bool same = got.size() == exp.size();
+        for (size_t i = 0; same && i < got.size(); ++i) same = got[i].qidx == exp[i].qidx && got[i].lb == exp[i].lb && got[i].len == exp[i].len;
+        CHECK(same);
+    }
     // ---- multi-GPU host logic: replicas + contiguous shards (every visible device) -------------------------------------------
     {
         CHECK(fmb200::shard_range(10, 0, 3) == (std::pair<size_t, size_t>{0, 4}));

@@ -79,6 +79,14 @@ def test_loader_rejects_damaged_files_before_touching_the_device(fmb, small, tmp
     assert "truncated" in str(load_error())
     open(p, "wb").write(data[:60])
     assert "truncated header" in str(load_error())
+    # a header that claims 2^60 rows: refused from the file size, nothing is allocated
+    head = bytearray(data[:120])
+    head[16:24] = struct.pack("<Q", 1 << 60)
+    head[40:48] = struct.pack("<Q", 1 << 60)
+    head[48:56] = struct.pack("<Q", 1 << 60)
+    head[56:64] = struct.pack("<Q", (((1 << 60) + 63) // 64) * 8)
+    open(p, "wb").write(bytes(head) + data[120:])
+    assert load_error().code == FMB_EINVAL and "truncated" in str(load_error())
     _write(p, 5, bwt, bwt_rev[:-1], bm, sq, sp)                     # bwtRev shorter than bwt
     assert "section 1" in str(load_error())
     # a well-formed file passes validation: without a device the call then fails with ENODEVICE (no CPU fallback), with one it loads

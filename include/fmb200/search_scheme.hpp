@@ -5,12 +5,13 @@
 //   search_scheme/Search.h:19-28     struct Search{pi, l, u}
 //   search_scheme/Scheme.h:13        using Scheme = std::vector<Search>
 //   search_scheme/generator/optimum.h:11-75, backtracking.h:15-22, h2.h:128-149
-//   search_scheme/expand.h:301-343   limitToHamming, createUniformPartition
+//   search_scheme/expand.h:37-180    expandCount, expand;  :301-343 limitToHamming, createUniformPartition;  isValid.h:55-93 isValid
 //   search/CachedSearchScheme.h:15-36,61-71   the scheme fmc::search<Edit>(index, queries, k, cb) selects
 // The generators are pinned against tables produced by the reference's own generators
 // (tests/golden/ref_vectors.json, tests/cpp/shim_test.cpp).
 #pragma once
 #include <algorithm>
+#include <optional>
 #include <cstddef>
 #include <stdexcept>
 #include <string>
@@ -52,6 +53,71 @@ inline std::vector<size_t> createUniformPartition(size_t parts, size_t totalSum)
 inline std::vector<size_t> createUniformPartition(Scheme const& ss, size_t totalSum) {
     if (ss.empty()) throw std::invalid_argument("createUniformPartition: empty scheme");
     return createUniformPartition(ss[0].pi.size(), totalSum);
+}
+
+// isValid.h:55-93: pi connected and covering 0, l and u non-decreasing, l <= u
+inline bool isValid(Search const& s) {
+    if (s.pi.empty() || s.pi.size() != s.u.size() || s.pi.size() != s.l.size()) return false;
+    size_t lo = s.pi.front(), hi = s.pi.front();
+    for (size_t i = 1; i < s.pi.size(); ++i) {
+        if (s.pi[i] == hi + 1) hi = s.pi[i];
+        else if (s.pi[i] + 1 == lo) lo = s.pi[i];
+        else return false;
+    }
+    if (lo != 0) return false;
+    for (size_t i = 1; i < s.pi.size(); ++i)
+        if (s.l[i - 1] > s.l[i] || s.u[i - 1] > s.u[i]) return false;
+    for (size_t i = 0; i < s.pi.size(); ++i)
+        if (s.l[i] > s.u[i]) return false;
+    return true;
+}
+inline bool isValid(Scheme const& ss) {
+    for (auto const& s : ss)
+        if (!isValid(s) || s.pi.size() != ss.front().pi.size()) return false;
+    return true;
+}
+
+// expand.h:37-48: `newLen` symbols spread over `oldLen` parts, the first newLen % oldLen parts one longer
+inline std::vector<size_t> expandCount(size_t oldLen, size_t newLen) {
+    if (oldLen == 0 || newLen == 0) throw std::invalid_argument("expandCount: empty scheme or query");
+    std::vector<size_t> counts(oldLen, newLen / oldLen);
+    for (size_t i = 0; i < newLen % oldLen; ++i) counts[i] += 1;
+    return counts;
+}
+// expand.h:146-180: one pi / l / u entry per query symbol (the input of search_pseudo).  A part is walked forwards when the next
+// part lies to its right (the first part: like the second one, :21-28); every symbol of a part carries the part's upper bound, the
+// last one its lower bound and the others the lower bound of the part before (:105-121).  Searches that are not valid afterwards
+// are dropped, as in the reference.
+inline std::optional<Search> expand(Search const& s, std::vector<size_t> const& counts) {
+    size_t const P = s.pi.size();
+    if (counts.size() != P) throw std::invalid_argument("expand: one count per part is needed");
+    std::vector<size_t> starts(P, 0);
+    for (size_t i = 1; i < P; ++i) starts[i] = starts[i - 1] + counts[i - 1];
+    Search r;
+    for (size_t i = 0; i < P; ++i) {
+        bool const forward = i == 0 ? (P == 1 || s.pi[1] > s.pi[0]) : s.pi[i] > s.pi[i - 1];
+        size_t const b = starts[s.pi[i]], c = counts[s.pi[i]];
+        for (size_t j = 0; j < c; ++j) r.pi.push_back(forward ? b + j : b + c - 1 - j);
+        for (size_t j = 0; j < c; ++j) r.u.push_back(s.u[i]);
+        for (size_t j = 0; j + 1 < c; ++j) r.l.push_back(i > 0 ? s.l[i - 1] : 0);
+        if (c > 0) r.l.push_back(s.l[i]);
+        else if (!r.l.empty()) r.l.back() = s.l[i];
+    }
+    if (!isValid(r)) return std::nullopt;
+    return r;
+}
+inline std::optional<Search> expand(Search const& s, size_t newLen) { return expand(s, expandCount(s.pi.size(), newLen)); }
+inline Scheme expand(Scheme const& ss, std::vector<size_t> const& counts) {
+    Scheme r;
+    for (auto const& s : ss)
+        if (auto o = expand(s, counts)) r.push_back(std::move(*o));
+    return r;
+}
+inline Scheme expand(Scheme const& ss, size_t newLen) {
+    Scheme r;
+    for (auto const& s : ss)
+        if (auto o = expand(s, newLen)) r.push_back(std::move(*o));
+    return r;
 }
 
 namespace generator {

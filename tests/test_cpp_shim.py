@@ -135,3 +135,75 @@ int main(int argc, char** argv) {
                    "123410", "threw=1 missing=0"]
     assert (tmp_path / "out.txt").read_text() == "3 0 17\n4 1 2\n"
     assert (tmp_path / "out.txt2").read_text() == "7 1 99\n"
+
+
+REF_SRC = "/root/reference/src"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_SRC, "fmindex-collection")), reason="needs the reference headers (this container only)")
+def test_expand_and_fold_against_the_reference_headers(tmp_path):
+    """search_scheme.hpp expand / isValid == the reference's (search_scheme/expand.h:146-180, isValid.h:55-93) for every generator
+    and many lengths, and search_pseudo's fold() of an expanded scheme re-expands to exactly the same per-symbol scheme -- i.e. the
+    part form handed to the device describes the same search (CPU only: no device call)."""
+    src = tmp_path / "e.cpp"
+    src.write_text(r'''
+#include <fmindex-collection/search_scheme/expand.h>
+#include <fmindex-collection/search_scheme/generator/all.h>
+#include <fmindex-collection/search_scheme/isValid.h>
+#include <cstdio>
+#include "fmb200/fmb200.hpp"
+namespace rs = fmc::search_scheme;
+namespace ms = fmb200::search_scheme;
+static ms::Scheme conv(rs::Scheme const& ss) { ms::Scheme r; for (auto const& s : ss) r.push_back(ms::Search{s.pi, s.l, s.u}); return r; }
+int main() {
+    int checks = 0, bad = 0;
+    std::vector<rs::Scheme> schemes;
+    for (size_t k = 0; k <= 3; ++k) {
+        if (k <= 2) schemes.push_back(rs::generator::optimum(0, k));
+        schemes.push_back(rs::generator::h2(k + 2, 0, k));
+        schemes.push_back(rs::generator::h2(k + 1, 0, k));
+        schemes.push_back(rs::generator::pigeon_opt(0, k));
+        schemes.push_back(rs::generator::backtracking(k + 1, 0, k));
+        schemes.push_back(rs::generator::suffixFilter(k + 1, 0, k));
+    }
+    for (auto const& ref : schemes) {
+        auto mine = conv(ref);
+        ++checks; if (ms::isValid(mine) != rs::isValid(ref)) ++bad;
+        for (size_t L : {ref[0].pi.size(), ref[0].pi.size() + 1, size_t{7}, size_t{20}, size_t{50}, size_t{151}}) {
+            if (L < ref[0].pi.size()) continue;
+            auto e_ref = rs::expand(ref, L);
+            auto e_mine = ms::expand(mine, L);
+            ++checks; if (conv(e_ref) != e_mine) { ++bad; std::printf("expand differs (L=%zu)\n", L); continue; }
+            if (e_mine.empty()) continue;
+            // fold back into parts and expand again with the folded partition: must reproduce pi and u exactly, and a lower bound
+            // sequence that accepts exactly the same (position, errors) pairs: max over the prefix is what counts (e never decreases)
+            auto [folded, partition] = fmb200::search_pseudo::detail_pseudo::fold(e_mine);
+            auto again = ms::expand(folded, partition);
+            ++checks;
+            bool ok = again.size() == e_mine.size() && partition.size() <= 16;
+            for (size_t i = 0; ok && i < again.size(); ++i) {
+                // the first part may be walked in either direction (expand.h:21-28 derives it from the second part; search_ng26 and
+                // the device always walk it to the right): same symbols, same bounds -- compare it as a set
+                auto first = [&](ms::Search x) { std::sort(x.pi.begin(), x.pi.begin() + partition[folded[i].pi[0]]); return x.pi; };
+                ok = first(again[i]) == first(e_mine[i]) && again[i].u == e_mine[i].u;
+                size_t ma = 0, mb = 0;
+                for (size_t p = 0; ok && p < L; ++p) { ma = std::max(ma, again[i].l[p]); mb = std::max(mb, e_mine[i].l[p]); ok = ma == mb; }
+            }
+            if (!ok) { ++bad; std::printf("fold differs (L=%zu, parts=%zu)\n", L, partition.size()); }
+        }
+    }
+    std::printf("%d checks, %d bad\n", checks, bad);
+    return bad != 0;
+}
+''')
+    exe = tmp_path / "e"
+    lib = os.path.join(ROOT, "fmindex-collection_b200")
+    import fmb200  # noqa: F401
+    from fmb200 import build as b
+    b.build()
+    # the reference's headers need C++23 and mmser / libsais stand-ins only for the index types, which are not included here
+    subprocess.run(["g++", "-std=c++23", "-O1", "-Wno-comment", "-I", os.path.join(ROOT, "include"), "-I", REF_SRC, "-I", os.path.join(ROOT, "oracle", "shim"),
+                    str(src), "-L", lib, "-lfmb200", f"-Wl,-rpath,{lib}", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 bad" in r.stdout

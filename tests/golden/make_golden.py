@@ -34,6 +34,24 @@ def scheme_list(s):
     return [a.astype(int).tolist() for a in s]
 
 
+def hits_in_order(h):
+    """hit-limited searches: the delegate calls in the order the reference makes them (one thread: ascending qidx, depth-first
+    discovery order inside a query) -- NOT sorted"""
+    return [[int(x) for x in r] for r in h.tolist()]
+
+
+def repeat_text(seed):
+    """30 mutated copies of a 40-symbol unit, one sequence each: wide intervals, many rows per cursor"""
+    rng = np.random.default_rng(seed)
+    unit = rng.integers(1, 5, 40).astype(np.uint8)
+    seqs = []
+    for _ in range(30):
+        u = unit.copy()
+        u[rng.integers(0, 40, 2)] = rng.integers(1, 5, 2)
+        seqs.append(u)
+    return np.concatenate([np.concatenate([s, [0]]) for s in seqs]).astype(np.uint8), seqs
+
+
 def main():
     assert build_ref(), "reference library not available"
     out = {"schemes": {}, "cases": []}
@@ -74,6 +92,9 @@ def main():
                 entry["searches"][f"ng26_optimum_k{k}_{'edit' if edit else 'ham'}"] = dict(hits=hits_list(h), locs=locs_list(ref.locate(h)))
                 h = ref.search_facade(sym, off, edit, k)
                 entry["searches"][f"facade_k{k}_{'edit' if edit else 'ham'}"] = dict(hits=hits_list(h))
+                for lim in (1, 3):     # search_ng26::search(..., n): SearchNg26.h:408-433
+                    h = ref.search_ng26(sym, off, sch, part, edit, max_hits=lim)
+                    entry["searches"][f"ng26_optimum_k{k}_{'edit' if edit else 'ham'}_n{lim}"] = dict(hits_in_order=hits_in_order(h))
         short = reads_all[:, :10]
         ssym, soff = synth.flatten(short)
         entry["short_queries"] = short.tolist()
@@ -86,6 +107,21 @@ def main():
         entry["string"] = [dict(row=r, dir=d, rank=[int(ref.rank(r, s, d)) for s in range(5)],
                                 prefix_rank=[int(ref.prefix_rank(r, s, d)) for s in range(6)]) for r in rows for d in (0, 1)]
         out["cases"].append(entry)
+    # hit limit on a repetitive collection: the order of the children of wide nodes and the clipping of cursors with many rows
+    text, seqs = repeat_text(21)
+    ref = Ref.build(text, 5, 2, True)
+    reads = np.array([seqs[i % 30][4:20] for i in range(40)], dtype=np.uint8)
+    reads = synth.plant_errors(reads, 5, 1, True, 22)
+    sym, off = synth.flatten(reads)
+    entry = dict(name="repeats_hit_limit", rate=2, L=16, text=text.tolist(), queries=reads.tolist(), searches={})
+    for k in (1, 2):
+        for edit in (False, True):
+            sch = schemes.optimum(0, k)
+            part = schemes.uniform_partition(sch[0].shape[1], 16)
+            for lim in (1, 4, 25, 1000):
+                h = ref.search_ng26(sym, off, sch, part, edit, max_hits=lim)
+                entry["searches"][f"ng26_optimum_k{k}_{'edit' if edit else 'ham'}_n{lim}"] = dict(hits_in_order=hits_in_order(h))
+    out["hit_limit_case"] = entry
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_vectors.json")
     with open(path, "w") as f:
         json.dump(out, f, separators=(",", ":"))

@@ -41,6 +41,32 @@ def test_golden_search_n(gpu):
     assert len(g.search_scheme(g.upload(*q), sch, p, True, n=0)) == 0                       # SearchNg26.h:410
 
 
+def test_search_n_against_reference_output(gpu):
+    """the reference's own hit-limited output, in order (tests/golden/ref_vectors.json, produced by tests/golden/make_golden.py from
+    the compiled reference): the device must return exactly these lists"""
+    import json
+    import os
+    from fmb200 import schemes, synth
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.json")) as f:
+        golden = json.load(f)
+    checked = 0
+    for c in list(golden["cases"]) + [golden["hit_limit_case"]]:
+        o, g = make_index_pair(gpu, np.array(c["text"], dtype=np.uint8), 5, c["rate"])
+        sym, off = synth.flatten(np.array(c["queries"], dtype=np.uint8))
+        q = g.upload(sym, off)
+        for key, val in c["searches"].items():
+            if "hits_in_order" not in val:
+                continue
+            _, _, kk, tag, nn = key.split("_")
+            sch = schemes.optimum(0, int(kk[1:]))
+            part = schemes.uniform_partition(sch[0].shape[1], c["L"])
+            got = g.search_scheme(q, sch, part, tag == "edit", n=int(nn[1:])).hits()
+            exp = np.array([tuple(r) for r in val["hits_in_order"]], dtype=got.dtype) if val["hits_in_order"] else got[:0]
+            assert _same_list(got, exp), (c["name"], key)
+            checked += len(exp)
+    assert checked > 2000
+
+
 @pytest.fixture(scope="module")
 def pair(gpu):
     from fmb200 import synth

@@ -221,6 +221,26 @@ def test_oracle_matches_reference_vectors(golden, case):
         assert np.array_equal(sort_hits(o.search_backtracking(ssym, soff, k)), _hits_arr(S[f"backtracking_k{k}"]["hits"]))
 
 
+def test_hit_limited_searches_match_reference_output_in_order(golden):
+    """search_ng26::search(..., n) (SearchNg26.h:408-433): the reference's delegate calls, in the reference's order, recorded by
+    tests/golden/make_golden.py -- random texts and a repetitive collection (wide nodes, cursors with many rows that get clipped)"""
+    from fmb200 import schemes, synth
+    checked = 0
+    for c in list(golden["cases"]) + [golden["hit_limit_case"]]:
+        o = Oracle.build(np.array(c["text"], dtype=np.uint8), 5, c["rate"])
+        sym, off = synth.flatten(np.array(c["queries"], dtype=np.uint8))
+        for key, val in c["searches"].items():
+            if "hits_in_order" not in val:
+                continue
+            _, _, kk, tag, nn = key.split("_")                       # ng26_optimum_k1_edit_n3
+            sch = schemes.optimum(0, int(kk[1:]))
+            part = schemes.uniform_partition(sch[0].shape[1], c["L"])
+            got = o.search_ng26(sym, off, sch, part, tag == "edit", max_hits=int(nn[1:]))
+            assert np.array_equal(got, _hits_arr(val["hits_in_order"])), (c["name"], key)
+            checked += len(got)
+    assert checked > 2000
+
+
 # ---- live differential against the reference library, when it was built ------------------------------------
 @pytest.mark.skipif(not Ref.available(), reason="oracle/_ref/libfmref.so not built (needs /root/reference)")
 @pytest.mark.parametrize("seed", [1, 2])

@@ -50,6 +50,28 @@ def uniform_partition(parts, total):
     return np.array([base + (1 if i < rest else 0) for i in range(parts)], dtype=np.uint32)
 
 
+def expand(scheme, counts):
+    """expand(scheme, counts), search_scheme/expand.h:67-180: one pi / l / u entry per query symbol (the input of search_pseudo).
+    A part is walked forwards when the next part lies to its right (the first part: like the second one); every symbol of a part
+    carries the part's upper bound, the last one its lower bound, the others the lower bound of the part before.  (The reference
+    drops searches that are not valid afterwards; the generators used here never produce such.)"""
+    pi, l, u = scheme
+    counts = [int(c) for c in counts]
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int)
+    out_pi, out_l, out_u = [], [], []
+    for s in range(pi.shape[0]):
+        rp, rl, ru = [], [], []
+        P = pi.shape[1]
+        for i in range(P):
+            forward = (P == 1 or pi[s, 1] > pi[s, 0]) if i == 0 else pi[s, i] > pi[s, i - 1]
+            b, c = starts[pi[s, i]], counts[pi[s, i]]
+            rp += [b + j if forward else b + c - 1 - j for j in range(c)]
+            ru += [int(u[s, i])] * c
+            rl += [int(l[s, i - 1]) if i > 0 else 0] * (c - 1) + ([int(l[s, i])] if c > 0 else [])
+        out_pi.append(rp); out_l.append(rl); out_u.append(ru)
+    return (np.array(out_pi, dtype=np.uint32), np.array(out_l, dtype=np.uint32), np.array(out_u, dtype=np.uint32))
+
+
 def limit_to_hamming(scheme):
     """limitToHamming, search_scheme/expand.h:301-319"""
     pi, l, u = (a.copy() for a in scheme)

@@ -719,6 +719,56 @@ uint64_t fmo_search_ng26(const fmo_index* ix, const uint8_t* qsym, const uint64_
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* search_pseudo -- search/SearchPseudo.h:13-186: the plain recursive search over an EXPANDED     */
+/* scheme (one pi / l / u entry per query symbol), Hamming (search_hm :60-98) or edit distance    */
+/* without any redundancy filter (search_distance :100-165).                                      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const fmo_index* ix; const uint8_t* query; uint64_t L, qidx; const uint32_t *pi, *l, *u; hitvec* hv; fmo_counters* ctr;
+} pseudo_ctx;
+
+static int pseudo_right(const pseudo_ctx* cx, uint64_t pos) { return pos == 0 || cx->pi[pos - 1] < cx->pi[pos]; }   /* :43-56 */
+
+static void pseudo_search(pseudo_ctx* cx, int edit, cursor_t cur, uint64_t e, uint64_t pos) {
+    if (cur.len == 0) return;
+    if (pos == cx->L) {                                                        /* :66-71, :106-111 */
+        if (cx->l[pos - 1] <= e && e <= cx->u[pos - 1]) hit_push(cx->hv, cx->qidx, cur, e);
+        return;
+    }
+    if (e > cx->u[pos]) return;
+    uint8_t rank = cx->query[cx->pi[pos]];
+    const int right = pseudo_right(cx, pos);
+    cursor_t cursors[256];
+    memset(cursors, 0, sizeof(cursor_t) * cx->ix->sigma);
+    if (e + 1 <= cx->u[pos]) ext_all(cx->ix, cur, right, cursors, cx->ctr);     /* :82-86, :122-128 */
+    else cursors[rank] = right ? ext_right(cx->ix, cur, rank, cx->ctr) : ext_left(cx->ix, cur, rank, cx->ctr);
+    if (cx->l[pos] <= e) pseudo_search(cx, edit, cursors[rank], e, pos + 1);    /* match */
+    if (cx->l[pos] <= e + 1 && e + 1 <= cx->u[pos])                             /* substitution */
+        for (uint64_t i = 1; i < cx->ix->sigma; ++i)
+            if (i != rank) pseudo_search(cx, edit, cursors[i], e + 1, pos + 1);
+    if (!edit) return;
+    if (e + 1 <= cx->u[pos])                                                    /* deletion :150-155 */
+        for (uint64_t i = 1; i < cx->ix->sigma; ++i) pseudo_search(cx, edit, cursors[i], e + 1, pos);
+    if (cx->l[pos] <= e + 1 && e + 1 <= cx->u[pos]) pseudo_search(cx, edit, cur, e + 1, pos + 1);   /* insertion :158-160 */
+}
+
+uint64_t fmo_search_pseudo(const fmo_index* ix, const uint8_t* qsym, const uint64_t* qoff, uint64_t nq, int edit,
+                           uint32_t n_searches, uint32_t L, const uint32_t* pi, const uint32_t* l, const uint32_t* u, fmo_hit** out, fmo_counters* ctr) {
+    hitvec hv = {0, 0, 0};
+    *out = NULL;
+    for (uint64_t q = 0; q < nq; ++q) {                                         /* :171-186 */
+        if (qoff[q + 1] - qoff[q] != L) continue;                              /* the reference asserts equal lengths */
+        for (uint32_t s = 0; s < n_searches; ++s) {
+            pseudo_ctx cx = {ix, qsym + qoff[q], L, q, pi + (size_t)s * L, l + (size_t)s * L, u + (size_t)s * L, &hv, ctr};
+            cursor_t root = {0, 0, ix->n, 0};
+            pseudo_search(&cx, edit, root, 0, 0);
+        }
+    }
+    *out = hv.v;
+    return hv.n;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* search_backtracking -- search/Backtracking.h:15-98                                          */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {

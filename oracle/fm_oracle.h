@@ -99,6 +99,10 @@ uint64_t fmo_search_ng26_keys(const fmo_index* ix, const uint8_t* qsym, const ui
                               const uint32_t* partition, uint64_t max_hits, fmo_hit** out, uint64_t** keys_out, fmo_counters* ctr);
 int fmo_ng26_key_layout(uint32_t sigma, uint32_t n_searches, uint32_t n_parts, const uint32_t* u, const uint32_t* partition,
                         uint32_t* slots, uint32_t* bits, uint32_t* maxd, uint32_t* ords);
+/* search/SearchPseudo.h:171-186: expanded scheme = n_searches x L arrays pi, l, u (one entry per query symbol, search_scheme/expand.h);
+ * edit != 0: search_distance (no redundancy filter), else search_hm.  Queries of another length than L are skipped. */
+uint64_t fmo_search_pseudo(const fmo_index* ix, const uint8_t* qsym, const uint64_t* qoff, uint64_t nq, int edit,
+                           uint32_t n_searches, uint32_t L, const uint32_t* pi, const uint32_t* l, const uint32_t* u, fmo_hit** out, fmo_counters* ctr);
 /* search/Backtracking.h:85-88 (Hamming, works on unidirectional indices too) */
 uint64_t fmo_search_backtracking(const fmo_index* ix, const uint8_t* qsym, const uint64_t* qoff, uint64_t nq,
                                  uint32_t max_errors, fmo_hit** out, fmo_counters* ctr);

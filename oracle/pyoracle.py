@@ -209,6 +209,17 @@ class Oracle:
               C.c_uint64(max_hits), C.byref(out), C.byref(keys), None)
         return _take(self.lib().fmo_free, out.value, n, HIT_DTYPE), _take(self.lib().fmo_free, keys.value, n, np.dtype(np.uint64))
 
+    def search_pseudo(self, symbols, offsets, expanded, edit):
+        """search_pseudo::search<Edit> with an expanded scheme = (pi, l, u) arrays of shape n_searches x L"""
+        symbols, offsets = _u8(symbols), _u64(offsets)
+        pi, l, u = (np.ascontiguousarray(a, dtype=np.uint32) for a in expanded)
+        out = C.c_void_p()
+        f = self.lib().fmo_search_pseudo
+        f.restype = C.c_uint64
+        n = f(self.h, _p(symbols), _p(offsets), C.c_uint64(offsets.size - 1), C.c_int(int(edit)), C.c_uint32(pi.shape[0]), C.c_uint32(pi.shape[1]),
+              _p(pi), _p(l), _p(u), C.byref(out), None)
+        return _take(self.lib().fmo_free, out.value, n, HIT_DTYPE)
+
     def search_backtracking(self, symbols, offsets, max_errors, counters=None):
         symbols, offsets = _u8(symbols), _u64(offsets)
         out = C.c_void_p()
@@ -349,6 +360,16 @@ class Ref:
         n = self.lib().fmr_search_facade(self.h, _p(symbols), _p(offsets), C.c_uint64(offsets.size - 1), C.c_int(int(edit)),
                                          C.c_uint32(errors), C.byref(out), C.c_int(threads), self._secs())
         self.last_seconds = self._s.value
+        return _take(self.lib().fmr_free, out.value, n, HIT_DTYPE)
+
+    def search_pseudo(self, symbols, offsets, expanded, edit, threads=1):
+        symbols, offsets = _u8(symbols), _u64(offsets)
+        pi, l, u = (np.ascontiguousarray(a, dtype=np.uint32) for a in expanded)
+        out = C.c_void_p()
+        f = self.lib().fmr_search_pseudo
+        f.restype = C.c_uint64
+        n = f(self.h, _p(symbols), _p(offsets), C.c_uint64(offsets.size - 1), C.c_int(int(edit)), C.c_uint32(pi.shape[0]), C.c_uint32(pi.shape[1]),
+              _p(pi), _p(l), _p(u), C.byref(out), C.c_int(threads), self._secs())
         return _take(self.lib().fmr_free, out.value, n, HIT_DTYPE)
 
     def search_backtracking(self, symbols, offsets, max_errors, threads=1):

@@ -17,6 +17,7 @@
 #include <fmindex-collection/search/Backtracking.h>
 #include <fmindex-collection/search/SearchNg26.h>
 #include <fmindex-collection/search/SearchNoErrors.h>
+#include <fmindex-collection/search/SearchPseudo.h>
 #include <fmindex-collection/search/search.h>
 #include <fmindex-collection/search_scheme/expand.h>
 #include <fmindex-collection/search_scheme/generator/all.h>
@@ -280,6 +281,29 @@ uint64_t fmr_search_facade(fmr_index const* ix, uint8_t const* qsym, uint64_t co
             };
             if (edit) fmc::search<true>(index, sub, errors, cb);
             else fmc::search<false>(index, sub, errors, cb);
+        });
+    });
+}
+
+// fmc::search_pseudo::search<Edit>(index, queries, expandedScheme, cb) (search/SearchPseudo.h:171-186); pi / l / u = n_searches x L
+uint64_t fmr_search_pseudo(fmr_index const* ix, uint8_t const* qsym, uint64_t const* qoff, uint64_t nq, int edit,
+                           uint32_t n_searches, uint32_t L, uint32_t const* pi, uint32_t const* l, uint32_t const* u, fmo_hit** out, int threads, double* seconds) {
+    auto qs = make_queries(qsym, qoff, nq);
+    fmc::search_scheme::Scheme scheme;
+    for (uint32_t s = 0; s < n_searches; ++s) {
+        fmc::search_scheme::Search se;
+        for (uint32_t p = 0; p < L; ++p) {
+            se.pi.push_back(pi[s * L + p]);
+            se.l.push_back(l[s * L + p]);
+            se.u.push_back(u[s * L + p]);
+        }
+        scheme.push_back(se);
+    }
+    return dispatch_bi(ix, [&](auto const& index) {
+        return sharded<fmo_hit>(qs, threads, out, seconds, [&](uint64_t base, Queries const& sub, std::vector<fmo_hit>& res) {
+            auto cb = [&](size_t qidx, auto cur, size_t e) { res.push_back(fmo_hit{base + qidx, cur.lb, cur.lbRev, cur.len, cur.steps, e}); };
+            if (edit) fmc::search_pseudo::search<true>(index, sub, scheme, cb);
+            else fmc::search_pseudo::search<false>(index, sub, scheme, cb);
         });
     });
 }

@@ -308,3 +308,41 @@ def test_discovery_order_keys_ascend_in_report_order(kind):
                 assert np.all(keys[1:][same_q] > keys[:-1][same_q]), (kind, k, edit)
                 total += hits.size
     assert total > 500
+
+
+# ---- search_pseudo (search/SearchPseudo.h): golden literals + live differential ----------------------------
+def test_checkSearches_pseudo(check_searches):
+    """search/checkSearches.cpp:143-176 (edit distance, 'all search') and :215-241 (Hamming) with expand(pigeon_opt(0,1), 2)"""
+    from fmb200 import schemes
+    o = check_searches
+    sym, off = flat([A("CC"), A("BB")])
+    expanded = schemes.expand(PIGEON_OPT_K1, [1, 1])
+    exp_edit = [(0, 0, 2), (0, 0, 3), (0, 0, 3), (0, 0, 3), (0, 1, 6), (0, 1, 7), (0, 1, 7), (0, 1, 7),
+                (1, 0, 6), (1, 0, 7), (1, 0, 7), (1, 0, 7), (1, 1, 2), (1, 1, 3), (1, 1, 3), (1, 1, 3)]
+    assert located(o, o.search_pseudo(sym, off, expanded, True)) == exp_edit
+    assert located(o, o.search_pseudo(sym, off, expanded, False)) == HAM
+
+
+@pytest.mark.skipif(not Ref.available(), reason="oracle/_ref/libfmref.so not built (needs /root/reference)")
+def test_pseudo_oracle_vs_reference_library():
+    from fmb200 import schemes, synth
+    text = synth.multi_text([1800, 600], 5, 61)
+    o = Oracle.build(text, 5, 4)
+    r = Ref.build(text, 5, 4)
+    L = 18
+    reads, _ = synth.reads_from_text(text[:1800], 60, L, 5)
+    reads = synth.plant_errors(reads, 5, 1, True, 6)
+    sym, off = synth.flatten(reads)
+    total = 0
+    for k in (1, 2):
+        for sch in (schemes.optimum(0, k), schemes.h2(k + 2, 0, k), schemes.backtracking(k + 1, 0, k)):
+            expanded = schemes.expand(sch, schemes.uniform_partition(sch[0].shape[1], L))
+            for edit in (False, True):
+                a, b = sort_hits(o.search_pseudo(sym, off, expanded, edit)), sort_hits(r.search_pseudo(sym, off, expanded, edit))
+                assert np.array_equal(a, b), (k, edit)
+                total += len(a)
+            # Hamming: the per-symbol search equals the per-part search of search_ng26 (the argument behind the device's fold)
+            ham = schemes.limit_to_hamming(sch)
+            part = schemes.uniform_partition(sch[0].shape[1], L)
+            assert np.array_equal(sort_hits(o.search_pseudo(sym, off, schemes.expand(ham, part), False)), sort_hits(o.search_ng26(sym, off, ham, part, False)))
+    assert total > 1000

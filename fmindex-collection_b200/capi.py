@@ -42,7 +42,7 @@ SYMBOLS = [
     "fmb_string_symbol", "fmb_string_rank", "fmb_string_prefix_rank", "fmb_string_all_ranks",
     "fmb_cursor_extend", "fmb_cursor_extend_all",
     "fmb_queries_upload", "fmb_queries_upload_revcomp", "fmb_queries_destroy", "fmb_queries_count",
-    "fmb_search_exact", "fmb_search_scheme", "fmb_search_scheme_n", "fmb_search_backtracking", "fmb_locate", "fmb_locate_rows", "fmb_sample_value",
+    "fmb_search_exact", "fmb_search_scheme", "fmb_search_scheme_n", "fmb_search_scheme_pseudo", "fmb_search_backtracking", "fmb_locate", "fmb_locate_rows", "fmb_sample_value",
     "fmb_results_count", "fmb_results_kind", "fmb_results_fetch_hits", "fmb_results_fetch_locs", "fmb_results_fetch_locs32",
     "fmb_results_get_stats", "fmb_results_destroy",
     "fmb_search_and_locate", "fmb_index_save", "fmb_index_load", "fmb_checksum64",
@@ -250,6 +250,15 @@ class Index:
         else:
             _check(lib().fmb_search_scheme_n(self.h, queries.h, C.c_int(1 if edit else 0), C.c_uint32(pi.shape[0]),
                                              C.c_uint32(pi.shape[1]), _ptr(pi), _ptr(l), _ptr(u), _ptr(part), C.c_uint64(n), C.byref(r)))
+        return Results(r)
+
+    def search_scheme_pseudo(self, queries, scheme, partition, edit):
+        """search_pseudo::search<Edit> on the part form of an expanded scheme: edit distance without redundancy filter"""
+        pi, l, u = (np.ascontiguousarray(a, dtype=np.uint32) for a in scheme)
+        part = _u32(partition)
+        r = C.c_void_p()
+        _check(lib().fmb_search_scheme_pseudo(self.h, queries.h, C.c_int(1 if edit else 0), C.c_uint32(pi.shape[0]),
+                                              C.c_uint32(pi.shape[1]), _ptr(pi), _ptr(l), _ptr(u), _ptr(part), C.byref(r)))
         return Results(r)
 
     def search_backtracking(self, queries, max_errors):

@@ -211,7 +211,9 @@ __device__ __forceinline__ SimState sim_unpack(unsigned long long v) {
 }
 
 // BYTES: the window holds 4 symbols of 8 bits (generic layout, LF^4 table) instead of 16 codes of 2 bits (symbol - 1)
-template <bool EDIT, bool BYTES>
+// PSEUDO: edit distance without the redundancy filter (search_pseudo's search_distance, search/SearchPseudo.h:100-165): deletions and
+// insertions are allowed after every kind of step and a match may follow them
+template <bool EDIT, bool BYTES, bool PSEUDO>
 __device__ bool sim_subtree_dies(const SchemeParams& sp, uint32_t search, uint32_t R, uint32_t window /*w[0] in the low bits*/,
                                  const uint8_t* __restrict__ qptr /*query symbol of c = 0*/, const SimState& root, uint32_t& ext) {
     constexpr int kStack = 12;
@@ -266,11 +268,11 @@ __device__ bool sim_subtree_dies(const SchemeParams& sp, uint32_t search, uint32
             continue;
         }
         // ---- search_next_dir_single :251-365
-        const bool Deletion = EDIT && s.T != INFO_S && s.T != INFO_I;
-        const bool Insertion = EDIT && s.T != INFO_S && s.T != INFO_D;
+        const bool Deletion = EDIT && (PSEUDO || (s.T != INFO_S && s.T != INFO_I));
+        const bool Insertion = EDIT && (PSEUDO || (s.T != INFO_S && s.T != INFO_D));
         const bool insAllowed = (s.pev > 1 || lp <= s.e + 1) && s.e + 1 <= up;
         const bool mismatchAllowed = s.e + 1 <= up;
-        const bool matchAllowed = (s.pev > 1 || lp <= s.e) && s.e <= up && (s.T != INFO_I || q != s.lastQRank) && (s.T != INFO_D || q != s.lastRank);
+        const bool matchAllowed = (s.pev > 1 || lp <= s.e) && s.e <= up && (PSEUDO || ((s.T != INFO_I || q != s.lastQRank) && (s.T != INFO_D || q != s.lastRank)));
         count += 1;
         if (top + 3 > kStack) return false;
         if (sym == q) {
@@ -324,7 +326,7 @@ constexpr int kFastForward = 12;
 #define FMB_SCHEME_MINB 4          // 4 blocks of 256 threads per SM -> 64 registers (a few spills beat the lower occupancy of 80)
 #endif   // consecutive single-child expansions a lane may chain in registers per pop
 
-template <class OCC, bool EDIT, bool ORDERED>
+template <class OCC, bool EDIT, bool ORDERED, bool PSEUDO>
 __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(const __grid_constant__ IndexView<OCC> ix, const __grid_constant__ SchemeParams sp,
                                                             const uint8_t* __restrict__ qsym, const uint64_t* __restrict__ qoff,
                                                             const __grid_constant__ JumpView jv, uint64_t n_roots,
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                 }
                 if (st.len != 0 && st.mode == MODE_NEXT) {                                          // search_next :98-117
                     if (st.part == np) {
-                        bool ok = !EDIT || ((st.LInfo == INFO_M || st.LInfo == INFO_I) && (st.RInfo == INFO_M || st.RInfo == INFO_I));
+                        bool ok = !EDIT || PSEUDO || ((st.LInfo == INFO_M || st.LInfo == INFO_I) && (st.RInfo == INFO_M || st.RInfo == INFO_I));
                         report = ok && sp.l[st.search][np - 1] <= st.e && st.e <= sp.u[st.search][np - 1];
                         go_dir = false;
                     } else {
@@ -662,10 +664,9 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         } else {
                             const uint32_t TInfo = R ? st.RInfo : st.LInfo;
                             const uint32_t lastRank = side_get(st.side, R, 0), lastQRank = side_get(st.side, R, 1);
-                            const bool Deletion = EDIT && TInfo != INFO_S && TInfo != INFO_I;
-                            const bool Insertion = EDIT && TInfo != INFO_S && TInfo != INFO_D;
-                            const bool matchAllowed = (st.pev > 1 || lp <= st.e) && st.e <= up && (TInfo != INFO_I || q != lastQRank) &&
-                                                      (TInfo != INFO_D || q != lastRank);
+                            const bool Deletion = EDIT && (PSEUDO || (TInfo != INFO_S && TInfo != INFO_I));
+                            const bool Insertion = EDIT && (PSEUDO || (TInfo != INFO_S && TInfo != INFO_D));
+                            const bool matchAllowed = (st.pev > 1 || lp <= st.e) && st.e <= up && (PSEUDO || ((TInfo != INFO_I || q != lastQRank) && (TInfo != INFO_D || q != lastRank)));
                             const bool insAllowed = (st.pev > 1 || lp <= st.e + 1) && st.e + 1 <= up;
                             const bool mismatchAllowed = st.e + 1 <= up;
                             if (st.len > 1) {                                                           // search_next_dir :143-224
@@ -768,7 +769,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                                                 }
                                             }
                                             uint32_t sim_ext = 0;
-                                            if (ok && sim_subtree_dies<EDIT, OCC::kSymbolLoad>(sp, st.search, R, window, qptr, cs, sim_ext)) {
+                                            if (ok && sim_subtree_dies<EDIT, OCC::kSymbolLoad, PSEUDO>(sp, st.search, R, window, qptr, cs, sim_ext)) {
                                                 cmask &= ~(1ull << bit);
                                                 n_ext += sim_ext; n_look += sim_ext;
                                             }

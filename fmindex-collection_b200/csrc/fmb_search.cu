@@ -31,12 +31,12 @@ int set_device(int device) {
 constexpr uint32_t kStackCapDefault = 160;   // items per warp (5 KB; 40 KB per block, 4 blocks per SM)
 constexpr uint32_t kWarpsPerBlock = 8;
 
-template <class OCC, bool EDIT, bool ORDERED>
+template <class OCC, bool EDIT, bool ORDERED, bool PSEUDO>
 int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const SchemeParams& sp, const fmb_queries* q, uint64_t n_roots, const Item* in_items,
                     uint64_t n_in, const SchemeOut& out, cudaStream_t st) {
     static const uint32_t kStackCap = getenv("FMB_SCHEME_CAP") ? (uint32_t)atoi(getenv("FMB_SCHEME_CAP")) : kStackCapDefault;
     size_t smem = (size_t)kStackCap * kWarpsPerBlock * (sizeof(Item) + (ORDERED ? sizeof(unsigned long long) : 0));
-    auto kern = scheme_search_kernel<OCC, EDIT, ORDERED>;
+    auto kern = scheme_search_kernel<OCC, EDIT, ORDERED, PSEUDO>;
     // launch geometry, computed once per kernel instantiation (several host threads drive one index in the pipelined path)
     static std::mutex cfg_mu;
     static int cfg_blocks_per_sm = 0, cfg_sms = 0;
@@ -86,11 +86,11 @@ int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const Schem
     note_launches(1);
     return FMB_OK;
 }
-template <bool EDIT, bool ORDERED>
+template <bool EDIT, bool ORDERED, bool PSEUDO = false>
 int launch_scheme(const fmb_index* ix, const SchemeParams& sp, const fmb_queries* q, uint64_t n_roots, const Item* in_items,
                   uint64_t n_in, const SchemeOut& out, cudaStream_t st) {
-    if (ix->dna) return launch_scheme_t<OccDna, EDIT, ORDERED>(ix, ix->view_dna(), sp, q, n_roots, in_items, n_in, out, st);
-    return launch_scheme_t<OccGen, EDIT, ORDERED>(ix, ix->view_gen(), sp, q, n_roots, in_items, n_in, out, st);
+    if (ix->dna) return launch_scheme_t<OccDna, EDIT, ORDERED, PSEUDO>(ix, ix->view_dna(), sp, q, n_roots, in_items, n_in, out, st);
+    return launch_scheme_t<OccGen, EDIT, ORDERED, PSEUDO>(ix, ix->view_gen(), sp, q, n_roots, in_items, n_in, out, st);
 }
 
 // ---- hit limit: put the hits into the reference's discovery order and cut every query off after n rows ----------------------
@@ -168,7 +168,8 @@ int order_and_limit(fmb_results* res, DevBuf<unsigned long long>& keys, uint64_t
 }
 
 // n_limit = UINT64_MAX: every hit, in no particular order; else the reference's search_n semantics (SearchNg26.h:408-423)
-int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp_in, fmb_results** out_res, uint64_t n_limit = UINT64_MAX) {
+// pseudo: edit distance without the redundancy filter of search_ng26 (search_pseudo::search<true>, search/SearchPseudo.h:100-165)
+int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp_in, fmb_results** out_res, uint64_t n_limit = UINT64_MAX, bool pseudo = false) {
     SchemeParams sp = sp_in;
     const bool ordered = n_limit != UINT64_MAX;
     if (ordered) {
@@ -238,6 +239,7 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
             if (roots + n_in > 0) {
                 int rc = ordered ? (sp.edit ? launch_scheme<true, true>(ix, sp, q, roots, in_items, n_in, so, st)
                                             : launch_scheme<false, true>(ix, sp, q, roots, in_items, n_in, so, st))
+                         : (pseudo && sp.edit) ? launch_scheme<true, false, true>(ix, sp, q, roots, in_items, n_in, so, st)
                                  : (sp.edit ? launch_scheme<true, false>(ix, sp, q, roots, in_items, n_in, so, st)
                                             : launch_scheme<false, false>(ix, sp, q, roots, in_items, n_in, so, st));
                 if (rc) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
@@ -284,6 +286,9 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
 
 extern "C" {
 
+static int scheme_entry(const fmb_index* ix, const fmb_queries* q, int edit, uint32_t n_searches, uint32_t n_parts,
+                        const uint32_t* pi, const uint32_t* l, const uint32_t* u, const uint32_t* partition, uint64_t n, bool pseudo, fmb_results** out);
+
 int fmb_search_scheme(const fmb_index* ix, const fmb_queries* q, int edit, uint32_t n_searches, uint32_t n_parts,
                       const uint32_t* pi, const uint32_t* l, const uint32_t* u, const uint32_t* partition, fmb_results** out) {
     return fmb_search_scheme_n(ix, q, edit, n_searches, n_parts, pi, l, u, partition, UINT64_MAX, out);
@@ -291,6 +296,16 @@ int fmb_search_scheme(const fmb_index* ix, const fmb_queries* q, int edit, uint3
 
 int fmb_search_scheme_n(const fmb_index* ix, const fmb_queries* q, int edit, uint32_t n_searches, uint32_t n_parts,
                         const uint32_t* pi, const uint32_t* l, const uint32_t* u, const uint32_t* partition, uint64_t n, fmb_results** out) {
+    return scheme_entry(ix, q, edit, n_searches, n_parts, pi, l, u, partition, n, false, out);
+}
+
+int fmb_search_scheme_pseudo(const fmb_index* ix, const fmb_queries* q, int edit, uint32_t n_searches, uint32_t n_parts,
+                             const uint32_t* pi, const uint32_t* l, const uint32_t* u, const uint32_t* partition, fmb_results** out) {
+    return scheme_entry(ix, q, edit, n_searches, n_parts, pi, l, u, partition, UINT64_MAX, true, out);
+}
+
+static int scheme_entry(const fmb_index* ix, const fmb_queries* q, int edit, uint32_t n_searches, uint32_t n_parts,
+                        const uint32_t* pi, const uint32_t* l, const uint32_t* u, const uint32_t* partition, uint64_t n, bool pseudo, fmb_results** out) {
     if (!ix || !q || !out || !pi || !l || !u || !partition) { set_error("NULL argument"); return FMB_EINVAL; }
     *out = nullptr;
     if (!ix->bidirectional) { set_error("search schemes need a bidirectional index (extendRight)"); return FMB_EINVAL; }
@@ -346,7 +361,7 @@ int fmb_search_scheme_n(const fmb_index* ix, const fmb_queries* q, int edit, uin
         *out = res;
         return FMB_OK;
     }
-    return run_scheme(ix, q, sp, out, n);
+    return run_scheme(ix, q, sp, out, n, pseudo);
 }
 
 int fmb_search_backtracking(const fmb_index* ix, const fmb_queries* q, uint32_t max_errors, fmb_results** out) {

@@ -184,6 +184,15 @@ int fmb_search_scheme_n(const fmb_index* ix, const fmb_queries* q, int edit,
                         uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l, const uint32_t* u,
                         const uint32_t* partition, uint64_t n, fmb_results** out);
 
+/* search_pseudo::search<Edit>(index, queries, expandedScheme, delegate) (search/SearchPseudo.h:171-186) on the PART form of the
+ * expanded scheme (the host side folds the per-symbol pi / l / u back into parts, include/fmb200/search.hpp): edit != 0 is
+ * search_distance (:100-165) -- edit distance WITHOUT the redundancy filter of search_ng26, i.e. insertions and deletions may
+ * follow every kind of step and every alignment is reported, duplicates included; edit == 0 is search_hm (= fmb_search_scheme
+ * with Hamming distance). */
+int fmb_search_scheme_pseudo(const fmb_index* ix, const fmb_queries* q, int edit,
+                             uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l, const uint32_t* u,
+                             const uint32_t* partition, fmb_results** out);
+
 /* search_backtracking::search(index, queries, maxError, delegate) (search/Backtracking.h:85-88); Hamming,
  * works on unidirectional indices. */
 int fmb_search_backtracking(const fmb_index* ix, const fmb_queries* q, uint32_t max_errors, fmb_results** out);

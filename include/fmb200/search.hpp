@@ -7,7 +7,7 @@
 //                                         search_ng26::search<Edit>(index, queries, maxErrors, delegate)
 //   search/Backtracking.h:85-98           search_backtracking::search(index, queries, maxError, delegate(qidx, cursor, e))
 //   search/SearchOneError.h:126-145       search_one_error::search(index, queries, delegate(qidx, cursor, e))
-//   search/SearchPseudo.h:171-186         search_pseudo::search<false>(index, queries, expanded scheme, delegate(qidx, cursor, e))
+//   search/SearchPseudo.h:171-186         search_pseudo::search<Edit>(index, queries, expanded scheme, delegate(qidx, cursor, e))
 //   search/search.h:14-75                 fmc::search<Edit>(index, queries, errors, delegate), fmc::Search{...}()
 //   locate.h:15-57                        LocateLinear{index, cursor}
 // Differences a caller can observe: delegates are invoked after the device finished, grouped by
@@ -324,7 +324,7 @@ void search(index_t const& index, queries_t const& queries, delegate_t&& delegat
 // (e never decreases, so `l[pos] <= e` holds once a part end with the same or a larger bound was passed -- the argument that makes
 // expand()'s own lower bounds, SearchNg26's per-part check and this per-symbol check agree).  All searches are cut at the union of
 // those boundaries.  The edit-distance form of search_pseudo enumerates alignments without the redundancy filter of search_ng26
-// (different duplicates) and is not provided.
+// (more duplicates): it runs on the PSEUDO instantiation of the same kernel (fmb_search_scheme_pseudo).
 namespace search_pseudo {
 
 namespace detail_pseudo {
@@ -377,9 +377,29 @@ std::tuple<search_scheme::Scheme, std::vector<size_t>> fold(scheme_t const& expa
 
 template <bool EditDistance, typename index_t, Sequences queries_t, fmb200::detail::SchemeLike scheme_t>
 std::vector<fmb_hit> search_bulk(index_t const& index, queries_t const& queries, scheme_t const& expanded) {
-    static_assert(!EditDistance, "fmb200::search_pseudo: only the Hamming-distance form maps onto the device kernels");
     auto [scheme, partition] = detail_pseudo::fold(expanded);
-    return search_ng26::search_bulk<false>(index, queries, scheme, partition);
+    if constexpr (!EditDistance) {
+        return search_ng26::search_bulk<false>(index, queries, scheme, partition);
+    } else {
+        // search_distance (SearchPseudo.h:100-165): the scheme kernel with the redundancy filter switched off.  The device walks the
+        // first part to the right; with errors allowed inside a first part that the expanded scheme walks to the left the two would
+        // enumerate different alignments -- refused (every generator of the reference starts with an error-free part or walks right).
+        size_t i = 0;
+        for (auto const& e : expanded) {
+            if (scheme[i].u[0] > 0 && e.pi.size() > 1 && e.pi[1] < e.pi[0]) throw std::invalid_argument("fmb200::search_pseudo<true>: errors inside a first part that is searched to the left");
+            ++i;
+        }
+        static_assert(fmb200::detail::is_bidirectional<index_t>, "search schemes need a bidirectional index (extendRight)");
+        auto fs = fmb200::detail::flatten(scheme, partition);
+        auto flat = flatten(queries);
+        auto q = fmb200::detail::upload(index.handle(), flat);
+        fmb_results* r{};
+        check(fmb_search_scheme_pseudo(index.handle(), q.get(), 1, fs.n_searches, fs.n_parts, fs.pi.data(), fs.l.data(), fs.u.data(), fs.partition.data(), &r));
+        fmb200::detail::ResultsHandle res{r};
+        auto hits = fmb200::detail::fetch_hits(r);
+        fmb200::detail::sort_hits(hits);
+        return hits;
+    }
 }
 
 template <bool EditDistance, typename index_t, Sequences queries_t, fmb200::detail::SchemeLike scheme_t, typename delegate_t>

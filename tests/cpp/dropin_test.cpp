@@ -219,6 +219,22 @@ int main() {
             CHECK(ref.cursors.size() > 300);
         }
     }
+    // search_pseudo<true> (SearchPseudo.h:100-165): edit distance without redundancy filter, every duplicate included
+    for (size_t k : {1, 2}) {
+        for (int kind = 0; kind < 3; ++kind) {
+            auto scheme = kind == 0 ? fmc::search_scheme::generator::optimum(0, k) : kind == 1 ? fmc::search_scheme::generator::h2(k + 2, 0, k)
+                                                                                                 : fmc::search_scheme::generator::backtracking(k + 1, 0, k);
+            std::vector<std::vector<uint8_t>> shortq(queries.begin(), queries.begin() + (kind == 2 ? 40 : 200));
+            for (auto& q : shortq) q.resize(kind == 2 ? 14 : 30);
+            auto expanded = fmc::search_scheme::expand(scheme, shortq[0].size());
+            Collector ref{index}, gpu{index};
+            fmc::search_pseudo::search<true>(index, shortq, expanded, [&](size_t q, auto c, size_t e) { ref.cursors.push_back({q, c.lb, c.lbRev, c.len, c.steps, e}); });
+            fmb200::search_pseudo::search<true>(dev, shortq, expanded, [&](size_t q, auto c, size_t e) { gpu.cursors.push_back({q, c.lb, c.lbRev, c.len, c.steps, e}); });
+            ref.sort(); gpu.sort();
+            CHECK(ref.cursors == gpu.cursors);
+            CHECK(ref.cursors.size() > shortq.size());
+        }
+    }
     // fmc::Search functor vs fmb200::Search: reportFunc(qidx, seqId, pos + offset, errors)
     {
         std::vector<std::array<uint64_t, 4>> ref, gpu;

@@ -78,6 +78,7 @@ typedef fmb_loc32 LocRec;
 
 struct fmb_index {
     int device = 0;
+    int sm_count = 0;                    // SMs of `device` (launch geometry of the persistent kernels)
     uint32_t sigma = 0;
     uint64_t n = 0;
     bool bidirectional = false;

@@ -1,6 +1,6 @@
 // fmb_io.cu -- on-disk format of an index.
 //
-// The reference persists an index with cereal: BiFMIndex::serialize archives (bwt, bwtRev, C, annotatedArray)
+// The reference persists an index with cereal: BiFMIndex::serialize archives (bwt, C, annotatedArray, bwtRev)
 // (fmindex/BiFMIndex.h:209-215), written and read by saveIndex / loadIndex (fmindex/diskStorage.h:13-27).  cereal is not
 // available here and its archive layout depends on the String_c implementation, so the file written by this library holds
 // the same CONTENT in a flat, versioned, layout-independent form: the BWT bytes of both directions and the sampled suffix
@@ -10,11 +10,11 @@
 // seconds and keeps files small (8 GB instead of a 122 GB device image at 3 Gbp) and valid across layout changes.
 //
 //   offset  0  char[8]  magic "FMB200IX"
-//           8  u32      version (1)
+//           8  u32      version (2; version 1 = the same layout without header checksum, still read)
 //          12  u32      sigma
 //          16  u64      n (rows = text length incl. delimiters)
 //          24  u32      bidirectional (1 = bwtRev present)
-//          28  u32      reserved (0)
+//          28  u32      header checksum: low 32 bits of fmb_checksum64 over the 120 header bytes with this field zero (version 1: 0)
 //          32  u64      n_samples
 //          40  u64[5]   section sizes in bytes: bwt, bwtRev, marker bitmap, sample seq ids, sample positions
 //          80  u64[5]   section checksums (fmb_checksum64 below)
@@ -24,6 +24,7 @@
 #include <filesystem>
 #include <memory>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "fmb_host.hpp"
@@ -33,7 +34,7 @@ using namespace fmb;
 namespace {
 
 constexpr char kMagic[8] = {'F', 'M', 'B', '2', '0', '0', 'I', 'X'};
-constexpr uint32_t kVersion = 1;
+constexpr uint32_t kVersion = 2;
 
 struct FileHeader {
     char magic[8];
@@ -62,6 +63,11 @@ uint64_t checksum64(const void* data, uint64_t bytes) {
         h = (h ^ w) * 0x100000001B3ull;
     }
     return h;
+}
+
+uint32_t header_checksum(FileHeader h) {
+    h.reserved = 0;
+    return (uint32_t)checksum64(&h, sizeof h);
 }
 
 struct FileCloser { void operator()(FILE* f) const { if (f) fclose(f); } };
@@ -117,12 +123,17 @@ static int save_impl(const fmb_index* ix, const char* path) {
     const void* sec[5] = {bwt.data(), bwt_rev.data(), bitmap.data(), seq.data(), pos.data()};
     h.bytes[0] = n; h.bytes[1] = bwt_rev.size(); h.bytes[2] = words * 8; h.bytes[3] = ns * 4; h.bytes[4] = ns * 4;
     for (int s = 0; s < 5; ++s) h.sum[s] = checksum64(sec[s], h.bytes[s]);
-    File f(fopen(path, "wb"));
-    if (!f) { set_error("cannot open %s for writing", path); return FMB_EINVAL; }
+    h.reserved = header_checksum(h);
+    // written next to the destination and renamed into place: a failed save never leaves a truncated file at `path`
+    const std::string tmp = std::string(path) + ".tmp";
+    File f(fopen(tmp.c_str(), "wb"));
+    if (!f) { set_error("cannot open %s for writing", tmp.c_str()); return FMB_EINVAL; }
     bool ok = fwrite(&h, sizeof h, 1, f.get()) == 1;
     for (int s = 0; s < 5 && ok; ++s) ok = h.bytes[s] == 0 || fwrite(sec[s], 1, h.bytes[s], f.get()) == h.bytes[s];
     ok = ok && fflush(f.get()) == 0;
-    if (!ok) { set_error("short write to %s", path); return FMB_EINVAL; }
+    ok = (fclose(f.release()) == 0) && ok;
+    if (!ok) { remove(tmp.c_str()); set_error("short write to %s", tmp.c_str()); return FMB_EINVAL; }
+    if (rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); set_error("cannot rename %s to %s", tmp.c_str(), path); return FMB_EINVAL; }
     return FMB_OK;
 }
 
@@ -134,7 +145,11 @@ static int load_impl(fmb_index** out, int device, const char* path) {
     FileHeader h{};
     if (fread(&h, sizeof h, 1, f.get()) != 1) { set_error("%s: truncated header", path); return FMB_EINVAL; }
     if (memcmp(h.magic, kMagic, 8) != 0) { set_error("%s: not an fmb200 index file (bad magic)", path); return FMB_EINVAL; }
-    if (h.version != kVersion) { set_error("%s: file format version %u, this library reads version %u", path, h.version, kVersion); return FMB_EINVAL; }
+    if (h.version != kVersion && h.version != 1) { set_error("%s: file format version %u, this library reads versions 1 and %u", path, h.version, kVersion); return FMB_EINVAL; }
+    if (h.version >= 2 && h.reserved != header_checksum(h)) { set_error("%s: header checksum mismatch", path); return FMB_EINVAL; }
+    if (h.version == 1 && h.reserved != 0) { set_error("%s: implausible header (reserved word set in a version 1 file)", path); return FMB_EINVAL; }
+    // the range this build supports, checked before anything is allocated
+    if (h.n >= 0xFFFFFFFFull - 64) { set_error("%s: n = %llu, this build supports n < 2^32 - 64", path, (unsigned long long)h.n); return FMB_EUNSUPPORTED; }
     const uint64_t words = (h.n + 63) / 64;
     const uint64_t want[5] = {h.n, h.bidirectional ? h.n : 0, words * 8, h.n_samples * 4, h.n_samples * 4};
     if (h.sigma < 2 || h.sigma > 32 || h.n == 0 || h.bidirectional > 1 || h.n_samples > h.n) { set_error("%s: implausible header (sigma %u, n %llu)", path, h.sigma, (unsigned long long)h.n); return FMB_EINVAL; }

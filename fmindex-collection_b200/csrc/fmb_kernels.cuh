@@ -996,6 +996,36 @@ __global__ void __launch_bounds__(256) locate_rows_kernel(const __grid_constant_
     }
 }
 
+// Measurement aid (SURVEY.md §8d "empirical ceiling"): independent -- not pointer chasing -- random gathers over one of the index's
+// own tables.  A group of LANES lanes fetches one aligned granule of PER * LANES bytes with ONE load instruction per lane, exactly
+// like the search kernels do (4 x 32 B for a pair line, 1 x 16 B for a jump entry, 1 x 32 B for an occ block); the addresses come
+// from a counter hash, so every load of a thread is independent of the ones before it.
+template <int PER, int LANES>
+__global__ void __launch_bounds__(256) gather_probe_kernel(const char* __restrict__ tab, uint64_t ngran, uint32_t iters, uint32_t* __restrict__ out) {
+    const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t group = tid / LANES;
+    const uint32_t lane = (uint32_t)(tid % LANES);
+    uint32_t acc = 0;
+#pragma unroll 4
+    for (uint32_t i = 0; i < iters; ++i) {
+        const uint64_t g = splitmix64(group * iters + i) % ngran;
+        const char* p = tab + g * (uint64_t)(PER * LANES) + lane * PER;
+        if (PER == 8) {
+            const uint2 x = __ldg(reinterpret_cast<const uint2*>(p));
+            acc ^= x.x ^ x.y;
+        } else if (PER == 16) {
+            const uint4 x = __ldg(reinterpret_cast<const uint4*>(p));
+            acc ^= x.x ^ x.y ^ x.z ^ x.w;
+        } else {
+            uint32_t a, b, c, d, e, f, g2, h;
+            asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(f), "=r"(g2), "=r"(h) : "l"(p));
+            acc ^= a ^ b ^ c ^ d ^ e ^ f ^ g2 ^ h;
+        }
+    }
+    if (acc == 0x12345678u) out[0] = acc;      // keeps the loads alive
+}
+
 // annotatedArray.value(row) (suffixarray/SparseArray.h:63-70)
 template <class OCC>
 __global__ void sample_value_kernel(IndexView<OCC> ix, const uint64_t* __restrict__ rows, uint64_t count, uint8_t* __restrict__ has,

@@ -124,6 +124,22 @@ static int use_device(int device) {
     return FMB_OK;
 }
 
+// cudaMalloc for buffers handed to the caller (fmb_device_free); the allocator's cached blocks are given back first when memory is short
+static int raw_alloc(uint8_t** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        pool_trim();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? FMB_ENOMEM : FMB_ECUDA;
+    }
+    return FMB_OK;
+}
+
 static inline unsigned grid_for(uint64_t items, unsigned block) {
     return (unsigned)std::max<uint64_t>(1, (items + block - 1) / block);
 }
@@ -607,6 +623,8 @@ int new_index(fmb_index** out, int device, uint32_t sigma, uint64_t n, bool bidi
     cudaError_t e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete ix; return FMB_ECUDA; }
     ix->stream = ix->own_stream;
+    cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (ix->sm_count < 1) ix->sm_count = 1;
     *out = ix;
     return FMB_OK;
 }
@@ -1048,8 +1066,7 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
         } else if (ix->dna && ix->locblocks.p) {
             auto v = ix->view_dna();
             // persistent grid: every SM full of lane pairs (8 blocks x 256 threads), rows handed out with a grid stride
-            static int sms = 0;
-            if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+            const int sms = ix->sm_count;
             unsigned grid = (unsigned)std::min<uint64_t>(grid_for((uint64_t)total * 2, 256), (uint64_t)sms * 8);
             locate_pair_kernel<true><<<grid, 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p);
         }
@@ -1171,7 +1188,7 @@ int fmb_synth_text_device(int device, uint32_t sigma, uint64_t n, uint64_t seed,
     if (!d_text || sigma < 2 || n == 0) { set_error("bad argument"); return FMB_EINVAL; }
     FMB_TRY(use_device(device));
     uint8_t* p = nullptr;
-    FMB_CUDA(cudaMalloc(&p, n));
+    FMB_TRY(raw_alloc(&p, n));
     synth_text_kernel<<<grid_for(n, 256), 256>>>(p, n, sigma, seed);
     FMB_CUDA(cudaGetLastError());
     FMB_CUDA(cudaDeviceSynchronize());
@@ -1182,7 +1199,7 @@ int fmb_synth_reads_device(int device, const uint8_t* d_text, uint64_t n, uint64
     if (!d_text || !d_reads || length == 0 || n <= (uint64_t)length + 1) { set_error("bad argument"); return FMB_EINVAL; }
     FMB_TRY(use_device(device));
     uint8_t* p = nullptr;
-    FMB_CUDA(cudaMalloc(&p, nq * length + 32));
+    FMB_TRY(raw_alloc(&p, nq * length + 32));
     synth_reads_kernel<<<grid_for(nq * length, 256), 256>>>(d_text, n, nq, length, seed, p);
     FMB_CUDA(cudaGetLastError());
     FMB_CUDA(cudaDeviceSynchronize());
@@ -1202,7 +1219,7 @@ int fmb_synth_unit_reads_device(int device, uint32_t sigma, uint64_t nq, uint32_
     if (!d_reads || length == 0 || unit_len <= length || sigma < 3) { set_error("bad argument"); return FMB_EINVAL; }
     FMB_TRY(use_device(device));
     uint8_t* p = nullptr;
-    FMB_CUDA(cudaMalloc(&p, nq * length + 32));
+    FMB_TRY(raw_alloc(&p, nq * length + 32));
     unit_reads_kernel<<<grid_for(nq * length, 256), 256>>>(nq, length, seed, unit_len, sigma, p);
     FMB_CUDA(cudaGetLastError());
     FMB_CUDA(cudaDeviceSynchronize());
@@ -1214,13 +1231,66 @@ int fmb_synth_reads_err_device(int device, const uint8_t* d_text, uint64_t n, ui
     if (!d_text || !d_reads || length < 3 || length > 512 || sigma < 3 || n <= (uint64_t)length + 1) { set_error("bad argument"); return FMB_EINVAL; }
     FMB_TRY(use_device(device));
     uint8_t* p = nullptr;
-    FMB_CUDA(cudaMalloc(&p, nq * length + 32));
+    FMB_TRY(raw_alloc(&p, nq * length + 32));
     synth_reads_err_kernel<<<grid_for(nq, 128), 128>>>(d_text, n, nq, length, seed, max_errors, edit ? 1u : 0u, sigma, p);
     FMB_CUDA(cudaGetLastError());
     FMB_CUDA(cudaDeviceSynchronize());
     *d_reads = p;
     return FMB_OK;
 }
+// Empirical random-access ceiling of THIS device over one of the index's own tables: independent random gathers,
+// one request per granule, timed with CUDA events on the index's stream.
+int fmb_measure_gather(const fmb_index* ix, int table, uint64_t requests, double* requests_per_s, uint64_t* table_bytes, uint32_t* request_bytes) {
+    if (!ix || !requests_per_s) { set_error("NULL argument"); return FMB_EINVAL; }
+    FMB_TRY(use_device(ix->device));
+    cudaStream_t st = active_stream(ix);
+    const char* tab = nullptr;
+    uint64_t bytes = 0;
+    uint32_t per = 0, lanes = 0;
+    switch (table) {
+        case FMB_GATHER_PAIR_LINE: tab = (const char*)ix->occ2[0].p; bytes = (ix->n / 128 + 1) * 128; per = 32; lanes = 4; break;
+        case FMB_GATHER_OCC_BLOCK:
+            if (ix->dna) { tab = (const char*)ix->occ_dna[0].p; bytes = (ix->n / 64 + 1) * 32; per = 32; lanes = 1; }
+            else { tab = (const char*)ix->occ_gen[0].p; bytes = (ix->n / 64 + 1) * (uint64_t)ix->gen_stride; per = 32; lanes = ix->gen_stride / 32; }
+            break;
+        case FMB_GATHER_JUMP_ENTRY:
+            if (ix->jump[0].p) { tab = (const char*)ix->jump[0].p; per = ix->jump_shift[0] ? 16 : 8; bytes = ix->n * per; lanes = 1; }
+            else if (ix->jump4[0].p) { tab = (const char*)ix->jump4[0].p; per = 8; bytes = ix->n * 8; lanes = 1; }
+            break;
+        default: set_error("unknown table %d", table); return FMB_EINVAL;
+    }
+    if (!tab || !(lanes == 1 || lanes == 2 || lanes == 4)) { set_error("the index has no such table"); return FMB_EUNSUPPORTED; }
+    int sms = 0;
+    FMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
+    const uint64_t groups = (uint64_t)sms * 8 * 256 / lanes;
+    const uint32_t iters = (uint32_t)std::max<uint64_t>(4, (requests + groups - 1) / groups / 4 * 4);
+    const uint64_t ngran = bytes / ((uint64_t)per * lanes);
+    DevBuf<uint32_t> sink;
+    FMB_TRY(sink.alloc(1));
+    auto launch = [&]() {
+        const unsigned grid = (unsigned)(sms * 8);
+        if (per == 8) gather_probe_kernel<8, 1><<<grid, 256, 0, st>>>(tab, ngran, iters, sink.p);
+        else if (per == 16) gather_probe_kernel<16, 1><<<grid, 256, 0, st>>>(tab, ngran, iters, sink.p);
+        else if (lanes == 1) gather_probe_kernel<32, 1><<<grid, 256, 0, st>>>(tab, ngran, iters, sink.p);
+        else if (lanes == 2) gather_probe_kernel<32, 2><<<grid, 256, 0, st>>>(tab, ngran, iters, sink.p);
+        else gather_probe_kernel<32, 4><<<grid, 256, 0, st>>>(tab, ngran, iters, sink.p);
+        note_launches(1);
+    };
+    launch();                                   // warm-up (TLB, clocks)
+    FMB_CUDA(cudaStreamSynchronize(st));
+    double best = 1e30;
+    for (int rep = 0; rep < 3; ++rep) {
+        EventTimer tm(st);
+        launch();
+        best = std::min(best, tm.stop());
+    }
+    FMB_CUDA(cudaGetLastError());
+    *requests_per_s = (double)groups * iters / (best * 1e-3);
+    if (table_bytes) *table_bytes = bytes;
+    if (request_bytes) *request_bytes = per * lanes;
+    return FMB_OK;
+}
+
 int fmb_index_set_stream(fmb_index* ix, void* stream) {
     if (!ix) { set_error("NULL index"); return FMB_EINVAL; }
     ix->stream = stream ? (cudaStream_t)stream : ix->own_stream;

@@ -321,6 +321,12 @@ __device__ bool sim_subtree_dies(const SchemeParams& sp, uint32_t search, uint32
 //   bit 0 match / error-free continuation, bit 1 insertion, bit 2 sixteen-symbol jump,
 //   bits 8+c deletion(c), bits 36+c substitution(c)
 constexpr unsigned long long CH_MATCH = 1ull, CH_INS = 2ull, CH_JUMP = 4ull;
+constexpr uint32_t kDelBit = 8, kSubBit = 36;
+// the two symbol ranges of the mask must not overlap nor leave the 64 bits: k-error searches are refused above this alphabet size
+constexpr uint32_t kMaxSchemeSigma = 28;
+static_assert(kDelBit + kMaxSchemeSigma <= kSubBit && kSubBit + kMaxSchemeSigma <= 64, "child mask layout");
+// the window simulation packs the error count of a state into 4 bits (sim_pack)
+constexpr uint32_t kMaxSchemeErrors = 15;
 constexpr int kFastForward = 12;
 #ifndef FMB_SCHEME_MINB
 #define FMB_SCHEME_MINB 4          // 4 blocks of 256 threads per SM -> 64 registers (a few spills beat the lower occupancy of 80)
@@ -507,8 +513,8 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                     ch.mode = MODE_POS;
                 }
             } else {
-                const bool is_sub = bit >= 36;
-                const uint32_t c = is_sub ? bit - 36 : bit - 8;
+                const bool is_sub = bit >= kSubBit;
+                const uint32_t c = is_sub ? bit - kSubBit : bit - kDelBit;
                 if constexpr (ORDERED)
                     ch.key = order_key_edge(sp, st.key, st.steps, st.e, false, is_single ? (is_sub ? 0u : 1u) : 2 * c + (is_sub ? 1u : 0u));
                 stepped(c);
@@ -682,8 +688,8 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                                     for (uint32_t c = first_symb; c < ix.sigma; ++c) {
                                         child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, c, false, same, dother, clen);
                                         if (!clen) continue;
-                                        if (Deletion) cmask |= 1ull << (8 + c);
-                                        if (insAllowed && c != q) cmask |= 1ull << (36 + c);
+                                        if (Deletion) cmask |= 1ull << (kDelBit + c);
+                                        if (insAllowed && c != q) cmask |= 1ull << (kSubBit + c);
                                     }
                                     if (Insertion && insAllowed) cmask |= CH_INS;
                                 } else if (matchAllowed) {
@@ -713,10 +719,10 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                                             }
                                             cmask |= CH_MATCH;
                                         }
-                                        if (Deletion && mismatchAllowed) cmask |= 1ull << (8 + single_sym);
+                                        if (Deletion && mismatchAllowed) cmask |= 1ull << (kDelBit + single_sym);
                                     } else if (mismatchAllowed) {
-                                        if (insAllowed) cmask |= 1ull << (36 + single_sym);
-                                        if (Deletion) cmask |= 1ull << (8 + single_sym);
+                                        if (insAllowed) cmask |= 1ull << (kSubBit + single_sym);
+                                        if (Deletion) cmask |= 1ull << (kDelBit + single_sym);
                                     }
                                 }
                                 // ---- window simulation of the error children -------------------------------------------------
@@ -750,7 +756,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                                             bool adv = false;
                                             if (bit == 1) {                      // insertion: stays on this row
                                                 cs.m = 0; cs.lastQRank = q; cs.T = INFO_I; adv = true;
-                                            } else if (bit >= 36) {              // substitution
+                                            } else if (bit >= kSubBit) {         // substitution
                                                 cs.lastRank = single_sym; cs.lastQRank = q; cs.T = INFO_S; adv = true;
                                             } else {                             // deletion: the query symbol is not consumed
                                                 cs.lastRank = single_sym; cs.T = INFO_D;

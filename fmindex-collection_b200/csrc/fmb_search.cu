@@ -30,6 +30,15 @@ int set_device(int device) {
 
 constexpr uint32_t kStackCapDefault = 160;   // items per warp (5 KB; 40 KB per block, 4 blocks per SM)
 constexpr uint32_t kWarpsPerBlock = 8;
+constexpr int kMaxDevices = 64;
+
+struct EventPair {          // the two timing events of a search call, destroyed on every exit path
+    cudaEvent_t a = nullptr, b = nullptr;
+    EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    EventPair(const EventPair&) = delete;
+    EventPair& operator=(const EventPair&) = delete;
+};
 
 template <class OCC, bool EDIT, bool ORDERED, bool PSEUDO>
 int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const SchemeParams& sp, const fmb_queries* q, uint64_t n_roots, const Item* in_items,
@@ -38,21 +47,23 @@ int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const Schem
     size_t smem = (size_t)kStackCap * kWarpsPerBlock * (sizeof(Item) + (ORDERED ? sizeof(unsigned long long) : 0));
     auto kern = scheme_search_kernel<OCC, EDIT, ORDERED, PSEUDO>;
     // launch geometry, computed once per kernel instantiation (several host threads drive one index in the pipelined path)
+    // (cached per device: several replicas of an index may be driven from concurrent threads, fmb200/multi.hpp)
     static std::mutex cfg_mu;
-    static int cfg_blocks_per_sm = 0, cfg_sms = 0;
+    static int cfg_blocks_per_sm[kMaxDevices] = {}, cfg_sms[kMaxDevices] = {};
     int blocks_per_sm, sms;
     {
         std::lock_guard<std::mutex> lk(cfg_mu);
+        const int dev = ix->device;
+        if (dev < 0 || dev >= kMaxDevices) { set_error("device %d outside [0,%d)", dev, kMaxDevices); return FMB_EINVAL; }
         FMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      // per device
-        if (!cfg_blocks_per_sm) {
-            int dev = 0, bps = 0;
-            FMB_CUDA(cudaGetDevice(&dev));
-            FMB_CUDA(cudaDeviceGetAttribute(&cfg_sms, cudaDevAttrMultiProcessorCount, dev));
+        if (!cfg_blocks_per_sm[dev]) {
+            int bps = 0;
+            FMB_CUDA(cudaDeviceGetAttribute(&cfg_sms[dev], cudaDevAttrMultiProcessorCount, dev));
             FMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 256, smem));
-            cfg_blocks_per_sm = bps < 1 ? 1 : bps;
+            cfg_blocks_per_sm[dev] = bps < 1 ? 1 : bps;
         }
-        blocks_per_sm = cfg_blocks_per_sm;
-        sms = cfg_sms;
+        blocks_per_sm = cfg_blocks_per_sm[dev];
+        sms = cfg_sms[dev];
     }
     uint64_t work = n_roots + n_in;
     uint64_t want_blocks = (work + 255) / 256;
@@ -209,9 +220,8 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
         FMB_TRY(ovf_keys[1].alloc(ovf_cap));
     }
     FMB_TRY(ctr.alloc(8));
-    cudaEvent_t ev0, ev1;
-    cudaEventCreate(&ev0);
-    cudaEventCreate(&ev1);
+    EventPair evs;
+    const cudaEvent_t ev0 = evs.a, ev1 = evs.b;
     double total_ms = 0;
     unsigned long long h_ctr[8];
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -242,12 +252,11 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
                          : (pseudo && sp.edit) ? launch_scheme<true, false, true>(ix, sp, q, roots, in_items, n_in, so, st)
                                  : (sp.edit ? launch_scheme<true, false>(ix, sp, q, roots, in_items, n_in, so, st)
                                             : launch_scheme<false, false>(ix, sp, q, roots, in_items, n_in, so, st));
-                if (rc) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
+                if (rc) return rc;
             }
             FMB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
             FMB_CUDA(cudaStreamSynchronize(st));
             if (h_ctr[5] > ovf_cap) {
-                cudaEventDestroy(ev0); cudaEventDestroy(ev1);
                 set_error("scheme search: frontier overflow list exceeded %llu items; split the query batch", (unsigned long long)ovf_cap);
                 return FMB_EOVERFLOW;
             }
@@ -267,8 +276,11 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
         if (h_ctr[4] <= hit_cap) break;
         hit_cap = h_ctr[4];                  // second attempt with the exact size
     }
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
+    if (h_ctr[4] > hit_cap) {
+        // the second attempt ran with the exact size of the first: only a non-deterministic hit count could get here
+        set_error("scheme search: %llu hits do not fit the %llu reserved", h_ctr[4], (unsigned long long)hit_cap);
+        return FMB_EOVERFLOW;
+    }
     res->count = h_ctr[4];
     res->stats.extensions = h_ctr[0];
     res->stats.occ_lookups = h_ctr[1];
@@ -309,6 +321,7 @@ static int scheme_entry(const fmb_index* ix, const fmb_queries* q, int edit, uin
     if (!ix || !q || !out || !pi || !l || !u || !partition) { set_error("NULL argument"); return FMB_EINVAL; }
     *out = nullptr;
     if (!ix->bidirectional) { set_error("search schemes need a bidirectional index (extendRight)"); return FMB_EINVAL; }
+    if (ix->sigma > kMaxSchemeSigma) { set_error("k-error searches support sigma <= %u (index has %u)", kMaxSchemeSigma, ix->sigma); return FMB_EUNSUPPORTED; }
     if (q->device != ix->device) { set_error("queries live on device %d, index on %d", q->device, ix->device); return FMB_EINVAL; }
     if (n_searches == 0 || n_searches > (uint32_t)kMaxSearches || n_parts == 0 || n_parts > (uint32_t)kMaxParts) {
         set_error("scheme shape %u x %u outside [1,%d] x [1,%d]", n_searches, n_parts, kMaxSearches, kMaxParts);
@@ -337,7 +350,7 @@ static int scheme_entry(const fmb_index* ix, const fmb_queries* q, int edit, uin
             uint32_t v = pi[s * n_parts + p];
             if (v >= n_parts || (seen >> v) & 1) { set_error("search %u: pi is not a permutation", s); return FMB_EINVAL; }
             seen |= 1u << v;
-            if (l[s * n_parts + p] > 255 || u[s * n_parts + p] > 255) { set_error("error bounds too large"); return FMB_EINVAL; }
+            if (l[s * n_parts + p] > kMaxSchemeErrors || u[s * n_parts + p] > kMaxSchemeErrors) { set_error("error bounds above %u are not supported", kMaxSchemeErrors); return FMB_EUNSUPPORTED; }
             sp.pi[s][p] = (uint8_t)v;
             sp.l[s][p] = (uint8_t)l[s * n_parts + p];
             sp.u[s][p] = (uint8_t)u[s * n_parts + p];
@@ -368,7 +381,8 @@ int fmb_search_backtracking(const fmb_index* ix, const fmb_queries* q, uint32_t 
     if (!ix || !q || !out) { set_error("NULL argument"); return FMB_EINVAL; }
     *out = nullptr;
     if (q->device != ix->device) { set_error("queries live on device %d, index on %d", q->device, ix->device); return FMB_EINVAL; }
-    if (max_errors > 255) { set_error("max_errors too large"); return FMB_EINVAL; }
+    if (max_errors > kMaxSchemeErrors) { set_error("error bounds above %u are not supported", kMaxSchemeErrors); return FMB_EUNSUPPORTED; }
+    if (ix->sigma > kMaxSchemeSigma) { set_error("k-error searches support sigma <= %u (index has %u)", kMaxSchemeSigma, ix->sigma); return FMB_EUNSUPPORTED; }
     if (q->nq && q->min_len != q->max_len) { set_error("backtracking: all queries of a batch must have the same length"); return FMB_EUNSUPPORTED; }
     if (q->nq && q->max_len == 0) { set_error("backtracking: empty queries"); return FMB_EINVAL; }
     SchemeParams sp;

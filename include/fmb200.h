@@ -260,6 +260,15 @@ int  fmb_synth_reads_err_device(int device, const uint8_t* d_text, uint64_t n, u
 int  fmb_synth_repeat_text_device(int device, uint32_t sigma, uint64_t n, uint64_t seed, uint32_t unit_len, uint32_t copies,
                                   uint32_t sub_per_mille, uint8_t** d_text);
 int  fmb_synth_unit_reads_device(int device, uint32_t sigma, uint64_t nq, uint32_t length, uint64_t seed, uint32_t unit_len, uint8_t** d_reads);
+/* Measurement aid ("the harness must additionally measure an empirical ceiling with an independent random gather
+ * over a table of the index's size"): `requests` independent random reads over one of the index's own tables, each issued the way the
+ * search kernels issue it -- FMB_GATHER_PAIR_LINE: one 128-byte pair line by 4 lanes x 32 B; FMB_GATHER_OCC_BLOCK: one 32-byte occ block
+ * (sigma > 5: one block of the generic layout); FMB_GATHER_JUMP_ENTRY: one 8/16-byte jump-table entry.  Reports requests per second
+ * (best of three launches, CUDA events), the table size and the bytes one request uses. */
+#define FMB_GATHER_PAIR_LINE  0
+#define FMB_GATHER_OCC_BLOCK  1
+#define FMB_GATHER_JUMP_ENTRY 2
+int  fmb_measure_gather(const fmb_index* ix, int table, uint64_t requests, double* requests_per_s, uint64_t* table_bytes, uint32_t* request_bytes);
 /* All work of `ix` is enqueued on `stream` (a cudaStream_t of the index's device, e.g. the caller's timing
  * stream) instead of the index's private stream.  NULL restores the private stream. */
 int  fmb_index_set_stream(fmb_index* ix, void* stream);

@@ -23,12 +23,16 @@ def _checksum(buf):
     return h
 
 
-def _write(path, sigma, bwt, bwt_rev, bitmap, seq, pos, version=1, magic=b"FMB200IX", tamper=None, extra=b""):
+def _write(path, sigma, bwt, bwt_rev, bitmap, seq, pos, version=2, magic=b"FMB200IX", tamper=None, extra=b"", tamper_head=None):
     secs = [np.asarray(bwt, np.uint8).tobytes(), b"" if bwt_rev is None else np.asarray(bwt_rev, np.uint8).tobytes(),
             np.asarray(bitmap, np.uint64).tobytes(), np.asarray(seq, np.uint32).tobytes(), np.asarray(pos, np.uint32).tobytes()]
     head = magic + struct.pack("<IIQIIQ", version, sigma, len(bwt), 0 if bwt_rev is None else 1, 0, len(seq))
     head += struct.pack("<5Q", *[len(s) for s in secs]) + struct.pack("<5Q", *[_checksum(s) for s in secs])
     assert len(head) == 120
+    if version >= 2:        # header checksum: low 32 bits of the checksum of the header with the field zero
+        head = head[:28] + struct.pack("<I", _checksum(head) & 0xFFFFFFFF) + head[32:]
+    if tamper_head is not None:
+        head = head[:tamper_head] + bytes([head[tamper_head] ^ 1]) + head[tamper_head + 1:]
     body = b"".join(secs)
     if tamper is not None:
         body = body[:tamper] + bytes([body[tamper] ^ 1]) + body[tamper + 1:]
@@ -65,8 +69,10 @@ def test_loader_rejects_damaged_files_before_touching_the_device(fmb, small, tmp
 
     _write(p, 5, bwt, bwt_rev, bm, sq, sp, magic=b"NOTANIDX")
     assert load_error().code == FMB_EINVAL and "magic" in str(load_error())
-    _write(p, 5, bwt, bwt_rev, bm, sq, sp, version=2)
+    _write(p, 5, bwt, bwt_rev, bm, sq, sp, version=3)
     assert load_error().code == FMB_EINVAL and "version" in str(load_error())
+    _write(p, 5, bwt, bwt_rev, bm, sq, sp, tamper_head=33)       # n_samples: covered by the header checksum
+    assert load_error().code == FMB_EINVAL and "header checksum" in str(load_error())
     _write(p, 5, bwt, bwt_rev, bm, sq, sp, tamper=17)
     assert load_error().code == FMB_EINVAL and "checksum" in str(load_error())
     _write(p, 5, bwt, bwt_rev, bm, sq, sp, tamper=2 * len(bwt) + 3)
@@ -79,14 +85,24 @@ def test_loader_rejects_damaged_files_before_touching_the_device(fmb, small, tmp
     assert "truncated" in str(load_error())
     open(p, "wb").write(data[:60])
     assert "truncated header" in str(load_error())
-    # a header that claims 2^60 rows: refused from the file size, nothing is allocated
-    head = bytearray(data[:120])
-    head[16:24] = struct.pack("<Q", 1 << 60)
-    head[40:48] = struct.pack("<Q", 1 << 60)
-    head[48:56] = struct.pack("<Q", 1 << 60)
-    head[56:64] = struct.pack("<Q", (((1 << 60) + 63) // 64) * 8)
-    open(p, "wb").write(bytes(head) + data[120:])
+    # a header that claims 2^31 rows (consistent, checksum included): refused from the file size, nothing is allocated
+    def lying_header(rows):
+        head = bytearray(data[:120])
+        head[16:24] = struct.pack("<Q", rows)
+        head[40:48] = struct.pack("<Q", rows)
+        head[48:56] = struct.pack("<Q", rows)
+        head[56:64] = struct.pack("<Q", ((rows + 63) // 64) * 8)
+        head[28:32] = b"\0" * 4
+        head[28:32] = struct.pack("<I", _checksum(head) & 0xFFFFFFFF)
+        return bytes(head)
+    open(p, "wb").write(lying_header(1 << 31) + data[120:])
     assert load_error().code == FMB_EINVAL and "truncated" in str(load_error())
+    # ... and 2^60 rows are outside what this build supports
+    open(p, "wb").write(lying_header(1 << 60) + data[120:])
+    assert load_error().code == -5 and "2^32" in str(load_error())
+    # version 1 files (no header checksum) are still read
+    _write(p, 5, bwt, bwt_rev, bm, sq, sp, version=1, tamper=17)
+    assert "checksum mismatch in section 0" in str(load_error())
     _write(p, 5, bwt, bwt_rev[:-1], bm, sq, sp)                     # bwtRev shorter than bwt
     assert "section 1" in str(load_error())
     # a well-formed file passes validation: without a device the call then fails with ENODEVICE (no CPU fallback), with one it loads

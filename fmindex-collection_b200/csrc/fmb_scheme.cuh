@@ -44,7 +44,7 @@ struct Item {
     uint32_t lb, lb_rev, len, qidx;
     uint32_t qpos;       // queryPosL | queryPosR << 16  (16-bit wrap-around, cf. the note at SearchNg26.h:69-71)
     uint32_t pev_steps;  // partitionEntryValue | steps << 16
-    uint32_t meta;       // e | part << 8 | search << 16 | mode << 24 | LInfo << 26 | RInfo << 28 | Right << 30 | NextPos << 31
+    uint32_t meta;       // e (7 bits) | notext << 7 | part << 8 | search << 16 | mode << 24 | LInfo << 26 | RInfo << 28 | Right << 30 | NextPos << 31
     uint32_t side;       // lastRank[L] | lastQRank[L] << 8 | lastRank[R] << 16 | lastQRank[R] << 24
 };
 static_assert(sizeof(Item) == 32, "item is two 16-byte words");
@@ -53,6 +53,7 @@ struct State {
     uint32_t lb, lb_rev, len, qidx;
     uint32_t qposL, qposR, pev, steps;
     uint32_t e, part, search, mode, LInfo, RInfo, Right, NextPos;
+    uint32_t notext;     // the text kernel handed this single-row item back (no usable text window at its row): expand it on the index
     uint32_t side;
     unsigned long long key;   // ordered mode only (not part of Item: kept in a parallel stack)
 };
@@ -62,7 +63,7 @@ __device__ __forceinline__ Item pack_item(const State& s) {
     it.lb = s.lb; it.lb_rev = s.lb_rev; it.len = s.len; it.qidx = s.qidx;
     it.qpos = (s.qposL & 0xFFFF) | (s.qposR << 16);
     it.pev_steps = (s.pev & 0xFFFF) | (s.steps << 16);
-    it.meta = s.e | (s.part << 8) | (s.search << 16) | (s.mode << 24) | (s.LInfo << 26) | (s.RInfo << 28) | (s.Right << 30) | (s.NextPos << 31);
+    it.meta = s.e | (s.notext << 7) | (s.part << 8) | (s.search << 16) | (s.mode << 24) | (s.LInfo << 26) | (s.RInfo << 28) | (s.Right << 30) | (s.NextPos << 31);
     it.side = s.side;
     return it;
 }
@@ -71,7 +72,7 @@ __device__ __forceinline__ State unpack_item(const Item& it) {
     s.lb = it.lb; s.lb_rev = it.lb_rev; s.len = it.len; s.qidx = it.qidx;
     s.qposL = it.qpos & 0xFFFF; s.qposR = it.qpos >> 16;
     s.pev = it.pev_steps & 0xFFFF; s.steps = it.pev_steps >> 16;
-    s.e = it.meta & 0xFF; s.part = (it.meta >> 8) & 0xFF; s.search = (it.meta >> 16) & 0xFF;
+    s.e = it.meta & 0x7F; s.notext = (it.meta >> 7) & 1; s.part = (it.meta >> 8) & 0xFF; s.search = (it.meta >> 16) & 0xFF;
     s.mode = (it.meta >> 24) & 3; s.LInfo = (it.meta >> 26) & 3; s.RInfo = (it.meta >> 28) & 3;
     s.Right = (it.meta >> 30) & 1; s.NextPos = it.meta >> 31;
     s.side = it.side;
@@ -126,6 +127,11 @@ struct SchemeOut {
     unsigned long long* counters;      // [0] extensions, [1] occ lookups, [3] peak items per warp
     unsigned long long* root_counter;
     uint32_t qidx_base;                // added to the reported qidx (chunked query batches)
+    uint64_t root_base;                // first root (query x search pair) of this launch's slab
+    // text list: single-row items of edit-distance searches, handed to scheme_text_kernel (null: not used)
+    Item* text;
+    unsigned long long* text_count;
+    uint64_t text_capacity;
     // ordered mode: keys of the hits / the spilled items / the items fed in
     unsigned long long* hit_keys;
     unsigned long long* overflow_keys;
@@ -320,7 +326,7 @@ __device__ bool sim_subtree_dies(const SchemeParams& sp, uint32_t search, uint32
 // children of one expanded node are described by a bit mask and re-derived when they are written:
 //   bit 0 match / error-free continuation, bit 1 insertion, bit 2 sixteen-symbol jump,
 //   bits 8+c deletion(c), bits 36+c substitution(c)
-constexpr unsigned long long CH_MATCH = 1ull, CH_INS = 2ull, CH_JUMP = 4ull;
+constexpr unsigned long long CH_MATCH = 1ull, CH_INS = 2ull, CH_JUMP = 4ull, CH_SELF = 8ull;    // CH_SELF: the node itself goes back (to the text list)
 constexpr uint32_t kDelBit = 8, kSubBit = 36;
 // the two symbol ranges of the mask must not overlap nor leave the 64 bits: k-error searches are refused above this alphabet size
 constexpr uint32_t kMaxSchemeSigma = 28;
@@ -331,6 +337,17 @@ constexpr int kFastForward = 12;
 #ifndef FMB_SCHEME_MINB
 #define FMB_SCHEME_MINB 4          // 4 blocks of 256 threads per SM -> 64 registers (a few spills beat the lower occupancy of 80)
 #endif   // consecutive single-child expansions a lane may chain in registers per pop
+
+// Text class: a single-row item of an edit-distance search that still branches (errors possible) and is not a leaf.  Its whole
+// subtree in the current direction is decided by the text that follows the row, so the frontier kernel does not expand it: it hands
+// it to scheme_text_kernel through the global text list.  Leaves (they only report), error-free stretches (multi-symbol jumps) and
+// items the text kernel handed back (notext) stay here.
+__device__ __forceinline__ bool text_class(const State& c, uint32_t np, const uint8_t* __restrict__ qflags) {
+    if (c.len != 1 || c.mode == MODE_NOERR || c.notext) return false;
+    if (c.mode == MODE_NEXT ? (c.part == np) : (c.NextPos && c.pev == 1 && c.part + 1 == np)) return false;
+    if (qflags != nullptr && qflags[c.qidx]) return false;
+    return true;
+}
 
 template <class OCC, bool EDIT, bool ORDERED, bool PSEUDO>
 __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(const __grid_constant__ IndexView<OCC> ix, const __grid_constant__ SchemeParams sp,
@@ -345,7 +362,21 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
     // ordered mode: the keys of the stacked items, behind the item stacks of all warps
     unsigned long long* kstack = reinterpret_cast<unsigned long long*>(reinterpret_cast<Item*>(smem_raw) + (size_t)(blockDim.x >> 5) * cap) + (size_t)warp * cap;
     const uint64_t total_roots = n_roots + n_in;
-    uint32_t top = 0;
+    // the warp's stack has two ends: pending items grow from stack[0] upwards (top of them), text-class items are staged from
+    // stack[cap - 1] downwards (ttop of them) and flushed to the global text list 32 at a time
+    constexpr bool kText = EDIT && !ORDERED;          // instantiations that can hand items to the text kernel
+    const bool text_on = kText && out.text != nullptr;
+    const uint8_t* text_qflags = OCC::kSymbolLoad ? nullptr : jv.qflags;
+    uint32_t top = 0, ttop = 0;
+    auto flush_text = [&](uint32_t count) {           // the `count` most recently staged items (warp uniform, count <= 32)
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(out.text_count, (unsigned long long)count);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        __syncwarp();
+        if (lane < count && base + lane < out.text_capacity) out.text[base + lane] = stack[cap - 1 - (ttop - count + lane)];
+        ttop -= count;
+        __syncwarp();
+    };
     uint32_t n_ext = 0, n_look = 0, n_phys = 0, peak = 0;
     bool more_roots = true;
     const uint32_t np = sp.n_parts;
@@ -355,7 +386,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
 
     for (;;) {
         // ---- refill: pull roots while fewer than 32 items are pending -------------------------------------
-        if (top < 32 && more_roots) {
+        if (top < 32 && more_roots && top + ttop + 32 <= cap) {
             uint32_t want = 32 - top;
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(out.root_counter, (unsigned long long)want);
@@ -366,15 +397,18 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                 uint64_t avail = total_roots - base;
                 uint32_t got = avail < want ? (uint32_t)avail : want;
                 if (got < want) more_roots = false;
+                bool to_text = false;
+                Item it;
+                unsigned long long rkey = 0;
                 if (lane < got) {
                     uint64_t r = base + lane;
-                    Item it;
-                    unsigned long long rkey = 0;
                     if (r < n_in) {
                         it = in_items[r];
                         if constexpr (ORDERED) rkey = out.in_keys[r];
+                        // items that come back from the text kernel (or were spilled) are routed by class
+                        if (text_on) to_text = text_class(unpack_item(it), np, text_qflags);
                     } else {
-                        r -= n_in;
+                        r = r - n_in + out.root_base;
                         uint32_t s = (uint32_t)(r % sp.n_searches);
                         State st;
                         st.qidx = (uint32_t)(r / sp.n_searches);
@@ -383,7 +417,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         st.qposL = (sp.start[s] - 1) & 0xFFFF;                                 // SearchNg26.h:69-72
                         st.pev = sp.partition[sp.pi[s][0]];
                         st.e = 0; st.part = 0; st.search = s; st.mode = MODE_NEXT;
-                        st.LInfo = INFO_M; st.RInfo = INFO_M; st.Right = 1; st.NextPos = 0; st.side = 0;
+                        st.LInfo = INFO_M; st.RInfo = INFO_M; st.Right = 1; st.NextPos = 0; st.side = 0; st.notext = 0;
                         if (sp.force_left) {                                                   // Backtracking.h: right to left
                             st.qposL = (sp.partition[0] - 1) & 0xFFFF;
                             st.qposR = 0;
@@ -414,11 +448,25 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         it = pack_item(st);
                         if constexpr (ORDERED) rkey = order_key_root(sp, s);
                     }
-                    stack[top + lane] = it;
-                    if constexpr (ORDERED) kstack[top + lane] = rkey;
                 }
-                top += got;
-                __syncwarp();
+                {
+                    const uint32_t below = (1u << lane) - 1u;
+                    const uint32_t bt = __ballot_sync(0xFFFFFFFFu, lane < got && to_text);
+                    const uint32_t bc = __ballot_sync(0xFFFFFFFFu, lane < got && !to_text);
+                    if (lane < got) {
+                        if (to_text) {
+                            stack[cap - 1 - (ttop + __popc(bt & below))] = it;
+                        } else {
+                            const uint32_t idx = top + __popc(bc & below);
+                            stack[idx] = it;
+                            if constexpr (ORDERED) kstack[idx] = rkey;
+                        }
+                    }
+                    top += __popc(bc);
+                    ttop += __popc(bt);
+                    __syncwarp();
+                    if (ttop >= 32) flush_text(32);
+                }
             }
         }
         if (top == 0) {
@@ -452,6 +500,8 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
             const uint32_t R = st.Right;
             const OCC& occ = ix.occ[R];
             State ch = st;
+            ch.notext = 0;
+            if (bit == 3) return ch;
             auto stepped = [&](uint32_t c) {
                 uint32_t same, dother, clen;
                 child_cursor(ix, occ, b0, b1, blk0, blk1, lo, hi, c, is_single, same, dother, clen);
@@ -540,6 +590,11 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                 is_single = false;
                 noerr_cont = false;
                 bool go_dir = true;
+                if (kText && ff > 0 && text_on && text_class(st, np, text_qflags)) {
+                    // the node this lane fast-forwarded into belongs to the text kernel: it goes back as it is
+                    cmask = CH_SELF;
+                    go_dir = false;
+                } else
                 if (st.len == 0) {
                     go_dir = false;                                                                 // a root whose k-mer does not occur
                 } else if (st.mode == MODE_POS) {                                                   // search_next_pos :119-141
@@ -553,7 +608,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         }
                     }
                 }
-                if (st.len != 0 && st.mode == MODE_NEXT) {                                          // search_next :98-117
+                if (cmask == 0 && st.len != 0 && st.mode == MODE_NEXT) {                            // search_next :98-117
                     if (st.part == np) {
                         bool ok = !EDIT || PSEUDO || ((st.LInfo == INFO_M || st.LInfo == INFO_I) && (st.RInfo == INFO_M || st.RInfo == INFO_I));
                         report = ok && sp.l[st.search][np - 1] <= st.e && st.e <= sp.u[st.search][np - 1];
@@ -788,7 +843,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                 }
             }
             // fast forward: lanes with exactly one child (and nothing to report) continue with it
-            const bool chain = live && !report && cmask != 0 && (cmask & (cmask - 1)) == 0 && ff + 1 < kFastForward;
+            const bool chain = live && !report && cmask != 0 && cmask != CH_SELF && (cmask & (cmask - 1)) == 0 && ff + 1 < kFastForward;
             // ... as long as enough lanes of the warp do so (the others idle meanwhile)
             if ((uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, chain)) < ff_min) break;
             if (chain) st = make_child((uint32_t)(__ffsll((long long)cmask) - 1));
@@ -814,43 +869,79 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
             }
         }
 
-        // ---- compact + push children ---------------------------------------------------------------------------
-        uint32_t nchild = __popcll(cmask);
-        uint32_t incl = nchild;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= (uint32_t)o) incl += v;
-        }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        if (total == 0) continue;
-        uint32_t slot = incl - nchild;
-        Item* dst;
-        unsigned long long* kdst = nullptr;
-        bool drop = false;
-        if (top + total <= cap) {
-            dst = stack + top;
-            if constexpr (ORDERED) kdst = kstack + top;
-            top += total;
-        } else {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(out.overflow_count, (unsigned long long)total);
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            dst = out.overflow + base;
-            if constexpr (ORDERED) kdst = out.overflow_keys + base;
-            drop = base + total > out.overflow_capacity;      // host sees overflow_count > capacity and fails loudly
-        }
-        if (cmask && !drop) {
+        if constexpr (kText) {
+            // ---- push children, one round per child rank: a round's children are compacted by class with two ballots --------
             unsigned long long rest = cmask;
-            while (rest) {
-                uint32_t bit = __ffsll((long long)rest) - 1;
-                rest &= rest - 1;
-                const State c = make_child(bit);
-                if constexpr (ORDERED) kdst[slot] = c.key;
-                dst[slot++] = pack_item(c);
+            const uint32_t below = (1u << lane) - 1u;
+            for (;;) {
+                const bool has = rest != 0;
+                if (!__any_sync(0xFFFFFFFFu, has)) break;
+                Item pk;
+                bool tx = false;
+                if (has) {
+                    const uint32_t bit = __ffsll((long long)rest) - 1;
+                    rest &= rest - 1;
+                    const State c = make_child(bit);
+                    tx = text_on && text_class(c, np, text_qflags);
+                    pk = pack_item(c);
+                }
+                const uint32_t bt = __ballot_sync(0xFFFFFFFFu, has && tx), bc = __ballot_sync(0xFFFFFFFFu, has && !tx);
+                const uint32_t nt = __popc(bt), nc = __popc(bc);
+                if (top + ttop + nt + nc <= cap) {
+                    if (has) stack[tx ? cap - 1 - (ttop + __popc(bt & below)) : top + __popc(bc & below)] = pk;
+                    top += nc;
+                    ttop += nt;
+                    __syncwarp();
+                    if (ttop >= 32) flush_text(32);
+                } else {
+                    // no room: the round goes to the global overflow list, which the host feeds to the next launch
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(out.overflow_count, (unsigned long long)(nt + nc));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    const unsigned long long idx = base + __popc((bt | bc) & below);
+                    if (has && idx < out.overflow_capacity) out.overflow[idx] = pk;          // host sees overflow_count > capacity and fails loudly
+                }
             }
+        } else {
+            // ---- compact + push children ---------------------------------------------------------------------------
+            uint32_t nchild = __popcll(cmask);
+            uint32_t incl = nchild;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= (uint32_t)o) incl += v;
+            }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (total == 0) continue;
+            uint32_t slot = incl - nchild;
+            Item* dst;
+            unsigned long long* kdst = nullptr;
+            bool drop = false;
+            if (top + total <= cap) {
+                dst = stack + top;
+                if constexpr (ORDERED) kdst = kstack + top;
+                top += total;
+            } else {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(out.overflow_count, (unsigned long long)total);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                dst = out.overflow + base;
+                if constexpr (ORDERED) kdst = out.overflow_keys + base;
+                drop = base + total > out.overflow_capacity;      // host sees overflow_count > capacity and fails loudly
+            }
+            if (cmask && !drop) {
+                unsigned long long rest = cmask;
+                while (rest) {
+                    uint32_t bit = __ffsll((long long)rest) - 1;
+                    rest &= rest - 1;
+                    const State c = make_child(bit);
+                    if constexpr (ORDERED) kdst[slot] = c.key;
+                    dst[slot++] = pack_item(c);
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
+    if (ttop) flush_text(ttop);
 
     // ---- statistics ------------------------------------------------------------------------------------------
     for (int o = 16; o > 0; o >>= 1) {

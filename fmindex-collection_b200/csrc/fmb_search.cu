@@ -13,6 +13,7 @@
 
 #include "fmb_host.hpp"
 #include "fmb_scheme.cuh"
+#include "fmb_text.cuh"
 
 using namespace fmb;
 
@@ -39,6 +40,70 @@ struct EventPair {          // the two timing events of a search call, destroyed
     EventPair(const EventPair&) = delete;
     EventPair& operator=(const EventPair&) = delete;
 };
+
+JumpView make_jump_view(const fmb_index* ix, const fmb_queries* q) {
+    JumpView jv{};
+    static const bool no_jump = getenv("FMB_NO_SCHEME_JUMP") != nullptr;
+    if (!ix->dna && !no_jump) {
+        jv.jump4[0] = ix->jump4[0].p;         // byte-symbol LF^4 tables of the generic layout
+        jv.jump4[1] = ix->jump4[1].p;
+    }
+    if (ix->dna && q->packed.p && !no_jump) {
+        jv.jump[0] = ix->jump[0].p;
+        jv.jump[1] = ix->jump[1].p;
+        jv.jshift[0] = ix->jump_shift[0];
+        jv.jshift[1] = ix->jump_shift[1];
+        jv.jump4[0] = ix->jump4[0].p;
+        jv.jump4[1] = ix->jump4[1].p;
+        jv.qpk = q->packed.p;
+        jv.qflags = q->flags.p;
+        jv.bikmer = ix->bikmer.p;
+        jv.bikmer_k = ix->bikmer.p ? ix->bikmer_k : 0;
+    }
+    return jv;
+}
+
+// edit-distance searches decide single-row intervals on the text (scheme_text_kernel) when the index holds the tables that serve as
+// text windows in both directions: LF^16 entries (sigma <= 5, 2-bit packed queries) or byte-symbol LF^4 entries (generic layout)
+bool text_mode_available(const fmb_index* ix, const fmb_queries* q) {
+    static const bool off = getenv("FMB_NO_TEXT") != nullptr;
+    if (off) return false;
+    const JumpView jv = make_jump_view(ix, q);
+    return ix->dna ? (jv.jump[0] && jv.jump[1] && jv.qpk) : (jv.jump4[0] && jv.jump4[1]);
+}
+
+template <class OCC, bool PSEUDO>
+int launch_text_t(const fmb_index* ix, const IndexView<OCC>& view, const SchemeParams& sp, const fmb_queries* q, const Item* items, uint64_t n_items,
+                  const SchemeOut& out, cudaStream_t st) {
+    auto kern = scheme_text_kernel<OCC, PSEUDO>;
+    static std::mutex cfg_mu;
+    static int cfg_blocks_per_sm[kMaxDevices] = {};
+    int blocks_per_sm;
+    {
+        std::lock_guard<std::mutex> lk(cfg_mu);
+        const int dev = ix->device;
+        if (dev < 0 || dev >= kMaxDevices) { set_error("device %d outside [0,%d)", dev, kMaxDevices); return FMB_EINVAL; }
+        if (!cfg_blocks_per_sm[dev]) {
+            int bps = 0;
+            FMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 256, 0));
+            cfg_blocks_per_sm[dev] = bps < 1 ? 1 : bps;
+        }
+        blocks_per_sm = cfg_blocks_per_sm[dev];
+    }
+    const uint64_t want_blocks = (n_items + 255) / 256;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ix->sm_count * blocks_per_sm, want_blocks));
+    kern<<<grid, 256, 0, st>>>(view, sp, q->symbols.p, q->offsets.p, make_jump_view(ix, q), items, n_items, out);
+    FMB_CUDA(cudaGetLastError());
+    note_launches(1);
+    return FMB_OK;
+}
+int launch_text(const fmb_index* ix, const SchemeParams& sp, const fmb_queries* q, const Item* items, uint64_t n_items, const SchemeOut& out, bool pseudo,
+                cudaStream_t st) {
+    if (ix->dna) return pseudo ? launch_text_t<OccDna, true>(ix, ix->view_dna(), sp, q, items, n_items, out, st)
+                               : launch_text_t<OccDna, false>(ix, ix->view_dna(), sp, q, items, n_items, out, st);
+    return pseudo ? launch_text_t<OccGen, true>(ix, ix->view_gen(), sp, q, items, n_items, out, st)
+                  : launch_text_t<OccGen, false>(ix, ix->view_gen(), sp, q, items, n_items, out, st);
+}
 
 template <class OCC, bool EDIT, bool ORDERED, bool PSEUDO>
 int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const SchemeParams& sp, const fmb_queries* q, uint64_t n_roots, const Item* in_items,
@@ -68,24 +133,7 @@ int launch_scheme_t(const fmb_index* ix, const IndexView<OCC>& view, const Schem
     uint64_t work = n_roots + n_in;
     uint64_t want_blocks = (work + 255) / 256;
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * blocks_per_sm, want_blocks));
-    JumpView jv{};
-    static const bool no_jump = getenv("FMB_NO_SCHEME_JUMP") != nullptr;
-    if (!ix->dna && !no_jump) {
-        jv.jump4[0] = ix->jump4[0].p;         // byte-symbol LF^4 tables of the generic layout
-        jv.jump4[1] = ix->jump4[1].p;
-    }
-    if (ix->dna && q->packed.p && !no_jump) {
-        jv.jump[0] = ix->jump[0].p;
-        jv.jump[1] = ix->jump[1].p;
-        jv.jshift[0] = ix->jump_shift[0];
-        jv.jshift[1] = ix->jump_shift[1];
-        jv.jump4[0] = ix->jump4[0].p;
-        jv.jump4[1] = ix->jump4[1].p;
-        jv.qpk = q->packed.p;
-        jv.qflags = q->flags.p;
-        jv.bikmer = ix->bikmer.p;
-        jv.bikmer_k = ix->bikmer.p ? ix->bikmer_k : 0;
-    }
+    const JumpView jv = make_jump_view(ix, q);
     // a warp keeps fast-forwarding while at least ff_min of its lanes have a single child; edit distance branches
     // at almost every node, so it only pays there when most of the warp is inside error-free stretches
     static const char* ff_env = getenv("FMB_SCHEME_FFMIN");
@@ -209,12 +257,19 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     const uint64_t nq = q->nq;
     const uint64_t n_roots = nq * sp.n_searches;
     uint64_t hit_cap = std::max<uint64_t>(1u << 20, nq * 8);
-    const uint64_t ovf_cap = 1u << 22;       // 4 M items = 128 MB per buffer
-    DevBuf<Item> ovf[2];
+    // Edit distance with text mode: the frontier kernel hands single-row items to the text kernel through a global list and gets
+    // the survivors back through the overflow list, so the lists scale with the number of roots in flight: the roots are processed
+    // in slabs.  Otherwise: all roots at once, the overflow list only takes what the warp stacks cannot hold.
+    const bool text_mode = sp.edit && !ordered && text_mode_available(ix, q);
+    static const uint64_t env_slab = getenv("FMB_SCHEME_SLAB") ? strtoull(getenv("FMB_SCHEME_SLAB"), nullptr, 10) : 0;
+    const uint64_t slab = text_mode ? std::min<uint64_t>(std::max<uint64_t>(n_roots, 1), env_slab ? env_slab : (uint64_t(8) << 20)) : std::max<uint64_t>(n_roots, 1);
+    const uint64_t ovf_cap = text_mode ? std::max<uint64_t>(1u << 20, slab * 2 + (1u << 18)) : (1u << 22);       // items of 32 bytes
+    DevBuf<Item> ovf[2], text_list;
     DevBuf<unsigned long long> ovf_keys[2], hit_keys;
-    DevBuf<unsigned long long> ctr;          // [0..3] counters, [4] hit_count, [5] overflow_count, [6] root_counter
+    DevBuf<unsigned long long> ctr;          // [0..3] counters, [4] hit_count, [5] overflow_count, [6] root_counter, [7] text_count
     FMB_TRY(ovf[0].alloc(ovf_cap));
     FMB_TRY(ovf[1].alloc(ovf_cap));
+    if (text_mode) FMB_TRY(text_list.alloc(ovf_cap));
     if (ordered) {
         FMB_TRY(ovf_keys[0].alloc(ovf_cap));
         FMB_TRY(ovf_keys[1].alloc(ovf_cap));
@@ -238,35 +293,75 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
         so.counters = ctr.p;
         so.root_counter = ctr.p + 6;
         so.qidx_base = (uint32_t)q->qidx_base;
-        uint64_t roots = n_roots, n_in = 0;
-        int cur = 0;
+        if (text_mode) {
+            so.text = text_list.p;
+            so.text_count = ctr.p + 7;
+            so.text_capacity = ovf_cap;
+        }
         cudaEventRecord(ev0, st);
-        for (int pass = 0;; ++pass) {
-            so.overflow = ovf[cur].p;
-            so.overflow_keys = ovf_keys[cur].p;
-            so.in_keys = pass ? ovf_keys[cur ^ 1].p : nullptr;
-            const Item* in_items = pass ? ovf[cur ^ 1].p : nullptr;
-            if (roots + n_in > 0) {
-                int rc = ordered ? (sp.edit ? launch_scheme<true, true>(ix, sp, q, roots, in_items, n_in, so, st)
-                                            : launch_scheme<false, true>(ix, sp, q, roots, in_items, n_in, so, st))
-                         : (pseudo && sp.edit) ? launch_scheme<true, false, true>(ix, sp, q, roots, in_items, n_in, so, st)
-                                 : (sp.edit ? launch_scheme<true, false>(ix, sp, q, roots, in_items, n_in, so, st)
-                                            : launch_scheme<false, false>(ix, sp, q, roots, in_items, n_in, so, st));
-                if (rc) return rc;
+        for (uint64_t root_base = 0; root_base < std::max<uint64_t>(n_roots, 1); root_base += slab) {
+            uint64_t roots = n_roots ? std::min<uint64_t>(slab, n_roots - root_base) : 0, n_in = 0;
+            int cur = 0;
+            so.root_base = root_base;
+            if (root_base) FMB_CUDA(cudaMemsetAsync(ctr.p + 5, 0, 3 * sizeof(unsigned long long), st));   // overflow_count, root_counter, text_count
+            for (int pass = 0;; ++pass) {
+                so.overflow = ovf[cur].p;
+                so.overflow_keys = ovf_keys[cur].p;
+                so.in_keys = pass ? ovf_keys[cur ^ 1].p : nullptr;
+                const Item* in_items = pass ? ovf[cur ^ 1].p : nullptr;
+                static const bool trace = getenv("FMB_TRACE_SCHEME") != nullptr;
+                EventPair tr;
+                if (trace) cudaEventRecord(tr.a, st);
+                if (roots + n_in > 0) {
+                    int rc = ordered ? (sp.edit ? launch_scheme<true, true>(ix, sp, q, roots, in_items, n_in, so, st)
+                                                : launch_scheme<false, true>(ix, sp, q, roots, in_items, n_in, so, st))
+                             : (pseudo && sp.edit) ? launch_scheme<true, false, true>(ix, sp, q, roots, in_items, n_in, so, st)
+                                     : (sp.edit ? launch_scheme<true, false>(ix, sp, q, roots, in_items, n_in, so, st)
+                                                : launch_scheme<false, false>(ix, sp, q, roots, in_items, n_in, so, st));
+                    if (rc) return rc;
+                }
+                if (trace) cudaEventRecord(tr.b, st);
+                FMB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
+                FMB_CUDA(cudaStreamSynchronize(st));
+                if (trace) {
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, tr.a, tr.b);
+                    fprintf(stderr, "[fmb scheme] slab %llu pass %d frontier kernel: %.3f ms, %llu roots + %llu items in -> %llu text, %llu back, %llu hits so far\n",
+                            (unsigned long long)root_base, pass, ms, (unsigned long long)roots, (unsigned long long)n_in, h_ctr[7], h_ctr[5], h_ctr[4]);
+                }
+                if (h_ctr[5] > ovf_cap || h_ctr[7] > ovf_cap) {
+                    set_error("scheme search: frontier lists exceeded %llu items; split the query batch", (unsigned long long)ovf_cap);
+                    return FMB_EOVERFLOW;
+                }
+                if (h_ctr[7]) {
+                    // the single-row items of this pass are decided on the text; what survives joins the overflow list
+                    const unsigned long long n_text = h_ctr[7], back0 = h_ctr[5];
+                    if (trace) cudaEventRecord(tr.a, st);
+                    FMB_TRY(launch_text(ix, sp, q, text_list.p, n_text, so, pseudo, st));
+                    if (trace) cudaEventRecord(tr.b, st);
+                    FMB_CUDA(cudaMemsetAsync(ctr.p + 7, 0, sizeof(unsigned long long), st));
+                    FMB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
+                    FMB_CUDA(cudaStreamSynchronize(st));
+                    h_ctr[7] = 0;
+                    if (trace) {
+                        float ms = 0;
+                        cudaEventElapsedTime(&ms, tr.a, tr.b);
+                        fprintf(stderr, "[fmb scheme] slab %llu pass %d text kernel: %.3f ms, %llu items -> %llu back\n", (unsigned long long)root_base, pass, ms,
+                                n_text, h_ctr[5] - back0);
+                    }
+                    if (h_ctr[5] > ovf_cap) {
+                        set_error("scheme search: frontier lists exceeded %llu items; split the query batch", (unsigned long long)ovf_cap);
+                        return FMB_EOVERFLOW;
+                    }
+                }
+                if (h_ctr[5] == 0) break;
+                // feed the spilled / returned items to the next pass
+                n_in = h_ctr[5];
+                roots = 0;
+                cur ^= 1;
+                FMB_CUDA(cudaMemsetAsync(ctr.p + 5, 0, 3 * sizeof(unsigned long long), st));   // overflow_count, root_counter, text_count
+                if (pass > 100000) { set_error("scheme search did not terminate"); return FMB_ECUDA; }
             }
-            FMB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
-            FMB_CUDA(cudaStreamSynchronize(st));
-            if (h_ctr[5] > ovf_cap) {
-                set_error("scheme search: frontier overflow list exceeded %llu items; split the query batch", (unsigned long long)ovf_cap);
-                return FMB_EOVERFLOW;
-            }
-            if (h_ctr[5] == 0) break;
-            // feed the spilled items to the next pass
-            n_in = h_ctr[5];
-            roots = 0;
-            cur ^= 1;
-            FMB_CUDA(cudaMemsetAsync(ctr.p + 5, 0, 2 * sizeof(unsigned long long), st));   // overflow_count, root_counter
-            if (pass > 100000) { set_error("scheme search did not terminate"); return FMB_ECUDA; }
         }
         cudaEventRecord(ev1, st);
         cudaEventSynchronize(ev1);

@@ -1,0 +1,479 @@
+// fmb_text.cuh -- K3b: edit-distance search on single-row intervals, decided on the TEXT instead of the index.
+//
+// Once the interval of a search is a single row, the search walks one fixed text: the row after t more symbols is LF^t(row) and
+// the symbols it meets are the entries of jump[row], jump[LF^16(row)], ... (16 symbols per 8-byte lookup; LF^4 with byte symbols
+// for the generic layout).  The whole subtree of such a node -- as long as the search keeps its direction -- is therefore a
+// function of (text window, query, scheme): the node state machine of search_ng26 (search_next_pos / search_next_dir_single /
+// search_next_dir_no_errors, search/SearchNg26.h:119-141, 225-365) is run here on the window symbols held in shared memory, with a
+// private depth-first stack per lane, and the index is touched only to fetch the window (one lookup per 16 symbols) and to compute
+// the rows of the few paths that survive.  What leaves the walk goes back to the frontier kernel (scheme_search_kernel) as an item:
+//   * a child whose position advance ends the last part of the direction run (the search turns around or ends): the child exactly
+//     as search_next_dir_single creates it, advance pending                                                    ("turn" items)
+//   * an error-free stretch that ends a part the same way: the state search_next_dir_no_errors leaves (:241-249)
+//   * a node at the end of the window (96 symbols, a delimiter ahead, or the private stack full): the node as it is ("continue")
+//   * an item whose row has no usable window at all (delimiter within the next 16 symbols): the item itself, flagged `notext`
+// The frontier kernel reports the leaves and routes text-class items back here.  Results are identical by construction: this is the
+// same state machine on the same symbols; fmb_stats.extensions still equals the oracle's count (one per node visit, one per symbol
+// of an error-free stretch).
+//
+// Work distribution: one item per LANE, in a flat loop -- every iteration each lane pops one node of its private stack (or takes its
+// next item when the stack is empty) -- so that the lanes of a warp always execute the same loop body although their items need
+// different numbers of node visits.
+#pragma once
+#include "fmb_scheme.cuh"
+
+namespace fmb {
+
+constexpr int kTextWords = 6;        // window words per lane: 96 symbols (2-bit codes) / 24 symbols (bytes)
+constexpr int kTextQWords = 7;       // query words per lane, walking order: 112 / 28 symbols
+constexpr int kTextStage = 64;       // staged items per warp before they are flushed to the global list
+constexpr int kTextStack = 16;       // private depth-first stack (packed nodes)
+#ifndef FMB_TEXT_MINB
+#define FMB_TEXT_MINB 4
+#endif
+
+struct TNode {             // one pending node, "ready to expand" (the position advance already applied)
+    uint32_t m;            // text symbols consumed since the item started: the node looks at window symbol m
+    uint32_t c;            // query symbols consumed since the item started
+    uint32_t part, pev, e;
+    uint32_t T;            // info of the walking side (INFO_*)
+    uint32_t lastRank, lastQRank;
+    uint32_t noerr;        // inside the error-free loop
+    uint32_t kind;         // TN_*: what happens to the node
+};
+// TN_EXPAND: a node of the private stack.  The other kinds are requests to hand the node to the frontier kernel:
+// TN_TURN = a child of search_next_dir_single whose pending position advance ends the direction run (mode POS, NextPos 1),
+// TN_NEXT = the state search_next_dir_no_errors leaves at such a part end (mode NEXT), TN_CONT = the node as it is (window end)
+enum : uint32_t { TN_EXPAND = 0, TN_TURN = 1, TN_NEXT = 2, TN_CONT = 3 };
+__device__ __forceinline__ unsigned long long tnode_pack(const TNode& s) {
+    // m:7 c:8 part:5 pev:16 e:4 T:2 lastRank:8 lastQRank:8 noerr:1 kind:2
+    return (unsigned long long)s.m | ((unsigned long long)s.c << 7) | ((unsigned long long)s.part << 15) | ((unsigned long long)s.pev << 20) |
+           ((unsigned long long)s.e << 36) | ((unsigned long long)s.T << 40) | ((unsigned long long)s.lastRank << 42) |
+           ((unsigned long long)s.lastQRank << 50) | ((unsigned long long)s.noerr << 58) | ((unsigned long long)s.kind << 59);
+}
+__device__ __forceinline__ TNode tnode_unpack(unsigned long long v) {
+    TNode s;
+    s.m = v & 127; s.c = (v >> 7) & 255; s.part = (v >> 15) & 31; s.pev = (v >> 20) & 0xFFFF; s.e = (v >> 36) & 15;
+    s.T = (v >> 40) & 3; s.lastRank = (v >> 42) & 255; s.lastQRank = (v >> 50) & 255; s.noerr = (v >> 58) & 1; s.kind = (v >> 59) & 3;
+    return s;
+}
+
+// reverses the order of the sixteen 2-bit fields of a word
+__device__ __forceinline__ uint32_t rev2(uint32_t w) {
+    w = __brev(w);
+    return ((w & 0xAAAAAAAAu) >> 1) | ((w & 0x55555555u) << 1);
+}
+
+template <class OCC, bool PSEUDO>
+__global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const __grid_constant__ IndexView<OCC> ix, const __grid_constant__ SchemeParams sp,
+                                                                         const uint8_t* __restrict__ qsym, const uint64_t* __restrict__ qoff,
+                                                                         const __grid_constant__ JumpView jv, const Item* __restrict__ items, uint64_t n_items,
+                                                                         const __grid_constant__ SchemeOut out) {
+    constexpr bool BYTES = OCC::kSymbolLoad;
+    constexpr uint32_t B = BYTES ? 8u : 2u;              // bits per symbol
+    constexpr uint32_t SPW = 32u / B;                     // symbols per word
+    constexpr uint32_t SM = (1u << B) - 1u;
+    constexpr uint32_t WCAP = kTextWords * SPW;           // symbols per window
+    constexpr uint32_t QCAP = kTextQWords * SPW;          // query symbols per item
+
+    __shared__ uint32_t sw[(kTextWords + 1) * 256];      // [word][thread]: window symbols in walking order, one zero word behind
+    __shared__ uint32_t sq[(kTextQWords + 1) * 256];     // [word][thread]: query symbols in walking order
+    __shared__ Item stage[8][kTextStage];
+    __shared__ uint32_t stage_cnt[8];
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    const uint32_t np = sp.n_parts;
+    if (lane == 0) stage_cnt[warp] = 0;
+    __syncwarp();
+
+    unsigned long long stk[kTextStack];
+    uint32_t rows[kTextWords + 1];
+    int top = 0;
+    uint32_t n_ext = 0, n_phys = 0;
+    uint64_t next_item = blockIdx.x * (uint64_t)blockDim.x + tid;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+
+    // per item
+    Item it0;                      // the entry state (position advance applied, direction decided), mode POS / NextPos 0
+    uint32_t R = 0, search = 0, have = 0, q_limit = 0;
+    bool closed = false;
+
+    auto dir_of = [&](uint32_t part) -> uint32_t { return (sp.pi[search][part - 1] < sp.pi[search][part]) ? 1u : 0u; };
+    auto stage_emit = [&](const Item& it) {
+        const uint32_t slot = atomicAdd(&stage_cnt[warp], 1u);
+        if (slot < (uint32_t)kTextStage) {
+            stage[warp][slot] = it;
+        } else {
+            atomicSub(&stage_cnt[warp], 1u);
+            const unsigned long long g = atomicAdd(out.overflow_count, 1ull);
+            if (g < out.overflow_capacity) out.overflow[g] = it;
+        }
+    };
+    // one LF step of a single row in direction R
+    auto lf1 = [&](uint32_t row) -> uint32_t {
+        const OCC& occ = ix.occ[R];
+        typename OCC::Block b = occ.load(row >> 6, 0);
+        const uint32_t s = occ.symbol(b, row);
+        if (OCC::kSymbolLoad) b = occ.load(row >> 6, s);
+        n_phys += 1;
+        return ix.C[s] + occ.rank(b, row, s);
+    };
+    // the row after m window symbols (m <= have * SPW)
+    auto row_at = [&](uint32_t m) -> uint32_t {
+        uint32_t row = rows[m / SPW];
+        uint32_t r = m % SPW;
+        if (!BYTES && r >= 4 && jv.jump4[R] != nullptr) {
+            while (r >= 4) {
+                const uint2 e = __ldg(jv.jump4[R] + row);      // valid: the window holds no delimiter
+                n_phys += 1;
+                row = e.x;
+                r -= 4;
+            }
+        }
+        while (r--) row = lf1(row);
+        return row;
+    };
+    // fetches window word `have`; false when the window ends here (full, or a delimiter within the next SPW symbols)
+    auto fetch = [&]() -> bool {
+        if (closed || have == (uint32_t)kTextWords) return false;
+        const uint32_t row = rows[have];
+        const uint2 e = BYTES ? __ldg(jv.jump4[R] + row) : __ldg(jv.jump[R] + ((size_t)row << jv.jshift[R]));
+        n_phys += 1;
+        if (e.x == kJumpInvalid) { closed = true; return false; }
+        uint32_t w = e.y;
+        if (!R) w = BYTES ? __byte_perm(w, 0, 0x0123) : rev2(w);     // direction 0 stores the nearest symbol in the high bits
+        sw[have * 256 + tid] = w;
+        sw[(have + 1) * 256 + tid] = 0;
+        rows[have + 1] = e.x;
+        have += 1;
+        return true;
+    };
+    auto ensure = [&](uint32_t m) -> bool {
+        while (m / SPW >= have)
+            if (!fetch()) return false;
+        return true;
+    };
+    auto wsym = [&](uint32_t m) -> uint32_t { return ((sw[(m / SPW) * 256 + tid] >> (B * (m % SPW))) & SM) + (BYTES ? 0u : 1u); };
+    auto qsy = [&](uint32_t c) -> uint32_t { return ((sq[(c / SPW) * 256 + tid] >> (B * (c % SPW))) & SM) + (BYTES ? 0u : 1u); };
+    auto wword = [&](uint32_t m) -> uint32_t { return __funnelshift_r(sw[(m / SPW) * 256 + tid], sw[(m / SPW + 1) * 256 + tid], B * (m % SPW)); };
+    auto qword = [&](uint32_t c) -> uint32_t { return __funnelshift_r(sq[(c / SPW) * 256 + tid], sq[(c / SPW + 1) * 256 + tid], B * (c % SPW)); };
+
+    // requests of the current iteration to hand a node to the frontier kernel (served at ONE place below: the row computation and the
+    // item packing are not replicated into every branch of the state machine)
+    unsigned long long req[4];
+    int nreq = 0;
+    auto request = [&](TNode s, uint32_t kind) {
+        s.kind = kind;
+        req[nreq++] = tnode_pack(s);
+    };
+    auto push = [&](TNode s) {
+        s.kind = TN_EXPAND;
+        if (top < kTextStack) stk[top++] = tnode_pack(s);
+        else request(s, TN_CONT);
+    };
+    // nodes of the current iteration that can only continue error free -- children whose error count has reached the bound of their
+    // part (their own visit still pending: noerr == 0) and error-free stretches to walk (noerr == 1); evaluated right after the visit
+    // instead of going through the stack
+    unsigned long long lc[3];
+    int nlc = 0;
+    // a child of node `s`; adv: the child consumes the query symbol (position advance of search_next_pos)
+    auto spawn = [&](TNode ch, bool adv) {
+        if (adv) {
+            if (ch.pev == 1) {                                           // the advance ends the part
+                const uint32_t next = ch.part + 1;
+                if (next == np || sp.force_left || dir_of(next) != R) {
+                    // the search ends or turns around: the child as search_next_dir_single creates it, advance pending
+                    request(ch, TN_TURN);
+                    return;
+                }
+                ch.part = next;
+                ch.pev = sp.partition[sp.pi[search][next]];
+            } else {
+                ch.pev -= 1;
+            }
+            ch.c += 1;
+        }
+        if (ch.e >= sp.u[search][ch.part]) { ch.kind = TN_EXPAND; lc[nlc++] = tnode_pack(ch); }
+        else push(ch);
+    };
+    // search_next_dir_no_errors (:225-250) from (m, c) with `rem` symbols left in the part, SPW symbols per comparison
+    auto run_noerr = [&](uint32_t m, uint32_t c, uint32_t part, uint32_t rem, uint32_t e, const TNode& origin) {
+        for (;;) {
+            if (c >= q_limit || !ensure(m)) {
+                TNode s = origin;
+                s.m = m; s.c = c; s.part = part; s.pev = rem; s.e = e; s.noerr = 1;
+                request(s, TN_CONT);
+                return;
+            }
+            uint32_t n = have * SPW - m;
+            n = n < SPW ? n : SPW;
+            n = n < rem ? n : rem;
+            n = n < q_limit - c ? n : q_limit - c;
+            const uint32_t x = wword(m) ^ qword(c);
+            uint32_t first = SPW;
+            if (BYTES) {
+                uint32_t y = x | (x >> 4);
+                y |= y >> 2;
+                y |= y >> 1;
+                y &= 0x01010101u;
+                if (y) first = (uint32_t)(__ffs(y) - 1) / 8u;
+            } else {
+                const uint32_t y = (x | (x >> 1)) & 0x55555555u;
+                if (y) first = (uint32_t)(__ffs(y) - 1) / 2u;
+            }
+            if (first < n) { n_ext += first + 1; return; }              // the path dies at that symbol
+            n_ext += n;
+            m += n; c += n; rem -= n;
+            if (rem == 0) {                                              // :241-249
+                const uint32_t lastq = qsy(c - 1);
+                const uint32_t next = part + 1;
+                const uint32_t npev = (next != np) ? sp.partition[sp.pi[search][next]] : 0u;
+                TNode s;
+                s.m = m; s.c = c; s.part = next; s.pev = npev; s.e = e; s.T = INFO_M; s.lastRank = lastq; s.lastQRank = lastq; s.noerr = 0;
+                if (next == np || sp.force_left || dir_of(next) != R) request(s, TN_NEXT);
+                else push(s);
+                return;
+            }
+        }
+    };
+
+    bool finished = false;
+    for (;;) {
+        __syncwarp();
+        // ---- flush the warp's staged items -------------------------------------------------------------------------------
+        {
+            const uint32_t n = stage_cnt[warp];
+            const bool all_done = __all_sync(0xFFFFFFFFu, finished && top == 0);
+            if (n >= 32 || (all_done && n > 0)) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(out.overflow_count, (unsigned long long)n);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                for (uint32_t i = lane; i < n; i += 32)
+                    if (base + i < out.overflow_capacity) out.overflow[base + i] = stage[warp][i];
+                __syncwarp();
+                if (lane == 0) stage_cnt[warp] = 0;
+                __syncwarp();
+            }
+            if (all_done) break;
+        }
+        // ---- next item ------------------------------------------------------------------------------------------------------
+        if (top == 0 && !finished) {
+            if (next_item >= n_items) {
+                finished = true;
+            } else {
+                const Item it = items[next_item];
+                next_item += stride;
+                State st = unpack_item(it);
+                bool ok = st.len == 1 && st.mode != MODE_NOERR;
+                if (ok && st.mode == MODE_POS && st.NextPos) {                                     // search_next_pos :119-141
+                    if (st.Right) st.qposR = (st.qposR + 1) & 0xFFFF; else st.qposL = (st.qposL - 1) & 0xFFFF;
+                    st.pev -= 1;
+                    if (st.pev == 0) {
+                        st.part += 1;
+                        if (st.part != np) st.pev = sp.partition[sp.pi[st.search][st.part]];
+                        st.mode = MODE_NEXT;
+                    }
+                }
+                if (ok && st.mode == MODE_NEXT) {                                                   // search_next :98-117
+                    if (st.part == np) ok = false;                                                  // a leaf: the frontier kernel reports it
+                    else {
+                        st.Right = (st.part == 0) || (sp.pi[st.search][st.part - 1] < sp.pi[st.search][st.part]);
+                        if (sp.force_left) st.Right = 0;
+                    }
+                }
+                if (ok) {
+                    R = st.Right;
+                    search = st.search;
+                    rows[0] = R ? st.lb_rev : st.lb;
+                    have = 0;
+                    closed = false;
+                    ok = fetch();
+                }
+                if (!ok) {
+                    Item back = it;
+                    back.meta |= 0x80u;                      // notext: expand this one on the index
+                    stage_emit(back);
+                } else {
+                    st.mode = MODE_POS; st.NextPos = 0; st.notext = 0;
+                    it0 = pack_item(st);
+                    // query symbols of this direction run in walking order
+                    const uint64_t qbase = qoff[st.qidx];
+                    const uint32_t qlen = (uint32_t)(qoff[st.qidx + 1] - qbase);
+                    const uint32_t run = R ? qlen - st.qposR : st.qposL + 1;
+                    q_limit = run < QCAP ? run : QCAP;
+                    const uint32_t nw = (q_limit + SPW - 1) / SPW;
+                    for (uint32_t k = 0; k < (uint32_t)kTextQWords + 1; ++k) {
+                        uint32_t w = 0;
+                        if (k < nw) {
+                            if (BYTES) {
+                                for (uint32_t j = 0; j < 4; ++j) {
+                                    const long long at = R ? (long long)(qbase + st.qposR + 4 * k + j) : (long long)(qbase + st.qposL) - (long long)(4 * k + j);
+                                    const uint32_t b = (at >= 0 && 4 * k + j < run) ? __ldg(qsym + at) : 0u;
+                                    w |= b << (8 * j);
+                                }
+                            } else if (R) {
+                                const uint64_t bit = 2 * (qbase + st.qposR + 16 * k);
+                                const uint32_t wi = (uint32_t)(bit >> 5);
+                                w = __funnelshift_r(__ldg(jv.qpk + wi), __ldg(jv.qpk + wi + 1), (uint32_t)bit & 31u);
+                            } else {
+                                // walking symbols 16k .. 16k+15 are the forward symbols qposL-16k-15 .. qposL-16k, reversed
+                                const long long p0 = (long long)(qbase + st.qposL) - (long long)(16 * k + 15);
+                                uint32_t v;
+                                if (p0 >= 0) {
+                                    const uint64_t bit = 2 * (uint64_t)p0;
+                                    const uint32_t wi = (uint32_t)(bit >> 5);
+                                    v = __funnelshift_r(__ldg(jv.qpk + wi), __ldg(jv.qpk + wi + 1), (uint32_t)bit & 31u);
+                                } else {
+                                    v = __ldg(jv.qpk) << (2 * (uint32_t)(-p0));      // before the first query: those fields are never read
+                                }
+                                w = rev2(v);
+                            }
+                        }
+                        sq[k * 256 + tid] = w;
+                    }
+                    TNode root;
+                    root.m = 0; root.c = 0; root.part = st.part; root.pev = st.pev; root.e = st.e;
+                    root.T = R ? st.RInfo : st.LInfo;
+                    root.lastRank = side_get(st.side, R, 0); root.lastQRank = side_get(st.side, R, 1);
+                    root.noerr = 0; root.kind = TN_EXPAND;
+                    stk[top++] = tnode_pack(root);
+                }
+            }
+        }
+        // ---- one node ----------------------------------------------------------------------------------------------------------
+        if (top > 0) {
+            const TNode s = tnode_unpack(stk[--top]);
+            if (s.noerr) {
+                lc[nlc++] = tnode_pack(s);
+            } else if (s.c >= q_limit || !ensure(s.m)) {
+                request(s, TN_CONT);                                     // the window ends here: the frontier kernel continues
+            } else {
+                // ---- search_next_dir_single :251-365
+                const uint32_t lp = sp.l[search][s.part], up = sp.u[search][s.part];
+                const uint32_t sym = wsym(s.m), q = qsy(s.c);
+                const bool Deletion = PSEUDO || (s.T != INFO_S && s.T != INFO_I);
+                const bool Insertion = PSEUDO || (s.T != INFO_S && s.T != INFO_D);
+                const bool insAllowed = (s.pev > 1 || lp <= s.e + 1) && s.e + 1 <= up;
+                const bool mismatchAllowed = s.e + 1 <= up;
+                const bool matchAllowed = (s.pev > 1 || lp <= s.e) && s.e <= up &&
+                                          (PSEUDO || ((s.T != INFO_I || q != s.lastQRank) && (s.T != INFO_D || q != s.lastRank)));
+                n_ext += 1;
+                if (sym == q) {
+                    if (matchAllowed) {
+                        if (!mismatchAllowed) {
+                            TNode ch = s;                                // same node again inside the error-free loop (:311-315)
+                            ch.noerr = 1;
+                            lc[nlc++] = tnode_pack(ch);
+                        } else {
+                            TNode ch = s;
+                            ch.m += 1; ch.lastRank = q; ch.lastQRank = q; ch.T = INFO_M;
+                            if (!PSEUDO && s.e + 1 == up && s.pev > 2) {
+                                // Last error level, inside the part: while the text keeps matching, every node (after a match, not at
+                                // the part's last symbol) has the same three visits -- itself, its deletion child (dies: it would
+                                // have to match the symbol it just deleted, :275) and its insertion child (dies: it would have to
+                                // match the symbol it just inserted) -- so the matching stretch is skipped SPW symbols per comparison.
+                                uint32_t skipped = 0, room = s.pev - 2;           // nodes that may be skipped: the part's last stays
+                                uint32_t m = s.m + 1, c = s.c + 1;
+                                while (room && c < q_limit && ensure(m)) {
+                                    uint32_t n = have * SPW - m;
+                                    n = n < SPW ? n : SPW;
+                                    n = n < room ? n : room;
+                                    n = n < q_limit - c ? n : q_limit - c;
+                                    const uint32_t x = wword(m) ^ qword(c);
+                                    uint32_t first = SPW;
+                                    if (BYTES) {
+                                        uint32_t y = x | (x >> 4);
+                                        y |= y >> 2;
+                                        y |= y >> 1;
+                                        y &= 0x01010101u;
+                                        if (y) first = (uint32_t)(__ffs(y) - 1) / 8u;
+                                    } else {
+                                        const uint32_t y = (x | (x >> 1)) & 0x55555555u;
+                                        if (y) first = (uint32_t)(__ffs(y) - 1) / 2u;
+                                    }
+                                    const uint32_t adv = first < n ? first : n;
+                                    skipped += adv; m += adv; c += adv; room -= adv;
+                                    if (first < n) break;
+                                }
+                                if (skipped) {
+                                    n_ext += 3 * skipped;
+                                    ch.m += skipped; ch.c += skipped; ch.pev -= skipped;
+                                    ch.lastRank = ch.lastQRank = qsy(ch.c);     // the last symbol matched (ch.c is advanced once more below)
+                                }
+                            }
+                            spawn(ch, true);
+                        }
+                    }
+                    if (Deletion && mismatchAllowed) {
+                        TNode ch = s;
+                        ch.m += 1; ch.e += 1; ch.lastRank = sym; ch.T = INFO_D;
+                        spawn(ch, false);
+                    }
+                } else if (mismatchAllowed) {
+                    if (insAllowed) {                                    // substitution
+                        TNode ch = s;
+                        ch.m += 1; ch.e += 1; ch.lastRank = sym; ch.lastQRank = q; ch.T = INFO_S;
+                        spawn(ch, true);
+                    }
+                    if (Deletion) {
+                        TNode ch = s;
+                        ch.m += 1; ch.e += 1; ch.lastRank = sym; ch.T = INFO_D;
+                        spawn(ch, false);
+                    }
+                }
+                if (Insertion && insAllowed) {
+                    TNode ch = s;
+                    ch.e += 1; ch.lastQRank = q; ch.T = INFO_I;
+                    spawn(ch, true);
+                }
+            }
+        }
+        // ---- nodes that can only continue error free ---------------------------------------------------------------------------------
+        for (int i = 0; i < nlc; ++i) {
+            const TNode s = tnode_unpack(lc[i]);
+            if (!s.noerr) {
+                // the node's own visit (search_next_dir_single with no error left): it continues iff its symbol matches
+                if (s.c >= q_limit || !ensure(s.m)) { request(s, TN_CONT); continue; }
+                const uint32_t lp = sp.l[search][s.part], up = sp.u[search][s.part];
+                const uint32_t q = qsy(s.c);
+                n_ext += 1;
+                const bool matchAllowed = (s.pev > 1 || lp <= s.e) && s.e <= up &&
+                                          (PSEUDO || ((s.T != INFO_I || q != s.lastQRank) && (s.T != INFO_D || q != s.lastRank)));
+                if (wsym(s.m) != q || !matchAllowed) continue;
+            }
+            run_noerr(s.m, s.c, s.part, s.pev, s.e, s);
+        }
+        nlc = 0;
+        // ---- hand-overs: the entry state moved to (m, c) with the node's fields --------------------------------------------------
+        for (int i = 0; i < nreq; ++i) {
+            const TNode s = tnode_unpack(req[i]);
+            State ch = unpack_item(it0);
+            const uint32_t row = row_at(s.m);
+            if (R) ch.lb_rev = row; else ch.lb = row;
+            ch.steps += s.m;
+            if (R) ch.qposR = (ch.qposR + s.c) & 0xFFFF; else ch.qposL = (ch.qposL - s.c) & 0xFFFF;
+            ch.part = s.part; ch.pev = s.pev; ch.e = s.e;
+            if (R) ch.RInfo = s.T; else ch.LInfo = s.T;
+            ch.side = side_set(side_set(ch.side, R, 0, s.lastRank), R, 1, s.lastQRank);
+            ch.mode = s.kind == TN_TURN ? MODE_POS : (s.kind == TN_NEXT ? MODE_NEXT : (s.noerr ? MODE_NOERR : MODE_POS));
+            ch.NextPos = s.kind == TN_TURN ? 1u : 0u;
+            ch.Right = R; ch.notext = 0;
+            stage_emit(pack_item(ch));
+        }
+        nreq = 0;
+    }
+
+    // ---- statistics: every visit / compared symbol is one extension and one occ lookup of the reference's walk -------------------
+    for (int o = 16; o > 0; o >>= 1) {
+        n_ext += __shfl_xor_sync(0xFFFFFFFFu, n_ext, o);
+        n_phys += __shfl_xor_sync(0xFFFFFFFFu, n_phys, o);
+    }
+    if (lane == 0) {
+        atomicAdd(out.counters + 0, (unsigned long long)n_ext);
+        atomicAdd(out.counters + 1, (unsigned long long)n_ext);
+        atomicAdd(out.counters + 2, (unsigned long long)n_phys);
+    }
+}
+
+}  // namespace fmb

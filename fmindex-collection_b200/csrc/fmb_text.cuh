@@ -45,6 +45,9 @@ struct TNode {             // one pending node, "ready to expand" (the position 
 // TN_TURN = a child of search_next_dir_single whose pending position advance ends the direction run (mode POS, NextPos 1),
 // TN_NEXT = the state search_next_dir_no_errors leaves at such a part end (mode NEXT), TN_CONT = the node as it is (window end)
 enum : uint32_t { TN_EXPAND = 0, TN_TURN = 1, TN_NEXT = 2, TN_CONT = 3 };
+// kinds of the queued comparisons along a diagonal: LC_VISIT = a node without errors left (its own visit, then error free),
+// LC_RUN = an error-free stretch, LC_SKIP = the matching stretch of a path at its last error level
+enum : uint32_t { LC_VISIT = 0, LC_RUN = 1, LC_SKIP = 2 };
 __device__ __forceinline__ unsigned long long tnode_pack(const TNode& s) {
     // m:7 c:8 part:5 pev:16 e:4 T:2 lastRank:8 lastQRank:8 noerr:1 kind:2
     return (unsigned long long)s.m | ((unsigned long long)s.c << 7) | ((unsigned long long)s.part << 15) | ((unsigned long long)s.pev << 20) |
@@ -159,10 +162,11 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
     auto wword = [&](uint32_t m) -> uint32_t { return __funnelshift_r(sw[(m / SPW) * 256 + tid], sw[(m / SPW + 1) * 256 + tid], B * (m % SPW)); };
     auto qword = [&](uint32_t c) -> uint32_t { return __funnelshift_r(sq[(c / SPW) * 256 + tid], sq[(c / SPW + 1) * 256 + tid], B * (c % SPW)); };
 
-    // requests of the current iteration to hand a node to the frontier kernel (served at ONE place below: the row computation and the
-    // item packing are not replicated into every branch of the state machine)
-    unsigned long long req[4];
-    int nreq = 0;
+    // Pending hand-overs of this lane's item to the frontier kernel (served in bulk, see the R phase below), the nodes visited in
+    // the current iteration (the popped node and those of its children whose own children can only continue error free) and the
+    // comparisons along a diagonal queued by those visits.
+    unsigned long long req[24], lc[12], mini[4];
+    int nreq = 0, nlc = 0, nmini = 0;
     auto request = [&](TNode s, uint32_t kind) {
         s.kind = kind;
         req[nreq++] = tnode_pack(s);
@@ -172,45 +176,22 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
         if (top < kTextStack) stk[top++] = tnode_pack(s);
         else request(s, TN_CONT);
     };
-    // nodes of the current iteration that can only continue error free -- children whose error count has reached the bound of their
-    // part (their own visit still pending: noerr == 0) and error-free stretches to walk (noerr == 1); evaluated right after the visit
-    // instead of going through the stack
-    unsigned long long lc[3];
-    int nlc = 0;
-    // a child of node `s`; adv: the child consumes the query symbol (position advance of search_next_pos)
-    auto spawn = [&](TNode ch, bool adv) {
-        if (adv) {
-            if (ch.pev == 1) {                                           // the advance ends the part
-                const uint32_t next = ch.part + 1;
-                if (next == np || sp.force_left || dir_of(next) != R) {
-                    // the search ends or turns around: the child as search_next_dir_single creates it, advance pending
-                    request(ch, TN_TURN);
-                    return;
-                }
-                ch.part = next;
-                ch.pev = sp.partition[sp.pi[search][next]];
-            } else {
-                ch.pev -= 1;
-            }
-            ch.c += 1;
-        }
-        if (ch.e >= sp.u[search][ch.part]) { ch.kind = TN_EXPAND; lc[nlc++] = tnode_pack(ch); }
-        else push(ch);
+    auto queue_run = [&](TNode s, uint32_t kind) {
+        s.kind = kind;
+        lc[nlc++] = tnode_pack(s);
     };
-    // search_next_dir_no_errors (:225-250) from (m, c) with `rem` symbols left in the part, SPW symbols per comparison
-    auto run_noerr = [&](uint32_t m, uint32_t c, uint32_t part, uint32_t rem, uint32_t e, const TNode& origin) {
-        for (;;) {
-            if (c >= q_limit || !ensure(m)) {
-                TNode s = origin;
-                s.m = m; s.c = c; s.part = part; s.pev = rem; s.e = e; s.noerr = 1;
-                request(s, TN_CONT);
-                return;
-            }
-            uint32_t n = have * SPW - m;
+    // symbols that match from (m, c), at most `limit`; status 0: stopped at a mismatch, 1: limit reached, 2: the window or the loaded
+    // part of the query ends at m + result / c + result
+    auto match_run = [&](uint32_t m, uint32_t c, uint32_t limit, uint32_t& status) -> uint32_t {
+        uint32_t done = 0;
+        status = 1;
+        while (done < limit) {
+            if (c + done >= q_limit || !ensure(m + done)) { status = 2; break; }
+            uint32_t n = have * SPW - (m + done);
             n = n < SPW ? n : SPW;
-            n = n < rem ? n : rem;
-            n = n < q_limit - c ? n : q_limit - c;
-            const uint32_t x = wword(m) ^ qword(c);
+            n = n < limit - done ? n : limit - done;
+            n = n < q_limit - (c + done) ? n : q_limit - (c + done);
+            const uint32_t x = wword(m + done) ^ qword(c + done);
             uint32_t first = SPW;
             if (BYTES) {
                 uint32_t y = x | (x >> 4);
@@ -222,29 +203,20 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                 const uint32_t y = (x | (x >> 1)) & 0x55555555u;
                 if (y) first = (uint32_t)(__ffs(y) - 1) / 2u;
             }
-            if (first < n) { n_ext += first + 1; return; }              // the path dies at that symbol
-            n_ext += n;
-            m += n; c += n; rem -= n;
-            if (rem == 0) {                                              // :241-249
-                const uint32_t lastq = qsy(c - 1);
-                const uint32_t next = part + 1;
-                const uint32_t npev = (next != np) ? sp.partition[sp.pi[search][next]] : 0u;
-                TNode s;
-                s.m = m; s.c = c; s.part = next; s.pev = npev; s.e = e; s.T = INFO_M; s.lastRank = lastq; s.lastQRank = lastq; s.noerr = 0;
-                if (next == np || sp.force_left || dir_of(next) != R) request(s, TN_NEXT);
-                else push(s);
-                return;
-            }
+            if (first < n) { done += first; status = 0; break; }
+            done += n;
         }
+        return done;
     };
 
-    bool finished = false;
     for (;;) {
         __syncwarp();
         // ---- flush the warp's staged items -------------------------------------------------------------------------------
+        const bool busy = top > 0;
+        const bool wants = !busy && (nreq > 0 || next_item < n_items);          // this lane needs the R / I phases to go on
         {
             const uint32_t n = stage_cnt[warp];
-            const bool all_done = __all_sync(0xFFFFFFFFu, finished && top == 0);
+            const bool all_done = !__any_sync(0xFFFFFFFFu, busy || wants);
             if (n >= 32 || (all_done && n > 0)) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(out.overflow_count, (unsigned long long)n);
@@ -257,11 +229,32 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
             }
             if (all_done) break;
         }
-        // ---- next item ------------------------------------------------------------------------------------------------------
-        if (top == 0 && !finished) {
-            if (next_item >= n_items) {
-                finished = true;
-            } else {
+        // ---- R / I phases: the rare, expensive steps (row computation + item packing; item fetch + query window) run when a quarter
+        //      of the warp waits for them -- or nobody can go on otherwise -- so that their instructions are issued for many lanes
+        const uint32_t n_wants = __popc(__ballot_sync(0xFFFFFFFFu, wants));
+        const bool serve = n_wants >= 8 || (n_wants > 0 && !__any_sync(0xFFFFFFFFu, busy)) || __any_sync(0xFFFFFFFFu, nreq >= 4);
+        if (serve) {
+            // ---- R: hand-overs: the entry state moved to (m, c) with the node's fields
+            for (int i = 0; __any_sync(0xFFFFFFFFu, i < nreq); ++i) {
+                if (i < nreq) {
+                    const TNode s = tnode_unpack(req[i]);
+                    State ch = unpack_item(it0);
+                    const uint32_t row = row_at(s.m);
+                    if (R) ch.lb_rev = row; else ch.lb = row;
+                    ch.steps += s.m;
+                    if (R) ch.qposR = (ch.qposR + s.c) & 0xFFFF; else ch.qposL = (ch.qposL - s.c) & 0xFFFF;
+                    ch.part = s.part; ch.pev = s.pev; ch.e = s.e;
+                    if (R) ch.RInfo = s.T; else ch.LInfo = s.T;
+                    ch.side = side_set(side_set(ch.side, R, 0, s.lastRank), R, 1, s.lastQRank);
+                    ch.mode = s.kind == TN_TURN ? MODE_POS : (s.kind == TN_NEXT ? MODE_NEXT : (s.noerr ? MODE_NOERR : MODE_POS));
+                    ch.NextPos = s.kind == TN_TURN ? 1u : 0u;
+                    ch.Right = R; ch.notext = 0;
+                    stage_emit(pack_item(ch));
+                }
+            }
+            nreq = 0;
+            // ---- I: next item
+            if (top == 0 && next_item < n_items) {
                 const Item it = items[next_item];
                 next_item += stride;
                 State st = unpack_item(it);
@@ -341,98 +334,87 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                 }
             }
         }
-        // ---- one node ----------------------------------------------------------------------------------------------------------
-        if (top > 0) {
-            const TNode s = tnode_unpack(stk[--top]);
-            if (s.noerr) {
-                lc[nlc++] = tnode_pack(s);
-            } else if (s.c >= q_limit || !ensure(s.m)) {
-                request(s, TN_CONT);                                     // the window ends here: the frontier kernel continues
-            } else {
-                // ---- search_next_dir_single :251-365
-                const uint32_t lp = sp.l[search][s.part], up = sp.u[search][s.part];
-                const uint32_t sym = wsym(s.m), q = qsy(s.c);
-                const bool Deletion = PSEUDO || (s.T != INFO_S && s.T != INFO_I);
-                const bool Insertion = PSEUDO || (s.T != INFO_S && s.T != INFO_D);
-                const bool insAllowed = (s.pev > 1 || lp <= s.e + 1) && s.e + 1 <= up;
-                const bool mismatchAllowed = s.e + 1 <= up;
-                const bool matchAllowed = (s.pev > 1 || lp <= s.e) && s.e <= up &&
-                                          (PSEUDO || ((s.T != INFO_I || q != s.lastQRank) && (s.T != INFO_D || q != s.lastRank)));
-                n_ext += 1;
-                if (sym == q) {
-                    if (matchAllowed) {
-                        if (!mismatchAllowed) {
-                            TNode ch = s;                                // same node again inside the error-free loop (:311-315)
-                            ch.noerr = 1;
-                            lc[nlc++] = tnode_pack(ch);
-                        } else {
-                            TNode ch = s;
-                            ch.m += 1; ch.lastRank = q; ch.lastQRank = q; ch.T = INFO_M;
-                            if (!PSEUDO && s.e + 1 == up && s.pev > 2) {
-                                // Last error level, inside the part: while the text keeps matching, every node (after a match, not at
-                                // the part's last symbol) has the same three visits -- itself, its deletion child (dies: it would
-                                // have to match the symbol it just deleted, :275) and its insertion child (dies: it would have to
-                                // match the symbol it just inserted) -- so the matching stretch is skipped SPW symbols per comparison.
-                                uint32_t skipped = 0, room = s.pev - 2;           // nodes that may be skipped: the part's last stays
-                                uint32_t m = s.m + 1, c = s.c + 1;
-                                while (room && c < q_limit && ensure(m)) {
-                                    uint32_t n = have * SPW - m;
-                                    n = n < SPW ? n : SPW;
-                                    n = n < room ? n : room;
-                                    n = n < q_limit - c ? n : q_limit - c;
-                                    const uint32_t x = wword(m) ^ qword(c);
-                                    uint32_t first = SPW;
-                                    if (BYTES) {
-                                        uint32_t y = x | (x >> 4);
-                                        y |= y >> 2;
-                                        y |= y >> 1;
-                                        y &= 0x01010101u;
-                                        if (y) first = (uint32_t)(__ffs(y) - 1) / 8u;
-                                    } else {
-                                        const uint32_t y = (x | (x >> 1)) & 0x55555555u;
-                                        if (y) first = (uint32_t)(__ffs(y) - 1) / 2u;
-                                    }
-                                    const uint32_t adv = first < n ? first : n;
-                                    skipped += adv; m += adv; c += adv; room -= adv;
-                                    if (first < n) break;
-                                }
-                                if (skipped) {
-                                    n_ext += 3 * skipped;
-                                    ch.m += skipped; ch.c += skipped; ch.pev -= skipped;
-                                    ch.lastRank = ch.lastQRank = qsy(ch.c);     // the last symbol matched (ch.c is advanced once more below)
-                                }
-                            }
-                            spawn(ch, true);
+        // ---- V: the popped node, then those of its children whose own children can only continue error free -----------------------
+        nmini = 0;
+        if (top > 0) mini[nmini++] = stk[--top];
+        for (int vi = 0; __any_sync(0xFFFFFFFFu, vi < nmini); ++vi) {
+            if (vi >= nmini) continue;
+            const TNode s = tnode_unpack(mini[vi]);
+            if (s.noerr) { queue_run(s, LC_RUN); continue; }
+            if (s.c >= q_limit || !ensure(s.m)) { request(s, TN_CONT); continue; }      // the window ends here: the frontier kernel continues
+            // ---- search_next_dir_single :251-365
+            const uint32_t lp = sp.l[search][s.part], up = sp.u[search][s.part];
+            const uint32_t sym = wsym(s.m), q = qsy(s.c);
+            const bool Deletion = PSEUDO || (s.T != INFO_S && s.T != INFO_I);
+            const bool Insertion = PSEUDO || (s.T != INFO_S && s.T != INFO_D);
+            const bool insAllowed = (s.pev > 1 || lp <= s.e + 1) && s.e + 1 <= up;
+            const bool mismatchAllowed = s.e + 1 <= up;
+            const bool matchAllowed = (s.pev > 1 || lp <= s.e) && s.e <= up &&
+                                      (PSEUDO || ((s.T != INFO_I || q != s.lastQRank) && (s.T != INFO_D || q != s.lastRank)));
+            const bool eq = sym == q;
+            n_ext += 1;
+            if (eq && matchAllowed && !mismatchAllowed) {
+                queue_run(s, LC_RUN);                                    // same node again inside the error-free loop (:311-315)
+                continue;
+            }
+            // the three children in one shape: 0 = along the diagonal (match / substitution), 1 = deletion, 2 = insertion
+            const uint32_t exists = ((eq ? (matchAllowed && mismatchAllowed) : (mismatchAllowed && insAllowed)) ? 1u : 0u) |
+                                    ((Deletion && mismatchAllowed) ? 2u : 0u) | ((Insertion && insAllowed) ? 4u : 0u);
+#pragma unroll 1
+            for (uint32_t slot = 0; slot < 3; ++slot) {
+                if (!((exists >> slot) & 1)) continue;
+                TNode ch = s;
+                const bool adv = slot != 1;                              // the child consumes the query symbol (search_next_pos)
+                if (slot != 2) { ch.m += 1; ch.lastRank = sym; }
+                if (slot != 1) ch.lastQRank = q;
+                if (slot != 0 || !eq) ch.e += 1;
+                ch.T = slot == 0 ? (eq ? INFO_M : INFO_S) : (slot == 1 ? INFO_D : INFO_I);
+                if (adv) {
+                    if (ch.pev == 1) {                                   // the advance ends the part
+                        const uint32_t next = ch.part + 1;
+                        if (next == np || sp.force_left || dir_of(next) != R) {
+                            request(ch, TN_TURN);                        // the search ends or turns around: the child as it is, advance pending
+                            continue;
                         }
+                        ch.part = next;
+                        ch.pev = sp.partition[sp.pi[search][next]];
+                    } else {
+                        ch.pev -= 1;
                     }
-                    if (Deletion && mismatchAllowed) {
-                        TNode ch = s;
-                        ch.m += 1; ch.e += 1; ch.lastRank = sym; ch.T = INFO_D;
-                        spawn(ch, false);
-                    }
-                } else if (mismatchAllowed) {
-                    if (insAllowed) {                                    // substitution
-                        TNode ch = s;
-                        ch.m += 1; ch.e += 1; ch.lastRank = sym; ch.lastQRank = q; ch.T = INFO_S;
-                        spawn(ch, true);
-                    }
-                    if (Deletion) {
-                        TNode ch = s;
-                        ch.m += 1; ch.e += 1; ch.lastRank = sym; ch.T = INFO_D;
-                        spawn(ch, false);
-                    }
+                    ch.c += 1;
                 }
-                if (Insertion && insAllowed) {
-                    TNode ch = s;
-                    ch.e += 1; ch.lastQRank = q; ch.T = INFO_I;
-                    spawn(ch, true);
+                const uint32_t cup = sp.u[search][ch.part];
+                if (ch.e >= cup) {
+                    queue_run(ch, LC_VISIT);                             // no error left: its own visit, then error free
+                } else if (!PSEUDO && slot == 0 && eq && ch.e + 1 == cup && ch.pev > 1 && ch.part == s.part) {
+                    queue_run(ch, LC_SKIP);                              // the matching stretch at the last error level is skipped
+                } else if (vi == 0 && !(slot == 0 && eq) && ch.e + 1 == cup && nmini < 4) {
+                    ch.kind = TN_EXPAND;
+                    mini[nmini++] = tnode_pack(ch);                      // visited in this iteration
+                } else {
+                    push(ch);
                 }
             }
         }
-        // ---- nodes that can only continue error free ---------------------------------------------------------------------------------
-        for (int i = 0; i < nlc; ++i) {
-            const TNode s = tnode_unpack(lc[i]);
-            if (!s.noerr) {
+        // ---- L: comparisons along a diagonal -------------------------------------------------------------------------------------------
+        for (int li = 0; __any_sync(0xFFFFFFFFu, li < nlc); ++li) {
+            if (li >= nlc) continue;
+            TNode s = tnode_unpack(lc[li]);
+            uint32_t status;
+            if (s.kind == LC_SKIP) {
+                // Last error level, inside the part, after a match: while the text keeps matching, every node that is not the part's
+                // last has the same three visits -- itself, its deletion child (dies: it would have to match the symbol it just
+                // deleted, :275) and its insertion child (dies: it would have to match the symbol it just inserted).
+                const uint32_t j = match_run(s.m, s.c, s.pev - 1, status);
+                if (j) {
+                    n_ext += 3 * j;
+                    s.m += j; s.c += j; s.pev -= j;
+                    s.lastRank = s.lastQRank = qsy(s.c - 1);
+                }
+                push(s);
+                continue;
+            }
+            if (s.kind == LC_VISIT) {
                 // the node's own visit (search_next_dir_single with no error left): it continues iff its symbol matches
                 if (s.c >= q_limit || !ensure(s.m)) { request(s, TN_CONT); continue; }
                 const uint32_t lp = sp.l[search][s.part], up = sp.u[search][s.part];
@@ -442,26 +424,23 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                                           (PSEUDO || ((s.T != INFO_I || q != s.lastQRank) && (s.T != INFO_D || q != s.lastRank)));
                 if (wsym(s.m) != q || !matchAllowed) continue;
             }
-            run_noerr(s.m, s.c, s.part, s.pev, s.e, s);
+            // search_next_dir_no_errors (:225-250): the rest of the part must match
+            const uint32_t j = match_run(s.m, s.c, s.pev, status);
+            if (status == 0) { n_ext += j + 1; continue; }               // the path dies at that symbol
+            n_ext += j;
+            s.m += j; s.c += j; s.pev -= j;
+            if (status == 2) { s.noerr = 1; request(s, TN_CONT); continue; }
+            {                                                            // :241-249
+                const uint32_t lastq = qsy(s.c - 1);
+                const uint32_t next = s.part + 1;
+                s.part = next;
+                s.pev = (next != np) ? sp.partition[sp.pi[search][next]] : 0u;
+                s.T = INFO_M; s.lastRank = lastq; s.lastQRank = lastq; s.noerr = 0;
+                if (next == np || sp.force_left || dir_of(next) != R) request(s, TN_NEXT);
+                else push(s);
+            }
         }
         nlc = 0;
-        // ---- hand-overs: the entry state moved to (m, c) with the node's fields --------------------------------------------------
-        for (int i = 0; i < nreq; ++i) {
-            const TNode s = tnode_unpack(req[i]);
-            State ch = unpack_item(it0);
-            const uint32_t row = row_at(s.m);
-            if (R) ch.lb_rev = row; else ch.lb = row;
-            ch.steps += s.m;
-            if (R) ch.qposR = (ch.qposR + s.c) & 0xFFFF; else ch.qposL = (ch.qposL - s.c) & 0xFFFF;
-            ch.part = s.part; ch.pev = s.pev; ch.e = s.e;
-            if (R) ch.RInfo = s.T; else ch.LInfo = s.T;
-            ch.side = side_set(side_set(ch.side, R, 0, s.lastRank), R, 1, s.lastQRank);
-            ch.mode = s.kind == TN_TURN ? MODE_POS : (s.kind == TN_NEXT ? MODE_NEXT : (s.noerr ? MODE_NOERR : MODE_POS));
-            ch.NextPos = s.kind == TN_TURN ? 1u : 0u;
-            ch.Right = R; ch.notext = 0;
-            stage_emit(pack_item(ch));
-        }
-        nreq = 0;
     }
 
     // ---- statistics: every visit / compared symbol is one extension and one occ lookup of the reference's walk -------------------

@@ -338,7 +338,7 @@ constexpr int kFastForward = 12;
 #define FMB_SCHEME_MINB 4          // 4 blocks of 256 threads per SM -> 64 registers (a few spills beat the lower occupancy of 80)
 #endif   // consecutive single-child expansions a lane may chain in registers per pop
 
-// Text class: a single-row item of an edit-distance search that still branches (errors possible) and is not a leaf.  Its whole
+// Text class: a single-row item that still branches (errors possible) and is not a leaf.  Its whole
 // subtree in the current direction is decided by the text that follows the row, so the frontier kernel does not expand it: it hands
 // it to scheme_text_kernel through the global text list.  Leaves (they only report), error-free stretches (multi-symbol jumps) and
 // items the text kernel handed back (notext) stay here.
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
     const uint64_t total_roots = n_roots + n_in;
     // the warp's stack has two ends: pending items grow from stack[0] upwards (top of them), text-class items are staged from
     // stack[cap - 1] downwards (ttop of them) and flushed to the global text list 32 at a time
-    constexpr bool kText = EDIT && !ORDERED;          // instantiations that can hand items to the text kernel
+    constexpr bool kText = !ORDERED;                  // instantiations that can hand items to the text kernel
     const bool text_on = kText && out.text != nullptr;
     const uint8_t* text_qflags = OCC::kSymbolLoad ? nullptr : jv.qflags;
     uint32_t top = 0, ttop = 0;

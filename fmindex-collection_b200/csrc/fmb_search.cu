@@ -65,17 +65,17 @@ JumpView make_jump_view(const fmb_index* ix, const fmb_queries* q) {
 
 // edit-distance searches decide single-row intervals on the text (scheme_text_kernel) when the index holds the tables that serve as
 // text windows in both directions: LF^16 entries (sigma <= 5, 2-bit packed queries) or byte-symbol LF^4 entries (generic layout)
-bool text_mode_available(const fmb_index* ix, const fmb_queries* q) {
+bool text_mode_available(const fmb_index* ix, const fmb_queries* q, bool left_only) {
     static const bool off = getenv("FMB_NO_TEXT") != nullptr;
     if (off) return false;
     const JumpView jv = make_jump_view(ix, q);
-    return ix->dna ? (jv.jump[0] && jv.jump[1] && jv.qpk) : (jv.jump4[0] && jv.jump4[1]);
+    return ix->dna ? (jv.jump[0] && (left_only || jv.jump[1]) && jv.qpk) : (jv.jump4[0] && (left_only || jv.jump4[1]));
 }
 
-template <class OCC, bool PSEUDO>
+template <class OCC, bool EDIT, bool PSEUDO>
 int launch_text_t(const fmb_index* ix, const IndexView<OCC>& view, const SchemeParams& sp, const fmb_queries* q, const Item* items, uint64_t n_items,
                   const SchemeOut& out, cudaStream_t st) {
-    auto kern = scheme_text_kernel<OCC, PSEUDO>;
+    auto kern = scheme_text_kernel<OCC, EDIT, PSEUDO>;
     static std::mutex cfg_mu;
     static int cfg_blocks_per_sm[kMaxDevices] = {};
     int blocks_per_sm;
@@ -99,10 +99,12 @@ int launch_text_t(const fmb_index* ix, const IndexView<OCC>& view, const SchemeP
 }
 int launch_text(const fmb_index* ix, const SchemeParams& sp, const fmb_queries* q, const Item* items, uint64_t n_items, const SchemeOut& out, bool pseudo,
                 cudaStream_t st) {
-    if (ix->dna) return pseudo ? launch_text_t<OccDna, true>(ix, ix->view_dna(), sp, q, items, n_items, out, st)
-                               : launch_text_t<OccDna, false>(ix, ix->view_dna(), sp, q, items, n_items, out, st);
-    return pseudo ? launch_text_t<OccGen, true>(ix, ix->view_gen(), sp, q, items, n_items, out, st)
-                  : launch_text_t<OccGen, false>(ix, ix->view_gen(), sp, q, items, n_items, out, st);
+    if (!sp.edit) return ix->dna ? launch_text_t<OccDna, false, false>(ix, ix->view_dna(), sp, q, items, n_items, out, st)
+                                 : launch_text_t<OccGen, false, false>(ix, ix->view_gen(), sp, q, items, n_items, out, st);
+    if (ix->dna) return pseudo ? launch_text_t<OccDna, true, true>(ix, ix->view_dna(), sp, q, items, n_items, out, st)
+                               : launch_text_t<OccDna, true, false>(ix, ix->view_dna(), sp, q, items, n_items, out, st);
+    return pseudo ? launch_text_t<OccGen, true, true>(ix, ix->view_gen(), sp, q, items, n_items, out, st)
+                  : launch_text_t<OccGen, true, false>(ix, ix->view_gen(), sp, q, items, n_items, out, st);
 }
 
 template <class OCC, bool EDIT, bool ORDERED, bool PSEUDO>
@@ -257,10 +259,10 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     const uint64_t nq = q->nq;
     const uint64_t n_roots = nq * sp.n_searches;
     uint64_t hit_cap = std::max<uint64_t>(1u << 20, nq * 8);
-    // Edit distance with text mode: the frontier kernel hands single-row items to the text kernel through a global list and gets
+    // Text mode: the frontier kernel hands single-row items to the text kernel through a global list and gets
     // the survivors back through the overflow list, so the lists scale with the number of roots in flight: the roots are processed
     // in slabs.  Otherwise: all roots at once, the overflow list only takes what the warp stacks cannot hold.
-    const bool text_mode = sp.edit && !ordered && text_mode_available(ix, q);
+    const bool text_mode = !ordered && text_mode_available(ix, q, sp.force_left != 0);
     static const uint64_t env_slab = getenv("FMB_SCHEME_SLAB") ? strtoull(getenv("FMB_SCHEME_SLAB"), nullptr, 10) : 0;
     const uint64_t slab = text_mode ? std::min<uint64_t>(std::max<uint64_t>(n_roots, 1), env_slab ? env_slab : (uint64_t(8) << 20)) : std::max<uint64_t>(n_roots, 1);
     const uint64_t ovf_cap = text_mode ? std::max<uint64_t>(1u << 20, slab * 2 + (1u << 18)) : (1u << 22);       // items of 32 bytes

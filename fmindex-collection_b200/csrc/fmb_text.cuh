@@ -1,4 +1,4 @@
-// fmb_text.cuh -- K3b: edit-distance search on single-row intervals, decided on the TEXT instead of the index.
+// fmb_text.cuh -- K3b: k-error search (edit and Hamming distance) on single-row intervals, decided on the TEXT instead of the index.
 //
 // Once the interval of a search is a single row, the search walks one fixed text: the row after t more symbols is LF^t(row) and
 // the symbols it meets are the entries of jump[row], jump[LF^16(row)], ... (16 symbols per 8-byte lookup; LF^4 with byte symbols
@@ -67,7 +67,7 @@ __device__ __forceinline__ uint32_t rev2(uint32_t w) {
     return ((w & 0xAAAAAAAAu) >> 1) | ((w & 0x55555555u) << 1);
 }
 
-template <class OCC, bool PSEUDO>
+template <class OCC, bool EDIT, bool PSEUDO>
 __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const __grid_constant__ IndexView<OCC> ix, const __grid_constant__ SchemeParams sp,
                                                                          const uint8_t* __restrict__ qsym, const uint64_t* __restrict__ qoff,
                                                                          const __grid_constant__ JumpView jv, const Item* __restrict__ items, uint64_t n_items,
@@ -345,8 +345,8 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
             // ---- search_next_dir_single :251-365
             const uint32_t lp = sp.l[search][s.part], up = sp.u[search][s.part];
             const uint32_t sym = wsym(s.m), q = qsy(s.c);
-            const bool Deletion = PSEUDO || (s.T != INFO_S && s.T != INFO_I);
-            const bool Insertion = PSEUDO || (s.T != INFO_S && s.T != INFO_D);
+            const bool Deletion = EDIT && (PSEUDO || (s.T != INFO_S && s.T != INFO_I));
+            const bool Insertion = EDIT && (PSEUDO || (s.T != INFO_S && s.T != INFO_D));
             const bool insAllowed = (s.pev > 1 || lp <= s.e + 1) && s.e + 1 <= up;
             const bool mismatchAllowed = s.e + 1 <= up;
             const bool matchAllowed = (s.pev > 1 || lp <= s.e) && s.e <= up &&
@@ -386,8 +386,8 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                 const uint32_t cup = sp.u[search][ch.part];
                 if (ch.e >= cup) {
                     queue_run(ch, LC_VISIT);                             // no error left: its own visit, then error free
-                } else if (!PSEUDO && slot == 0 && eq && ch.e + 1 == cup && ch.pev > 1 && ch.part == s.part) {
-                    queue_run(ch, LC_SKIP);                              // the matching stretch at the last error level is skipped
+                } else if (!PSEUDO && slot == 0 && eq && (EDIT ? ch.e + 1 == cup : true) && ch.pev > 1 && ch.part == s.part) {
+                    queue_run(ch, LC_SKIP);                              // the matching stretch (edit distance: at the last error level) is skipped
                 } else if (vi == 0 && !(slot == 0 && eq) && ch.e + 1 == cup && nmini < 4) {
                     ch.kind = TN_EXPAND;
                     mini[nmini++] = tnode_pack(ch);                      // visited in this iteration
@@ -402,12 +402,13 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
             TNode s = tnode_unpack(lc[li]);
             uint32_t status;
             if (s.kind == LC_SKIP) {
-                // Last error level, inside the part, after a match: while the text keeps matching, every node that is not the part's
-                // last has the same three visits -- itself, its deletion child (dies: it would have to match the symbol it just
-                // deleted, :275) and its insertion child (dies: it would have to match the symbol it just inserted).
+                // Edit distance, last error level, inside the part, after a match: while the text keeps matching, every node that is not
+                // the part's last has the same three visits -- itself, its deletion child (dies: it would have to match the symbol it
+                // just deleted, :275) and its insertion child (dies: it would have to match the symbol it just inserted).  Hamming
+                // distance: a matching node has its match child only, at every error level.
                 const uint32_t j = match_run(s.m, s.c, s.pev - 1, status);
                 if (j) {
-                    n_ext += 3 * j;
+                    n_ext += (EDIT ? 3 : 1) * j;
                     s.m += j; s.c += j; s.pev -= j;
                     s.lastRank = s.lastQRank = qsy(s.c - 1);
                 }

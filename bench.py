@@ -451,7 +451,24 @@ def main():
         e2e_qps = q_all * K / e2e_s
         h2d = nq * L + (nq + 1) * 8
         d2h = len(locs) * 16
-        e2e_locs[wl] = (locs, out)
+        e2e_locs[wl] = (locs.copy(), out)       # `out` is reused below
+        # the same call on 2-bit packed host reads (what fmb200/io.hpp produces while parsing FASTA): a quarter of the bytes cross PCIe
+        e2e_packed = None
+        if sigma <= 5:
+            pw = capi.PinnedArray((nq * L + 15) // 16 + 1, np.uint32)
+            packed = capi.pack_queries(sym.array, sigma, words=pw.array)          # untimed: done once, by the reader
+            for _ in range(2):
+                index.search_and_locate(None, off.array, scheme=scheme, partition=partition, edit=edit, out=out.array, packed=packed)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                plocs, _st = index.search_and_locate(None, off.array, scheme=scheme, partition=partition, edit=edit, out=out.array, packed=packed)
+            torch.cuda.synchronize()
+            pk_s = max_over_ranks(time.perf_counter() - t0)
+            e2e_packed = {"value": q_all * K / pk_s, "unit": "queries/s", "h2d_bytes_per_step": pw.array.nbytes + (nq + 1) * 8 + packed[1].nbytes + packed[2].nbytes,
+                          "d2h_bytes_per_step": len(plocs) * 16, "rows_equal_byte_path": int(len(plocs)) == int(len(locs)),
+                          "input": "reads 2-bit packed on the host beforehand (fmb_pack_symbols), fmb_search_and_locate_packed"}
+            pw.free()
 
         # ---- roofline of the dominant kernel (physical; see the module docstring) -------------------------------------------------
         k_ms = float(np.mean(search_ms))
@@ -507,9 +524,49 @@ def main():
                        "workload": describe(wl, nq, L, n_text, sigma, args.rate, k, edit, per),
                        "hits_per_step": n_hits, "located_rows_per_step": n_locs, "roofline": roofline,
                        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                               "frac_of_h2d_ceiling": e2e_qps / world / (nq / (h2d / (h2d_gbs * 1e9)))}}
+                               "frac_of_h2d_ceiling": (e2e_qps / world if not strong else e2e_qps * nq / nq_total) / (nq / (h2d / (h2d_gbs * 1e9)))}}
+        if e2e_packed:
+            results[wl]["e2e_packed"] = e2e_packed
         log(f"{wl}: resident {results[wl]['value'] / 1e6:.1f} M q/s ({ms_per_step:.2f} ms/step, search kernel {k_ms:.2f} ms, locate {l_ms:.2f} ms), "
-            f"e2e {e2e_qps / 1e6:.1f} M q/s, frac {roofline['frac']:.3f}")
+            f"e2e {e2e_qps / 1e6:.1f} M q/s" + (f" (packed {e2e_packed['value'] / 1e6:.1f})" if e2e_packed else "") + f", frac {roofline['frac']:.3f}")
+    # ---- strong scaling (N > 1, default weak run): ONE batch of nq reads split over the ranks -- rank r searches the reads
+    #      [r * nq / N, (r + 1) * nq / N) of its batch; value = nq / max-over-ranks time (BASELINE configs[2]: "sharded queries")
+    strong_rows = None
+    if world > 1 and not strong:
+        strong_rows = {}
+        lo, hi = rank * nq // world, (rank + 1) * nq // world
+        for wl in wls:
+            sym, off = data[wl]
+            scheme, partition, edit, k = scheme_of(wl, L)
+            ssym = sym.array[lo * L: hi * L]
+            soff = (off.array[lo: hi + 1] - off.array[lo]).astype(np.uint64)
+            queries = index.upload(ssym, soff)
+
+            def sstep():
+                res = index.search_exact(queries) if scheme is None else index.search_scheme(queries, scheme, partition, edit)
+                loc = index.locate(res)
+                return len(loc)
+            sstep()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(K):
+                sstep()
+            e1.record(stream)
+            barrier()
+            s_ms = max_over_ranks(e0.elapsed_time(e1)) / K
+            del queries
+            out = e2e_locs[wl][1]
+            index.search_and_locate(ssym, soff, scheme=scheme, partition=partition, edit=edit, out=out.array)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                index.search_and_locate(ssym, soff, scheme=scheme, partition=partition, edit=edit, out=out.array)
+            torch.cuda.synchronize()
+            s_e2e = max_over_ranks(time.perf_counter() - t0) / K
+            strong_rows[wl] = {"reads_total": nq, "reads_per_rank": hi - lo, "ms_per_step": s_ms, "value": nq / (s_ms * 1e-3),
+                               "e2e": nq / s_e2e, "unit": "queries/s"}
+            log(f"{wl} strong scaling ({nq} reads over {world} ranks): resident {nq / (s_ms * 1e-3) / 1e6:.1f} M q/s, e2e {nq / s_e2e / 1e6:.1f} M q/s")
     launches = capi.kernel_launch_count() - launches0
     clocks = sampler.stop()
     clocks["window"] = "warm-up + timed steps + e2e loops of all workloads"
@@ -526,6 +583,8 @@ def main():
             "ceilings": {"random_requests": ceilings, "request_ceiling_per_s": req_ceiling,
                          "pinned_h2d_gbs_per_gpu_all_ranks_concurrent": h2d_gbs, "ranks": world},
             "workloads": results}
+    if strong_rows is not None:
+        line["strong_scaling"] = strong_rows
 
     # ---- CPU baseline + parity: the reference's own search on this box's host cores (rank 0) -------------------------------------
     # N = 1: cpu_baseline (bounded sample, all host threads) + parity on that sample for every workload; N > 1: parity only, on a

@@ -41,11 +41,11 @@ SYMBOLS = [
     "fmb_index_create", "fmb_index_build", "fmb_index_destroy", "fmb_index_get_info", "fmb_index_get_C", "fmb_index_export",
     "fmb_string_symbol", "fmb_string_rank", "fmb_string_prefix_rank", "fmb_string_all_ranks",
     "fmb_cursor_extend", "fmb_cursor_extend_all",
-    "fmb_queries_upload", "fmb_queries_upload_revcomp", "fmb_queries_destroy", "fmb_queries_count",
+    "fmb_queries_upload", "fmb_queries_upload_revcomp", "fmb_queries_upload_packed", "fmb_pack_symbols", "fmb_queries_destroy", "fmb_queries_count",
     "fmb_search_exact", "fmb_search_scheme", "fmb_search_scheme_n", "fmb_search_scheme_pseudo", "fmb_search_backtracking", "fmb_locate", "fmb_locate_rows", "fmb_sample_value",
     "fmb_results_count", "fmb_results_kind", "fmb_results_fetch_hits", "fmb_results_fetch_locs", "fmb_results_fetch_locs32",
     "fmb_results_get_stats", "fmb_results_destroy",
-    "fmb_search_and_locate", "fmb_index_save", "fmb_index_load", "fmb_checksum64",
+    "fmb_search_and_locate", "fmb_search_and_locate_packed", "fmb_search_and_locate_multi", "fmb_index_replicate", "fmb_index_save", "fmb_index_load", "fmb_checksum64",
     "fmb_index_set_exact_mode", "fmb_index_set_locate_mode", "fmb_synth_text_device", "fmb_synth_reads_device", "fmb_synth_reads_err_device", "fmb_synth_repeat_text_device", "fmb_synth_unit_reads_device", "fmb_index_set_stream", "fmb_measure_gather", "fmb_kernel_launch_count", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
 ]
 
@@ -147,6 +147,12 @@ class Index:
                                      C.c_uint32(sampling_rate), C.c_int(1 if bidirectional else 0), C.c_int(1)))
         return cls(h)
 
+    def replicate(self, device):
+        """a replica of the finished device image on another GPU (peer-to-peer copy, no rebuild)"""
+        h = C.c_void_p()
+        _check(lib().fmb_index_replicate(self.h, C.c_int(device), C.byref(h)))
+        return Index(h)
+
     def close(self):
         if self.h:
             lib().fmb_index_destroy(self.h)
@@ -229,10 +235,10 @@ class Index:
         return out
 
     # searches
-    def upload(self, symbols, offsets, complement=None):
+    def upload(self, symbols, offsets, complement=None, packed=None):
         """complement: table of sigma symbols (DNA: [0, 4, 3, 2, 1]) -> the device batch holds every query followed by its reverse
-        complement (2 nq queries, example/utils.h:62-74), built on the device"""
-        return Queries(self, symbols, offsets, complement)
+        complement (2 nq queries, example/utils.h:62-74), built on the device.  packed = pack_queries(symbols): the 2-bit host form"""
+        return Queries(self, symbols, offsets, complement, packed)
 
     def search_exact(self, queries):
         r = C.c_void_p()
@@ -290,10 +296,10 @@ class Index:
         return has, seq, pos
 
     def search_and_locate(self, symbols, offsets, scheme=None, partition=None, edit=False, capacity=None,
-                          out=None):
-        """One-call host-to-host path (fmb_search_and_locate).  symbols/offsets may be numpy arrays or raw
-        (pointer, count) pairs built on pinned memory."""
-        symbols, offsets = _u8(symbols), _u64(offsets)
+                          out=None, packed=None):
+        """One-call host-to-host path (fmb_search_and_locate; with packed = pack_queries(symbols): fmb_search_and_locate_packed,
+        symbols may then be None)."""
+        symbols, offsets = (None if packed is not None else _u8(symbols)), _u64(offsets)
         nq = offsets.size - 1
         if scheme is None:
             ns, npart, pi, l, u, part = 0, 0, None, None, None, None
@@ -305,16 +311,73 @@ class Index:
             out = np.zeros(capacity if capacity is not None else max(nq, 1) * 4, dtype=LOC32_DTYPE)
         n_out = C.c_uint64(0)
         st = Stats()
+        if packed is not None:
+            words, exc_pos, exc_sym = packed
+            words, exc_pos, exc_sym = np.ascontiguousarray(words, dtype=np.uint32), _u64(exc_pos), _u8(exc_sym)
+            _check(lib().fmb_search_and_locate_packed(self.h, _ptr(words), _ptr(offsets), C.c_uint64(nq), _ptr(exc_pos), _ptr(exc_sym),
+                                                      C.c_uint64(exc_pos.size), C.c_int(1 if edit else 0),
+                                                      C.c_uint32(ns), C.c_uint32(npart), _ptr(pi), _ptr(l), _ptr(u), _ptr(part),
+                                                      _ptr(out), C.c_uint64(out.size), C.byref(n_out), C.byref(st)))
+            return out[: n_out.value], st
         _check(lib().fmb_search_and_locate(self.h, _ptr(symbols), _ptr(offsets), C.c_uint64(nq), C.c_int(1 if edit else 0),
                                            C.c_uint32(ns), C.c_uint32(npart), _ptr(pi), _ptr(l), _ptr(u), _ptr(part),
                                            _ptr(out), C.c_uint64(out.size), C.byref(n_out), C.byref(st)))
         return out[: n_out.value], st
 
 
+def pack_queries(symbols, sigma=5, words=None):
+    """2-bit packing of byte symbols (symbol - 1, 16 per little-endian word) + exception list (positions of symbols without 2-bit
+    code: 0 and >= sigma), the input form of fmb_queries_upload_packed / fmb_search_and_locate_packed (host-side fmb_pack_symbols;
+    `words`: optional destination, e.g. a view of pinned memory, of at least (n + 15) // 16 + 1 words)"""
+    s = _u8(symbols)
+    L = lib()
+    L.fmb_pack_symbols.restype = C.c_uint64
+    if words is None:
+        words = np.zeros((s.size + 15) // 16 + 1, dtype=np.uint32)
+    cap = 1024
+    while True:
+        exc_pos, exc_sym = np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint8)
+        n = L.fmb_pack_symbols(_ptr(s), C.c_uint64(0), C.c_uint64(s.size), C.c_uint32(sigma), _ptr(words), _ptr(exc_pos), _ptr(exc_sym), C.c_uint64(cap))
+        if n <= cap:
+            return words, exc_pos[:n].copy(), exc_sym[:n].copy()
+        cap = int(n)
+
+
+def search_and_locate_multi(replicas, symbols, offsets, scheme=None, partition=None, edit=False, shard_capacity=None, out=None):
+    """fmb_search_and_locate_multi: one call, the queries sharded contiguously over the replicas; returns (list of row arrays, stats)"""
+    symbols, offsets = _u8(symbols), _u64(offsets)
+    nq = offsets.size - 1
+    G = len(replicas)
+    if scheme is None:
+        ns, npart, pi, l, u, part = 0, 0, None, None, None, None
+    else:
+        pi, l, u = (np.ascontiguousarray(a, dtype=np.uint32) for a in scheme)
+        part = _u32(partition)
+        ns, npart = pi.shape
+    if shard_capacity is None:
+        shard_capacity = (out.size // G) if out is not None else max((nq + G - 1) // G, 1) * 4
+    if out is None:
+        out = np.zeros(shard_capacity * G, dtype=LOC32_DTYPE)
+    handles = (C.c_void_p * G)(*[r.h for r in replicas])
+    n_out = (C.c_uint64 * G)()
+    st = Stats()
+    _check(lib().fmb_search_and_locate_multi(handles, C.c_uint32(G), _ptr(symbols), _ptr(offsets), C.c_uint64(nq), C.c_int(1 if edit else 0),
+                                             C.c_uint32(ns), C.c_uint32(npart), _ptr(pi), _ptr(l), _ptr(u), _ptr(part),
+                                             _ptr(out), C.c_uint64(shard_capacity), n_out, C.byref(st)))
+    return [out[g * shard_capacity: g * shard_capacity + n_out[g]] for g in range(G)], st
+
+
 class Queries:
-    def __init__(self, index, symbols, offsets, complement=None):
-        symbols, offsets = _u8(symbols), _u64(offsets)
+    def __init__(self, index, symbols, offsets, complement=None, packed=None):
+        offsets = _u64(offsets)
         self.h = C.c_void_p()
+        if packed is not None:
+            words, exc_pos, exc_sym = packed
+            words, exc_pos, exc_sym = np.ascontiguousarray(words, dtype=np.uint32), _u64(exc_pos), _u8(exc_sym)
+            _check(lib().fmb_queries_upload_packed(C.byref(self.h), index.h, _ptr(words), _ptr(offsets), C.c_uint64(offsets.size - 1),
+                                                   _ptr(exc_pos), _ptr(exc_sym), C.c_uint64(exc_pos.size)))
+            return
+        symbols = _u8(symbols)
         if complement is None:
             _check(lib().fmb_queries_upload(C.byref(self.h), index.h, _ptr(symbols), _ptr(offsets), C.c_uint64(offsets.size - 1)))
         else:

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -113,6 +114,9 @@ struct fmb_index {
     fmb::DevBuf<uint4> bikmer;           // bidirectional k-mer table for scheme-search roots
     uint32_t bikmer_k = 0;
     int exact_mode = 0;                  // FMB_EXACT_*
+    // engine of the one-call end-to-end path (persistent worker threads + streams, csrc/fmb_engine.cu), created on first use
+    mutable void* engine = nullptr;
+    mutable std::mutex engine_mu;
 
     fmb::IndexView<fmb::OccDna> view_dna() const;
     fmb::IndexView<fmb::OccGen> view_gen() const;
@@ -125,6 +129,7 @@ namespace fmb {
 // search+locate path, where several host threads drive one index on their own streams) or the index's stream.
 extern thread_local cudaStream_t tls_stream_override;
 inline cudaStream_t active_stream(const fmb_index* ix) { return tls_stream_override ? tls_stream_override : ix->stream; }
+void engine_destroy(fmb_index* ix);   // joins the worker threads of the index's engine, if it has one
 }  // namespace fmb
 
 struct fmb_queries {

@@ -572,6 +572,23 @@ __global__ void __launch_bounds__(256) pack_queries_kernel(const uint8_t* __rest
     }
 }
 
+// 2-bit packed host queries -> byte symbols (fmb_queries_upload_packed): thread t writes the 16 symbols [16 t, 16 t + 16) of the slice;
+// symbol i of the slice is the 2-bit field `shift + i` of the word stream (shift < 16: the slice may start inside a word)
+__global__ void __launch_bounds__(256) unpack_queries_kernel(const uint32_t* __restrict__ words, uint64_t shift, uint64_t total, uint8_t* __restrict__ out) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t * 16 >= total) return;
+    const uint64_t bit = 2 * (shift + t * 16);
+    const uint64_t wi = bit >> 5;
+    const uint32_t lo = words[wi], hi = (bit & 31u) ? words[wi + 1] : 0u;      // the second word exists whenever it is needed
+    const uint32_t v = __funnelshift_r(lo, hi, (uint32_t)bit & 31u);
+    for (uint32_t i = 0; i < 16 && t * 16 + i < total; ++i) out[t * 16 + i] = (uint8_t)(((v >> (2 * i)) & 3u) + 1u);
+}
+// symbols without 2-bit code (the delimiter, anything >= sigma): listed by position in the whole batch
+__global__ void apply_exceptions_kernel(const uint64_t* __restrict__ pos, const uint8_t* __restrict__ sym, uint64_t count, uint64_t first, uint8_t* __restrict__ out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < count) out[pos[i] - first] = sym[i];
+}
+
 // LF^16 jump table by pointer doubling: J1[row] = {LF(row), BWT[row]-1};  J2k[row] = {J_k[J_k[row].x].x, syms << 2k | syms'}
 // (the farthest symbol ends up in the low bits: the order of the 2-bit packed query stream)
 // DNA layout: 2-bit codes (symbol - 1); generic layout: the symbol itself in 8 bits (compared with the raw query bytes)

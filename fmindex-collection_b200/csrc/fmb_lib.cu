@@ -630,6 +630,14 @@ int new_index(fmb_index** out, int device, uint32_t sigma, uint64_t n, bool bidi
 }
 
 template <typename T>
+static int replicate_buf(DevBuf<T>& dst, const DevBuf<T>& src, int dst_dev, int src_dev, cudaStream_t st) {
+    if (!src.p) return FMB_OK;
+    FMB_TRY(dst.alloc(src.n));
+    FMB_CUDA(cudaMemcpyPeerAsync(dst.p, dst_dev, src.p, src_dev, src.bytes(), st));
+    return FMB_OK;
+}
+
+template <typename T>
 static int upload(DevBuf<T>& buf, const T* host, size_t count, cudaStream_t st) {
     FMB_TRY(buf.alloc(count));
     if (count) FMB_CUDA(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, st));
@@ -706,8 +714,65 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, co
     return FMB_OK;
 }
 
+// Copies the finished device image to another GPU (peer-to-peer when the two devices allow it; cudaMemcpyPeer stages through the
+// host otherwise): a replica costs one pass over the image instead of another build.
+int fmb_index_replicate(const fmb_index* src, int device, fmb_index** out) {
+    if (!src || !out) { set_error("NULL argument"); return FMB_EINVAL; }
+    *out = nullptr;
+    if (device == src->device) { set_error("replica on the device of the original (%d)", device); return FMB_EINVAL; }
+    fmb_index* ix = nullptr;
+    FMB_TRY(new_index(&ix, device, src->sigma, src->n, src->bidirectional));      // makes `device` current
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
+        cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0);
+        if (pe != cudaSuccess) cudaGetLastError();                                  // already enabled, or not possible: the copies still work
+    }
+    cudaGetLastError();
+    auto fail = [&](int rc) { fmb_index_destroy(ix); return rc; };
+    cudaStream_t st = ix->stream;
+    // the source image must be complete before it is read
+    {
+        cudaError_t se = cudaSetDevice(src->device);
+        if (se == cudaSuccess) se = cudaStreamSynchronize(src->stream);
+        if (se == cudaSuccess) se = cudaSetDevice(device);
+        if (se != cudaSuccess) { set_error("fmb_index_replicate: %s", cudaGetErrorString(se)); return fail(FMB_ECUDA); }
+    }
+    int rc = FMB_OK;
+    for (int d = 0; d < 2 && !rc; ++d) {
+        if (!rc) rc = replicate_buf(ix->occ_dna[d], src->occ_dna[d], device, src->device, st);
+        if (!rc) rc = replicate_buf(ix->occ_gen[d], src->occ_gen[d], device, src->device, st);
+        if (!rc) rc = replicate_buf(ix->delim_rows[d], src->delim_rows[d], device, src->device, st);
+        if (!rc) rc = replicate_buf(ix->occ2[d], src->occ2[d], device, src->device, st);
+        if (!rc) rc = replicate_buf(ix->specials[d], src->specials[d], device, src->device, st);
+        if (!rc) rc = replicate_buf(ix->jump[d], src->jump[d], device, src->device, st);
+        if (!rc) rc = replicate_buf(ix->jump4[d], src->jump4[d], device, src->device, st);
+        ix->delim0[d] = src->delim0[d];
+        ix->n_specials[d] = src->n_specials[d];
+        ix->jump_shift[d] = src->jump_shift[d];
+        for (int i = 0; i < 2; ++i) ix->special01[d][i] = src->special01[d][i];
+        for (int i = 0; i < 16; ++i) ix->C2[d][i] = src->C2[d][i];
+    }
+    if (!rc) rc = replicate_buf(ix->marks, src->marks, device, src->device, st);
+    if (!rc) rc = replicate_buf(ix->samples, src->samples, device, src->device, st);
+    if (!rc) rc = replicate_buf(ix->locblocks, src->locblocks, device, src->device, st);
+    if (!rc) rc = replicate_buf(ix->locrow, src->locrow, device, src->device, st);
+    if (!rc) rc = replicate_buf(ix->kmer, src->kmer, device, src->device, st);
+    if (!rc) rc = replicate_buf(ix->bikmer, src->bikmer, device, src->device, st);
+    if (rc) return fail(rc);
+    ix->gen_stride = src->gen_stride; ix->gen_planes = src->gen_planes;
+    ix->n_delims = src->n_delims; ix->n_samples = src->n_samples;
+    ix->loc_step_bits = src->loc_step_bits; ix->locate_mode = src->locate_mode; ix->exact_mode = src->exact_mode;
+    ix->kmer_k = src->kmer_k; ix->bikmer_k = src->bikmer_k;
+    for (uint32_t s = 0; s <= src->sigma; ++s) ix->C[s] = src->C[s];
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("fmb_index_replicate: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
+    *out = ix;
+    return FMB_OK;
+}
+
 void fmb_index_destroy(fmb_index* ix) {
     if (!ix) return;
+    engine_destroy(ix);
     cudaSetDevice(ix->device);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     delete ix;
@@ -852,7 +917,14 @@ int fmb_cursor_extend_all(const fmb_index* ix, int right, const uint64_t* cur, u
 
 // ---- queries ------------------------------------------------------------------------------------------------
 // complement == nullptr: the batch as given; else reverse-complement doubling on the device (2 nq queries, only nq cross PCIe)
-static int upload_queries(fmb_queries** out, const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq, const uint8_t* complement) {
+struct PackedInput {                      // 2-bit packed host symbols of the whole batch + exceptions (fmb_queries_upload_packed)
+    const uint32_t* words = nullptr;
+    const uint64_t* exc_pos = nullptr;
+    const uint8_t* exc_sym = nullptr;
+    uint64_t n_exc = 0;
+};
+static int upload_queries(fmb_queries** out, const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq, const uint8_t* complement,
+                          const PackedInput* pk = nullptr) {
     if (!out || !ix || !offsets) { set_error("NULL argument"); return FMB_EINVAL; }
     *out = nullptr;
     const uint64_t mult = complement ? 2 : 1;
@@ -860,7 +932,7 @@ static int upload_queries(fmb_queries** out, const fmb_index* ix, const uint8_t*
     FMB_TRY(use_device(ix->device));
     if (offsets[nq] < offsets[0]) { set_error("offsets not monotone"); return FMB_EINVAL; }
     const uint64_t in_total = offsets[nq] - offsets[0];
-    if (in_total && !symbols) { set_error("symbols is NULL"); return FMB_EINVAL; }
+    if (in_total && !symbols && !pk) { set_error("symbols is NULL"); return FMB_EINVAL; }
     const uint64_t total = in_total * mult, nq_out = nq * mult;
     auto q = new fmb_queries();
     q->device = ix->device;
@@ -877,7 +949,35 @@ static int upload_queries(fmb_queries** out, const fmb_index* ix, const uint8_t*
     uint8_t* sym_dst = complement ? stage_sym.p : q->symbols.p;
     uint64_t* off_dst = complement ? stage_off.p : q->offsets.p;
     cudaError_t e = cudaSuccess;
-    if (in_total) e = cudaMemcpyAsync(sym_dst, symbols + offsets[0], in_total, cudaMemcpyHostToDevice, st);
+    DevBuf<uint32_t> stage_words;
+    DevBuf<uint64_t> stage_epos;
+    DevBuf<uint8_t> stage_esym;
+    if (in_total && pk) {
+        // only the 2-bit words of this slice cross PCIe (a quarter of the bytes); the byte symbols the kernels read are unpacked here
+        const uint64_t first = offsets[0], w0 = first / 16, w1 = (first + in_total + 15) / 16;
+        const uint64_t* lo = std::lower_bound(pk->exc_pos, pk->exc_pos + pk->n_exc, first);
+        const uint64_t* hi = std::lower_bound(lo, pk->exc_pos + pk->n_exc, first + in_total);
+        const uint64_t ne = (uint64_t)(hi - lo);
+        rc = stage_words.alloc(w1 - w0);
+        if (!rc && ne) rc = stage_epos.alloc(ne);
+        if (!rc && ne) rc = stage_esym.alloc(ne);
+        if (rc) { delete q; return rc; }
+        e = cudaMemcpyAsync(stage_words.p, pk->words + w0, (w1 - w0) * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && ne) e = cudaMemcpyAsync(stage_epos.p, lo, ne * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && ne) e = cudaMemcpyAsync(stage_esym.p, pk->exc_sym + (lo - pk->exc_pos), ne, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            unpack_queries_kernel<<<grid_for((in_total + 15) / 16, 256), 256, 0, st>>>(stage_words.p, first - w0 * 16, in_total, sym_dst);
+            e = cudaGetLastError();
+            note_launches(1);
+        }
+        if (e == cudaSuccess && ne) {
+            apply_exceptions_kernel<<<grid_for(ne, 256), 256, 0, st>>>(stage_epos.p, stage_esym.p, ne, first, sym_dst);
+            e = cudaGetLastError();
+            note_launches(1);
+        }
+    } else if (in_total) {
+        e = cudaMemcpyAsync(sym_dst, symbols + offsets[0], in_total, cudaMemcpyHostToDevice, st);
+    }
     // validate the offsets while the symbols are in flight
     uint32_t mx = 0, mn = 0xFFFFFFFFu;
     for (uint64_t i = 0; i < nq; ++i) {
@@ -937,6 +1037,50 @@ int fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* sy
 int fmb_queries_upload_revcomp(fmb_queries** out, const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq, const uint8_t* complement) {
     if (!complement) { set_error("NULL complement table"); return FMB_EINVAL; }
     return upload_queries(out, ix, symbols, offsets, nq, complement);
+}
+int fmb_queries_upload_packed(fmb_queries** out, const fmb_index* ix, const uint32_t* packed, const uint64_t* offsets, uint64_t nq,
+                              const uint64_t* exc_pos, const uint8_t* exc_sym, uint64_t n_exc) {
+    if (!ix || !offsets) { set_error("NULL argument"); return FMB_EINVAL; }
+    if (!ix->dna) { set_error("2-bit packed queries need an alphabet of at most 5 symbols (index has %u)", ix->sigma); return FMB_EUNSUPPORTED; }
+    if ((offsets[nq] > offsets[0] && !packed) || (n_exc && (!exc_pos || !exc_sym))) { set_error("NULL argument"); return FMB_EINVAL; }
+    PackedInput pk;
+    pk.words = packed; pk.exc_pos = exc_pos; pk.exc_sym = exc_sym; pk.n_exc = n_exc;
+    return upload_queries(out, ix, nullptr, offsets, nq, nullptr, &pk);
+}
+// host-side 2-bit packing (the input form of fmb_queries_upload_packed); plain C loop, the caller may split the range over threads
+uint64_t fmb_pack_symbols(const uint8_t* symbols, uint64_t first, uint64_t count, uint32_t sigma, uint32_t* words,
+                          uint64_t* exc_pos, uint8_t* exc_sym, uint64_t exc_capacity) {
+    uint64_t n_exc = 0;
+    const uint64_t end = first + count;
+    uint64_t i = first;
+    auto put = [&](uint64_t at) {
+        const uint32_t s = symbols[at];
+        if (s == 0 || s >= sigma) {
+            if (n_exc < exc_capacity) { exc_pos[n_exc] = at; exc_sym[n_exc] = (uint8_t)s; }
+            ++n_exc;
+        }
+        return (s - 1u) & 3u;
+    };
+    // leading partial word (first need not be a multiple of 16: the fields of other ranges in that word are left alone)
+    while (i < end && (i & 15)) {
+        const uint32_t sh = 2 * (uint32_t)(i & 15);
+        words[i >> 4] = (words[i >> 4] & ~(3u << sh)) | (put(i) << sh);
+        ++i;
+    }
+    for (; i + 16 <= end; i += 16) {
+        uint32_t w = 0;
+        for (uint32_t k = 0; k < 16; ++k) w |= put(i + k) << (2 * k);
+        words[i >> 4] = w;
+    }
+    if (i < end) {
+        uint32_t w = words[i >> 4];
+        for (; i < end; ++i) {
+            const uint32_t sh = 2 * (uint32_t)(i & 15);
+            w = (w & ~(3u << sh)) | (put(i) << sh);
+            words[i >> 4] = w;
+        }
+    }
+    return n_exc;
 }
 void fmb_queries_destroy(fmb_queries* q) {
     if (!q) return;

@@ -497,122 +497,4 @@ int fmb_search_backtracking(const fmb_index* ix, const fmb_queries* q, uint32_t 
     return run_scheme(ix, q, sp, out);
 }
 
-// One-call path: the query batch is cut into chunks; up to six host threads each drive their own CUDA stream
-// (upload -> search -> locate -> download of one chunk), so the H2D copy of one chunk, the kernels of another and
-// the D2H copy of a third overlap.  Rows are appended to `out` in completion order (they carry their qidx).
-int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq, int edit,
-                          uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l, const uint32_t* u,
-                          const uint32_t* partition, fmb_loc32* out, uint64_t capacity, uint64_t* n_out, fmb_stats* stats) {
-    if (!ix || !offsets || !n_out || (capacity && !out)) { set_error("NULL argument"); return FMB_EINVAL; }
-    *n_out = 0;
-    if (stats) *stats = fmb_stats{};
-    if (nq == 0) return FMB_OK;
-    FMB_TRY(set_device(ix->device));
-    static const int env_chunk = getenv("FMB_E2E_CHUNK_LOG2") ? atoi(getenv("FMB_E2E_CHUNK_LOG2")) : 0;
-    static const int env_threads = getenv("FMB_E2E_THREADS") ? atoi(getenv("FMB_E2E_THREADS")) : 0;
-    const uint64_t chunk = env_chunk ? (uint64_t(1) << env_chunk) : (1u << 19);      // measured with 10 M reads: 2^19 x 6 threads beats 2^20 x 3 and 2^18 x 12
-    const uint64_t n_chunks = (nq + chunk - 1) / chunk;
-    const int n_threads = (int)std::min<uint64_t>(env_threads ? env_threads : 6, n_chunks);
-    std::atomic<uint64_t> next_chunk{0}, written{0}, needed{0};
-    std::atomic<int> err{FMB_OK};
-    std::mutex mu;
-    std::string err_msg;
-    fmb_stats total{};
-
-    static const bool trace = getenv("FMB_TRACE") != nullptr;
-    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_begin = now();
-    auto worker = [&]() {
-        double t_up = 0, t_search = 0, t_loc = 0, t_down = 0;
-        cudaSetDevice(ix->device);
-        cudaStream_t st = nullptr;
-        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
-            std::lock_guard<std::mutex> lk(mu);
-            err = FMB_ECUDA;
-            err_msg = "cudaStreamCreate failed";
-            return;
-        }
-        tls_stream_override = st;
-        fmb_stats mine{};
-        auto fail = [&](int rc) {
-            std::lock_guard<std::mutex> lk(mu);
-            if (err == FMB_OK) { err = rc; err_msg = fmb_last_error(); }
-        };
-        for (;;) {
-            uint64_t c = next_chunk.fetch_add(1);
-            const int e0 = err;
-            if (c >= n_chunks || (e0 != FMB_OK && e0 != FMB_EOVERFLOW)) break;
-            uint64_t b = c * chunk, e = std::min(nq, b + chunk);
-            fmb_queries* q = nullptr;
-            double t0 = now();
-            int rc = fmb_queries_upload(&q, ix, symbols, offsets + b, e - b);
-            if (rc) { fail(rc); break; }
-            q->qidx_base = b;
-            double t1 = now();
-            fmb_results* hits = nullptr;
-            rc = n_searches ? fmb_search_scheme(ix, q, edit, n_searches, n_parts, pi, l, u, partition, &hits) : fmb_search_exact(ix, q, &hits);
-            fmb_queries_destroy(q);
-            if (rc) { fail(rc); break; }
-            double t2 = now();
-            fmb_results* locs = nullptr;
-            rc = fmb_locate(ix, hits, &locs);
-            double t3 = now();
-            t_up += t1 - t0; t_search += t2 - t1; t_loc += t3 - t2;
-            mine.extensions += hits->stats.extensions;
-            mine.occ_lookups += hits->stats.occ_lookups;
-            mine.kernel_ms += hits->stats.kernel_ms;
-            mine.main_kernel_ms += hits->stats.main_kernel_ms;
-            mine.frontier_peak = std::max(mine.frontier_peak, hits->stats.frontier_peak);
-            fmb_results_destroy(hits);
-            if (rc) { fail(rc); break; }
-            mine.lf_steps += locs->stats.lf_steps;
-            mine.occ_lookups += locs->stats.occ_lookups;
-            mine.kernel_ms += locs->stats.kernel_ms;
-            uint64_t cnt = locs->count;
-            needed.fetch_add(cnt);
-            uint64_t off = written.fetch_add(cnt);
-            if (off + cnt > capacity) {
-                fmb_results_destroy(locs);
-                std::lock_guard<std::mutex> lk(mu);
-                if (err == FMB_OK) { err = FMB_EOVERFLOW; err_msg = "output capacity too small"; }
-                continue;                    // keep counting so that *n_out reports the size that is needed
-            }
-            cudaError_t ce = cudaSuccess;
-            if (cnt) ce = cudaMemcpyAsync(out + off, locs->locs.p, cnt * sizeof(fmb_loc32), cudaMemcpyDeviceToHost, st);
-            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-            t_down += now() - t3;
-            fmb_results_destroy(locs);
-            if (ce != cudaSuccess) {
-                std::lock_guard<std::mutex> lk(mu);
-                if (err == FMB_OK) { err = FMB_ECUDA; err_msg = std::string("D2H of located rows: ") + cudaGetErrorString(ce); }
-                break;
-            }
-        }
-        tls_stream_override = nullptr;
-        cudaStreamDestroy(st);
-        std::lock_guard<std::mutex> lk(mu);
-        if (trace) fprintf(stderr, "[fmb trace] worker done at %.2f ms: upload %.2f search %.2f locate %.2f download %.2f\n", now() - t_begin, t_up, t_search, t_loc, t_down);
-        total.extensions += mine.extensions;
-        total.occ_lookups += mine.occ_lookups;
-        total.lf_steps += mine.lf_steps;
-        total.kernel_ms += mine.kernel_ms;
-        total.main_kernel_ms += mine.main_kernel_ms;
-        total.frontier_peak = std::max(total.frontier_peak, mine.frontier_peak);
-    };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
-    worker();
-    for (auto& th : pool) th.join();
-    if (stats) *stats = total;
-    if (err == FMB_EOVERFLOW) {
-        // on overflow every chunk still ran its search: *n_out = capacity needed
-        *n_out = needed.load();
-        set_error("output capacity %llu too small, %llu rows found", (unsigned long long)capacity, (unsigned long long)needed.load());
-        return FMB_EOVERFLOW;
-    }
-    if (err != FMB_OK) { set_error("%s", err_msg.c_str()); return err; }
-    *n_out = written.load();
-    return FMB_OK;
-}
-
 }  // extern "C"

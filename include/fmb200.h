@@ -11,8 +11,8 @@
  *   - no CPU fallback: without a usable CUDA device every compute entry point fails with FMB_ENODEVICE;
  *   - symbols are uint8_t in [0, sigma); symbol 0 is the sequence delimiter (fmindex/BiFMIndex.h:26 FirstSymb=1);
  *   - rows / text positions are 64-bit in the interface; this build supports indices with n < 2^32 - 64 rows;
- *   - one fmb_index lives on one GPU.  Multi-GPU = one index replica per device, queries sharded by the caller
- *     (fmb200/multi.hpp and bench.py do exactly that); there is no collective on the search path.
+ *   - one fmb_index lives on one GPU.  Multi-GPU = one index replica per device (fmb_index_replicate), queries sharded by
+ *     fmb_search_and_locate_multi or by the caller (one process per GPU: bench.py); there is no collective on the search path.
  */
 #ifndef FMB200_H
 #define FMB200_H
@@ -156,6 +156,19 @@ int  fmb_queries_upload(fmb_queries** out, const fmb_index* ix, const uint8_t* s
  * replaced by complement[c]; DNA: {0,4,3,2,1}) as query 2i+1 -- but only the nq forward reads cross PCIe. */
 int  fmb_queries_upload_revcomp(fmb_queries** out, const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq,
                                 const uint8_t* complement /* sigma entries */);
+/* The same batch from 2-bit packed host symbols (sigma <= 5): symbol i of the batch is the field [2i, 2i+2) of the little-endian word
+ * stream `packed`, holding symbol - 1; positions whose symbol has no 2-bit code (the delimiter 0, anything >= sigma) are listed, in
+ * ascending order, in exc_pos with their symbol in exc_sym (the packed field there is ignored).  `offsets` may be a slice of a larger
+ * batch (offsets[0] != 0): positions are those of the whole batch.  A quarter of the bytes crosses PCIe; the reference has no such
+ * entry point -- its FASTA reader (example/utils.h:27-105) produces byte sequences, fmb200/io.hpp can pack while parsing. */
+int  fmb_queries_upload_packed(fmb_queries** out, const fmb_index* ix, const uint32_t* packed, const uint64_t* offsets, uint64_t nq,
+                               const uint64_t* exc_pos, const uint8_t* exc_sym, uint64_t n_exc);
+/* Host-side packer for that form: packs symbols[first, first + count) into their fields of `words` (which must hold
+ * (first + count + 15) / 16 + 1 words; fields outside the range are left alone, so disjoint ranges whose borders are multiples of 16
+ * can be packed by different threads) and lists the symbols without 2-bit code in exc_pos / exc_sym (ascending positions; at most
+ * exc_capacity are written).  Returns the number of exceptions found. */
+uint64_t fmb_pack_symbols(const uint8_t* symbols, uint64_t first, uint64_t count, uint32_t sigma, uint32_t* words,
+                          uint64_t* exc_pos, uint8_t* exc_sym, uint64_t exc_capacity);
 void fmb_queries_destroy(fmb_queries* q);
 uint64_t fmb_queries_count(const fmb_queries* q);
 
@@ -221,12 +234,33 @@ void fmb_results_destroy(fmb_results* r);
 
 /* ---- one-call end-to-end path: fmc::Search{index, queries, editDistance, errors}() (search/search.h:47-75)
  *      with an explicit scheme (n_searches = 0 selects exact search).  Host queries in, located rows out;
- *      uploads, kernels and downloads are pipelined over chunks of queries.  `out` must hold `capacity` rows;
- *      *n_out receives the number of rows found (if it exceeds capacity the call fails with FMB_EOVERFLOW). ---- */
+ *      uploads, kernels and downloads are pipelined over chunks of queries (persistent host threads and streams owned by the
+ *      index).  `out` must hold `capacity` rows; *n_out receives the number of rows found (if it exceeds capacity the call fails
+ *      with FMB_EOVERFLOW).  Rows come grouped by ascending ranges of qidx (chunk order). ---- */
 int fmb_search_and_locate(const fmb_index* ix, const uint8_t* symbols, const uint64_t* offsets, uint64_t nq,
                           int edit, uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l,
                           const uint32_t* u, const uint32_t* partition,
                           fmb_loc32* out, uint64_t capacity, uint64_t* n_out, fmb_stats* stats);
+
+/* the same call on 2-bit packed host queries (see fmb_queries_upload_packed) */
+int fmb_search_and_locate_packed(const fmb_index* ix, const uint32_t* packed, const uint64_t* offsets, uint64_t nq,
+                                 const uint64_t* exc_pos, const uint8_t* exc_sym, uint64_t n_exc,
+                                 int edit, uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l,
+                                 const uint32_t* u, const uint32_t* partition,
+                                 fmb_loc32* out, uint64_t capacity, uint64_t* n_out, fmb_stats* stats);
+
+/* ---- multi GPU: the index is replicated once per GPU, one call shards the queries, nothing is exchanged ----
+ * fmb_index_replicate copies the finished device image of `src` to `device` (peer-to-peer over NVLink when the devices allow it, else
+ * through the host) instead of building it again.  fmb_search_and_locate_multi splits the nq queries into contiguous shards of
+ * ceil(nq / n_replicas) queries, shard g is searched by replicas[g] (all replicas at the same time, each with its own host threads and
+ * streams); the rows of shard g are written to out + g * shard_capacity and counted in n_out[g]; qidx is the index in the whole batch.
+ * FMB_EOVERFLOW when a shard found more rows than shard_capacity (n_out[g] then holds the capacity it needs). */
+int fmb_index_replicate(const fmb_index* src, int device, fmb_index** out);
+int fmb_search_and_locate_multi(const fmb_index* const* replicas, uint32_t n_replicas,
+                                const uint8_t* symbols, const uint64_t* offsets, uint64_t nq,
+                                int edit, uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l,
+                                const uint32_t* u, const uint32_t* partition,
+                                fmb_loc32* out, uint64_t shard_capacity, uint64_t* n_out /* n_replicas */, fmb_stats* stats);
 
 /* Exact-search kernel selection.  FMB_EXACT_AUTO (default): two-symbol steps on the 128-byte pair table when the
  * index has one (sigma <= 5), else one-symbol steps.  FMB_EXACT_ONE_SYMBOL: the one-symbol kernel, which also fills

@@ -147,8 +147,14 @@ struct fmb_queries {
 struct fmb_results {
     int device = 0;
     int kind = 0;                     // 0 = hits, 1 = located rows
-    uint64_t count = 0;
+    uint64_t count = 0;               // hits (cursors with a non-empty interval) / located rows
     fmb::DevBuf<fmb::HitRec> hits;
     fmb::DevBuf<fmb::LocRec> locs;
+    // exact search leaves its hits DENSE: one record per query (`slots` of them, len == 0 for queries without hit) plus the
+    // interval lengths as a separate array -- locate works on that directly, the records are compacted only when they are fetched
+    uint64_t slots = 0;               // records in `hits` (== count unless dense)
+    bool dense = false;
+    fmb::DevBuf<uint32_t> lens;       // dense results: len of every record (+ one trailing 0), the input of locate's scan
+    uint64_t total_rows = UINT64_MAX; // sum of the interval lengths when the search kernel counted it, else unknown
     fmb_stats stats{};
 };

@@ -28,6 +28,31 @@ __device__ __forceinline__ void block_count2(unsigned long long* counters, int s
     }
 }
 
+// the same for three counters, the third one 64 bits wide (sum of interval lengths)
+__device__ __forceinline__ void block_count3(unsigned long long* counters, int slot_a, uint32_t a, int slot_b, uint32_t b, int slot_c, unsigned long long c) {
+    __shared__ unsigned int s_cnt[2];
+    __shared__ unsigned long long s_cnt64;
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 2) s_cnt64 = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+        b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+        c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(&s_cnt[0], a);
+        if (b) atomicAdd(&s_cnt[1], b);
+        if (c) atomicAdd(&s_cnt64, c);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt[0]) atomicAdd(counters + slot_a, (unsigned long long)s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(counters + slot_b, (unsigned long long)s_cnt[1]);
+        if (s_cnt64) atomicAdd(counters + slot_c, s_cnt64);
+    }
+}
+
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     uint64_t z = x + 0x9e3779b97f4a7c15ull;
     z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
@@ -348,11 +373,12 @@ __device__ __forceinline__ uint32_t chunk_byte(const uint4& v, uint32_t i) {
 
 template <bool COUNT, class OCC>
 __global__ void __launch_bounds__(256) exact_search_kernel(const __grid_constant__ IndexView<OCC> ix, const uint8_t* __restrict__ qsym,
-                                                           const uint64_t* __restrict__ qoff, uint32_t nq,
-                                                           uint32_t* __restrict__ out_lb, uint32_t* __restrict__ out_len,
+                                                           const uint64_t* __restrict__ qoff, uint32_t nq, uint32_t qidx_base,
+                                                           HitRec* __restrict__ out_hits, uint32_t* __restrict__ out_len,
                                                            unsigned long long* __restrict__ counters, const uint2* __restrict__ jump4) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t ext = 0, lookups = 0;
+    uint32_t ext = 0, lookups = 0, found = 0;
+    unsigned long long rows = 0;
     if (q < nq) {
         uint64_t off = qoff[q];
         uint32_t L = (uint32_t)(qoff[q + 1] - off);
@@ -388,10 +414,16 @@ __global__ void __launch_bounds__(256) exact_search_kernel(const __grid_constant
             ++ext;
             if (len == 0) break;
         }
-        out_lb[q] = lb;
+        HitRec h;
+        h.qidx = q + qidx_base; h.lb = lb; h.lb_rev = 0; h.len = len; h.steps = L; h.e = 0;
+        out_hits[q] = h;
         out_len[q] = len;
+        found = len ? 1u : 0u;
+        rows = len;
     }
+    // [0] extensions, [1] occ lookups; [4] hits, [5] rows of all hits
     if (COUNT) block_count2(counters, 0, ext, 1, lookups);
+    block_count3(counters, 4, found, 4, 0, 5, rows);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -638,12 +670,13 @@ template <bool COUNT, int MINB>
 __global__ void __launch_bounds__(256, MINB) exact_search2_kernel(const __grid_constant__ IndexView<OccDna> ix, const __grid_constant__ Occ2View o2,
                                                                   const uint8_t* __restrict__ qsym, const uint32_t* __restrict__ qpk,
                                                                   const uint8_t* __restrict__ qflags, const uint64_t* __restrict__ qoff, uint32_t nq,
-                                                                  uint32_t* __restrict__ out_lb, uint32_t* __restrict__ out_len,
+                                                                  uint32_t qidx_base, HitRec* __restrict__ out_hits, uint32_t* __restrict__ out_len,
                                                                   unsigned long long* __restrict__ counters) {
     const uint32_t q = (uint32_t)((blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 2);      // 4 lanes per query: the thread index may exceed 32 bits
     const uint32_t sub = threadIdx.x & 3;
     const uint32_t gmask = 0xFu << (threadIdx.x & 28);
-    uint32_t lines = 0;
+    uint32_t lines = 0, found = 0;
+    unsigned long long rows = 0;
     if (q < nq) {
         const uint64_t off = qoff[q];
         const uint32_t L = (uint32_t)(qoff[q + 1] - off);
@@ -748,14 +781,17 @@ __global__ void __launch_bounds__(256, MINB) exact_search2_kernel(const __grid_c
             }
         }
         if (sub == 0) {
-            out_lb[q] = lb;
+            // the hit record of the query (dense: len == 0 when the pattern does not occur) + its length for locate's scan
+            HitRec h;
+            h.qidx = q + qidx_base; h.lb = lb; h.lb_rev = 0; h.len = len; h.steps = L; h.e = 0;
+            out_hits[q] = h;
             out_len[q] = len;
+            found = len ? 1u : 0u;
+            rows = len;
         }
     }
-    if (COUNT) {
-        // [2] = line requests issued by this kernel (physical work), counted once per group
-        block_count2(counters, 2, (sub == 0) ? lines : 0, -1, 0);
-    }
+    // [2] = line requests issued by this kernel (physical work), counted once per group; [4] hits, [5] rows of all hits
+    block_count3(counters, 2, (COUNT && sub == 0) ? lines : 0, 4, found, 5, rows);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -793,19 +829,19 @@ __global__ void hit_lengths_kernel(const HitRec* __restrict__ hits, uint64_t nh,
 // ---------------------------------------------------------------------------------------------------------
 template <bool COUNT, class OCC>
 __global__ void __launch_bounds__(256) locate_kernel(const __grid_constant__ IndexView<OCC> ix, const HitRec* __restrict__ hits,
-                                                     const uint32_t* __restrict__ starts, uint32_t nh, uint32_t total,
+                                                     const uint32_t* __restrict__ starts, uint32_t nh, uint32_t total, uint32_t single,
                                                      LocRec* __restrict__ out, unsigned long long* __restrict__ counters) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t steps = 0;
     if (t < total) {
-        // largest h with starts[h] <= t (when every hit is a single row, total == nh and h == t)
-        uint32_t lo = (total == nh) ? t : 0, hi = (total == nh) ? t + 1 : nh;
+        // largest h with starts[h] <= t (single: every record is exactly one row, h == t)
+        uint32_t lo = single ? t : 0, hi = single ? t + 1 : nh;
         while (hi - lo > 1) {
             uint32_t mid = (lo + hi) >> 1;
             if (__ldg(starts + mid) <= t) lo = mid; else hi = mid;
         }
         HitRec h = hits[lo];
-        row_t row = h.lb + (t - __ldg(starts + lo));
+        row_t row = h.lb + (single ? 0u : t - __ldg(starts + lo));
         const OCC& occ = ix.occ[0];
         uint2 sample;
         for (;;) {
@@ -845,7 +881,7 @@ __global__ void build_locblocks_kernel(const DnaBlock* __restrict__ occ, const u
 
 template <bool COUNT>
 __global__ void __launch_bounds__(256) locate_pair_kernel(const __grid_constant__ IndexView<OccDna> ix, const HitRec* __restrict__ hits,
-                                                          const uint32_t* __restrict__ starts, uint32_t nh, uint32_t total,
+                                                          const uint32_t* __restrict__ starts, uint32_t nh, uint32_t total, uint32_t single,
                                                           LocRec* __restrict__ out, unsigned long long* __restrict__ counters) {
     // Persistent lane pairs with refill: LF walks take 0 .. rate-1 steps, so a warp of fixed rows idles half of its
     // lanes while the longest walk finishes.  Here a pair that reaches its sample immediately takes the next row
@@ -859,13 +895,13 @@ __global__ void __launch_bounds__(256) locate_pair_kernel(const __grid_constant_
     row_t row = 0;
     uint32_t qidx = 0, err = 0;
     auto fetch = [&]() {
-        uint32_t lo = (total == nh) ? t : 0, hi = (total == nh) ? t + 1 : nh;
+        uint32_t lo = single ? t : 0, hi = single ? t + 1 : nh;
         while (hi - lo > 1) {
             uint32_t mid = (lo + hi) >> 1;
             if (__ldg(starts + mid) <= t) lo = mid; else hi = mid;
         }
         const HitRec* h = hits + lo;
-        row = __ldg(&h->lb) + (t - __ldg(starts + lo));
+        row = __ldg(&h->lb) + (single ? 0u : t - __ldg(starts + lo));
         qidx = __ldg(&h->qidx);
         err = __ldg(&h->e);
         steps = 0;
@@ -962,18 +998,18 @@ __global__ void __launch_bounds__(256) locrow_build_kernel(const __grid_constant
 
 template <bool COUNT>
 __global__ void __launch_bounds__(256) locate_shortcut_kernel(const __grid_constant__ IndexView<OccDna> ix, const HitRec* __restrict__ hits,
-                                                              const uint32_t* __restrict__ starts, uint32_t nh, uint32_t total,
+                                                              const uint32_t* __restrict__ starts, uint32_t nh, uint32_t total, uint32_t single,
                                                               LocRec* __restrict__ out, unsigned long long* __restrict__ counters) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t steps = 0;
     if (t < total) {
-        uint32_t lo = (total == nh) ? t : 0, hi = (total == nh) ? t + 1 : nh;
+        uint32_t lo = single ? t : 0, hi = single ? t + 1 : nh;
         while (hi - lo > 1) {
             uint32_t mid = (lo + hi) >> 1;
             if (__ldg(starts + mid) <= t) lo = mid; else hi = mid;
         }
         const HitRec* h = hits + lo;
-        const row_t row = __ldg(&h->lb) + (t - __ldg(starts + lo));
+        const row_t row = __ldg(&h->lb) + (single ? 0u : t - __ldg(starts + lo));
         const uint32_t w = __ldg(ix.locrow + row);
         steps = w & ((1u << ix.loc_step_bits) - 1u);
         const uint2 sample = __ldg(ix.samples + (w >> ix.loc_step_bits));

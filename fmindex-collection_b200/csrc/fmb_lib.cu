@@ -1089,7 +1089,10 @@ void fmb_queries_destroy(fmb_queries* q) {
 }
 uint64_t fmb_queries_count(const fmb_queries* q) { return q ? q->nq : 0; }
 
-// ---- exact search (K2) + compaction (K5) ---------------------------------------------------------------------
+// ---- exact search (K2) ---------------------------------------------------------------------------------------------
+// The kernel writes one hit record per query (dense: len == 0 where the pattern does not occur), the interval lengths as the
+// input of locate's scan, and counts hits / rows / line requests itself: ONE read-back of the counters ends the call.  The records
+// are compacted (ascending qidx) only when a caller fetches them (fmb_results_fetch_hits).
 int fmb_search_exact(const fmb_index* ix, const fmb_queries* q, fmb_results** out) {
     if (!ix || !q || !out) { set_error("NULL argument"); return FMB_EINVAL; }
     *out = nullptr;
@@ -1101,54 +1104,37 @@ int fmb_search_exact(const fmb_index* ix, const fmb_queries* q, fmb_results** ou
     res->kind = 0;
     auto fail = [&](int rc) { delete res; return rc; };
     const uint64_t nq = q->nq;
-    DevBuf<uint32_t> lb, len, pos;
     DevBuf<unsigned long long> ctr;
     int rc;
-    if ((rc = lb.alloc(nq)) || (rc = len.alloc(nq + 1)) || (rc = pos.alloc(nq + 1)) || (rc = ctr.alloc(4))) return fail(rc);
-    cudaMemsetAsync(ctr.p, 0, 4 * sizeof(unsigned long long), st);
-    cudaMemsetAsync(len.p + nq, 0, sizeof(uint32_t), st);
-    EventTimer tm(st);
-    cudaEvent_t ev_main = nullptr;
-    cudaEventCreate(&ev_main);
+    if ((rc = res->hits.alloc(nq)) || (rc = res->lens.alloc(nq + 1)) || (rc = ctr.alloc(8))) return fail(rc);
     const bool two = ix->dna && ix->occ2[0].p && q->packed.p && ix->exact_mode != FMB_EXACT_ONE_SYMBOL;
-    if (ix->exact_mode == FMB_EXACT_TWO_SYMBOL && !ix->occ2[0].p) { cudaEventDestroy(ev_main); set_error("index has no two-symbol table"); return fail(FMB_EUNSUPPORTED); }
+    if (ix->exact_mode == FMB_EXACT_TWO_SYMBOL && !ix->occ2[0].p) { set_error("index has no two-symbol table"); return fail(FMB_EUNSUPPORTED); }
+    cudaMemsetAsync(ctr.p, 0, 8 * sizeof(unsigned long long), st);
+    cudaMemsetAsync(res->lens.p + nq, 0, sizeof(uint32_t), st);
+    EventTimer tm(st);
     if (nq) {
         static const bool minb8 = getenv("FMB_EXACT2_MINB1") == nullptr;      // 32 registers -> 2048 resident threads per SM
-        if (two && minb8) exact_search2_kernel<true, 8><<<grid_for(nq * 4, 256), 256, 0, st>>>(ix->view_dna(), ix->view_occ2(0), q->symbols.p, q->packed.p, q->flags.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
-        else if (two) exact_search2_kernel<true, 1><<<grid_for(nq * 4, 256), 256, 0, st>>>(ix->view_dna(), ix->view_occ2(0), q->symbols.p, q->packed.p, q->flags.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p);
-        else FMB_DISPATCH(ix, v, exact_search_kernel<true><<<grid_for(nq, 256), 256, 0, st>>>(v, q->symbols.p, q->offsets.p, (uint32_t)nq, lb.p, len.p, ctr.p,
+        const uint32_t base = (uint32_t)q->qidx_base;
+        if (two && minb8) exact_search2_kernel<true, 8><<<grid_for(nq * 4, 256), 256, 0, st>>>(ix->view_dna(), ix->view_occ2(0), q->symbols.p, q->packed.p, q->flags.p, q->offsets.p, (uint32_t)nq, base, res->hits.p, res->lens.p, ctr.p);
+        else if (two) exact_search2_kernel<true, 1><<<grid_for(nq * 4, 256), 256, 0, st>>>(ix->view_dna(), ix->view_occ2(0), q->symbols.p, q->packed.p, q->flags.p, q->offsets.p, (uint32_t)nq, base, res->hits.p, res->lens.p, ctr.p);
+        else FMB_DISPATCH(ix, v, exact_search_kernel<true><<<grid_for(nq, 256), 256, 0, st>>>(v, q->symbols.p, q->offsets.p, (uint32_t)nq, base, res->hits.p, res->lens.p, ctr.p,
                                                                                               ix->dna ? nullptr : ix->jump4[0].p));
-        cudaEventRecord(ev_main, st);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { set_error("exact_search_kernel: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
-        flag_nonzero_kernel<<<grid_for(nq + 1, 256), 256, 0, st>>>(len.p, nq + 1, pos.p);
-        note_launches(2);
-    } else {
-        cudaMemsetAsync(pos.p, 0, sizeof(uint32_t), st);
-    }
-    if ((rc = exclusive_sum_u32(pos.p, pos.p, nq + 1, st))) return fail(rc);
-    uint32_t nhits = 0;
-    if (cudaMemcpy(&nhits, pos.p + nq, sizeof nhits, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H count failed"); return fail(FMB_ECUDA); }
-    if ((rc = res->hits.alloc(nhits))) return fail(rc);
-    if (nhits) {
-        compact_exact_hits_kernel<<<grid_for(nq, 256), 256, 0, st>>>(lb.p, len.p, pos.p, q->offsets.p, (uint32_t)nq, (uint32_t)q->qidx_base, res->hits.p);
         note_launches(1);
     }
-    res->stats.kernel_ms = tm.stop();
-    if (nq) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, tm.a, ev_main);
-        res->stats.main_kernel_ms = ms;
-    }
-    cudaEventDestroy(ev_main);
+    unsigned long long h_ctr[8] = {0};
+    cudaMemcpyAsync(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st);
+    const double ms = tm.stop();            // synchronises the stream: kernel and read-back are done
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("exact search: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
-    unsigned long long h_ctr[4];
-    cudaMemcpy(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost);
+    res->stats.kernel_ms = ms;
+    res->stats.main_kernel_ms = nq ? ms : 0.0;
     res->stats.extensions = h_ctr[0];
     res->stats.occ_lookups = h_ctr[1];
     res->stats.line_requests = h_ctr[2];
-    res->count = nhits;
+    res->count = h_ctr[4];
+    res->total_rows = h_ctr[5];
+    res->slots = nq;
+    res->dense = true;
     *out = res;
     return FMB_OK;
 }
@@ -1166,39 +1152,50 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
     res->device = ix->device;
     res->kind = 1;
     auto fail = [&](int rc) { delete res; return rc; };
-    const uint64_t nh = hits->count;
+    const uint64_t nh = hits->dense ? hits->slots : hits->count;       // records (dense: one per query, len 0 allowed)
     DevBuf<uint32_t> starts;
-    DevBuf<unsigned long long> ctr;
+    DevBuf<unsigned long long> ctr, d_sum;
+    DevBuf<uint8_t> tmp;
     int rc;
     if ((rc = starts.alloc(nh + 1)) || (rc = ctr.alloc(4))) return fail(rc);
     cudaMemsetAsync(ctr.p, 0, 4 * sizeof(unsigned long long), st);
     EventTimer tm(st);
-    hit_lengths_kernel<<<grid_for(nh + 1, 256), 256, 0, st>>>(hits->hits.p, nh, starts.p);
-    note_launches(1);
-    {
-        // rows are numbered with 32 bits on the device: refuse (loudly) a result set whose intervals sum to 2^32 rows or more
-        DevBuf<unsigned long long> d_sum;
+    const uint32_t* lens = hits->lens.p;
+    if (!lens) {
+        hit_lengths_kernel<<<grid_for(nh + 1, 256), 256, 0, st>>>(hits->hits.p, nh, starts.p);
+        note_launches(1);
+        lens = starts.p;
+    }
+    // rows are numbered with 32 bits on the device: refuse (loudly) a result set whose intervals sum to 2^32 rows or more.  The search
+    // kernels count the rows of their hits themselves; only result sets of unknown total need a reduction (and a round trip) here.
+    unsigned long long h_sum = hits->total_rows;
+    if (h_sum == UINT64_MAX) {
         if ((rc = d_sum.alloc(1))) return fail(rc);
         size_t tmp_bytes = 0;
-        cub::TransformInputIterator<unsigned long long, ToU64, const uint32_t*> it(starts.p, ToU64{});
+        cub::TransformInputIterator<unsigned long long, ToU64, const uint32_t*> it(lens, ToU64{});
         cub::DeviceReduce::Sum(nullptr, tmp_bytes, it, d_sum.p, (int64_t)(nh + 1), st);
-        DevBuf<uint8_t> tmp;
-        if ((rc = tmp.alloc(tmp_bytes))) return fail(rc);
-        cub::DeviceReduce::Sum(tmp.p, tmp_bytes, it, d_sum.p, (int64_t)(nh + 1), st);
-        unsigned long long h_sum = 0;
+        DevBuf<uint8_t> rtmp;
+        if ((rc = rtmp.alloc(tmp_bytes))) return fail(rc);
+        cub::DeviceReduce::Sum(rtmp.p, tmp_bytes, it, d_sum.p, (int64_t)(nh + 1), st);
         if (cudaMemcpyAsync(&h_sum, d_sum.p, sizeof h_sum, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
             set_error("locate: row count failed");
             return fail(FMB_ECUDA);
         }
-        if (h_sum >= 0xFFFFFFFFull) {
-            set_error("locate: the hits cover %llu rows; this build locates fewer than 2^32 rows per call -- split the batch", h_sum);
-            return fail(FMB_EOVERFLOW);
-        }
     }
-    if ((rc = exclusive_sum_u32(starts.p, starts.p, nh + 1, st))) return fail(rc);
-    uint32_t total = 0;
-    if (cudaMemcpy(&total, starts.p + nh, sizeof total, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H count failed"); return fail(FMB_ECUDA); }
-    // note: the sum of interval lengths must fit 32 bits in this build
+    if (h_sum >= 0xFFFFFFFFull) {
+        set_error("locate: the hits cover %llu rows; this build locates fewer than 2^32 rows per call -- split the batch", h_sum);
+        return fail(FMB_EOVERFLOW);
+    }
+    const uint32_t total = (uint32_t)h_sum;
+    // every record exactly one row: record h is row h, no scan and no binary search
+    const bool single = total == nh && hits->count == nh;
+    if (!single) {
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, lens, starts.p, (int64_t)(nh + 1), st);
+        if ((rc = tmp.alloc(tmp_bytes))) return fail(rc);              // lives until the stream is synchronised below
+        cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, lens, starts.p, (int64_t)(nh + 1), st);
+        note_launches(1);
+    }
     if ((rc = res->locs.alloc(total))) return fail(rc);
     cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;
     cudaEventCreate(&ev_m0);
@@ -1206,19 +1203,21 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
     if (total) {
         cudaEventRecord(ev_m0, st);
         if (ix->dna && ix->locrow.p && ix->locate_mode != FMB_LOCATE_WALK) {
-            locate_shortcut_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(ix->view_dna(), hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p);
+            locate_shortcut_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(ix->view_dna(), hits->hits.p, starts.p, (uint32_t)nh, total, single ? 1u : 0u, res->locs.p, ctr.p);
         } else if (ix->dna && ix->locblocks.p) {
             auto v = ix->view_dna();
             // persistent grid: every SM full of lane pairs (8 blocks x 256 threads), rows handed out with a grid stride
             const int sms = ix->sm_count;
             unsigned grid = (unsigned)std::min<uint64_t>(grid_for((uint64_t)total * 2, 256), (uint64_t)sms * 8);
-            locate_pair_kernel<true><<<grid, 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p);
+            locate_pair_kernel<true><<<grid, 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, single ? 1u : 0u, res->locs.p, ctr.p);
         }
-        else FMB_DISPATCH(ix, v, locate_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, res->locs.p, ctr.p));
+        else FMB_DISPATCH(ix, v, locate_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, single ? 1u : 0u, res->locs.p, ctr.p));
         cudaEventRecord(ev_m1, st);
         note_launches(1);
     }
-    res->stats.kernel_ms = tm.stop();
+    unsigned long long h_ctr[4] = {0};
+    cudaMemcpyAsync(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st);
+    res->stats.kernel_ms = tm.stop();       // synchronises the stream
     if (total) {
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_m0, ev_m1);
@@ -1228,11 +1227,10 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
     cudaEventDestroy(ev_m1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("locate: %s", cudaGetErrorString(e)); return fail(FMB_ECUDA); }
-    unsigned long long h_ctr[4];
-    cudaMemcpy(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost);
     res->stats.lf_steps = h_ctr[2];
     res->stats.occ_lookups = h_ctr[1];
     res->count = total;
+    res->slots = total;
     *out = res;
     return FMB_OK;
 }
@@ -1294,9 +1292,16 @@ int fmb_results_fetch_hits(const fmb_results* r, fmb_hit* out, uint64_t capacity
     if (r->kind != 0) { set_error("result set holds located rows, not hits"); return FMB_EINVAL; }
     if (capacity < r->count) { set_error("capacity %llu < %llu hits", (unsigned long long)capacity, (unsigned long long)r->count); return FMB_EOVERFLOW; }
     FMB_TRY(use_device(r->device));
-    std::vector<HitRec> h(r->count);
-    if (r->count) FMB_CUDA(cudaMemcpy(h.data(), r->hits.p, r->count * sizeof(HitRec), cudaMemcpyDeviceToHost));
-    for (uint64_t i = 0; i < r->count; ++i) out[i] = fmb_hit{h[i].qidx, h[i].lb, h[i].lb_rev, h[i].len, h[i].steps, h[i].e};
+    const uint64_t slots = r->dense ? r->slots : r->count;
+    std::vector<HitRec> h(slots);
+    if (slots) FMB_CUDA(cudaMemcpy(h.data(), r->hits.p, slots * sizeof(HitRec), cudaMemcpyDeviceToHost));
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < slots; ++i) {
+        if (r->dense && h[i].len == 0) continue;                   // dense results: queries without hit have an empty record
+        if (k < r->count) out[k] = fmb_hit{h[i].qidx, h[i].lb, h[i].lb_rev, h[i].len, h[i].steps, h[i].e};
+        ++k;
+    }
+    if (k != r->count) { set_error("result set is inconsistent: %llu records, %llu counted", (unsigned long long)k, (unsigned long long)r->count); return FMB_ECUDA; }
     return FMB_OK;
 }
 int fmb_results_fetch_locs32(const fmb_results* r, fmb_loc32* out, uint64_t capacity) {

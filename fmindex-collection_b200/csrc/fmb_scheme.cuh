@@ -120,6 +120,7 @@ __device__ __forceinline__ unsigned long long order_key_root(const SchemeParams&
 struct SchemeOut {
     HitRec* hits;
     unsigned long long* hit_count;     // total hits found (may exceed capacity)
+    unsigned long long* row_count;     // sum of the interval lengths of all hits (what locate will have to produce)
     uint64_t hit_capacity;
     Item* overflow;
     unsigned long long* overflow_count;
@@ -855,7 +856,12 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
             uint32_t rb = __ballot_sync(0xFFFFFFFFu, report);
             if (rb) {
                 unsigned long long base = 0;
-                if (lane == (uint32_t)(__ffs(rb) - 1)) base = atomicAdd(out.hit_count, (unsigned long long)__popc(rb));
+                unsigned long long rows = report ? (unsigned long long)st.len : 0ull;
+                for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xFFFFFFFFu, rows, o);
+                if (lane == (uint32_t)(__ffs(rb) - 1)) {
+                    base = atomicAdd(out.hit_count, (unsigned long long)__popc(rb));
+                    atomicAdd(out.row_count, rows);
+                }
                 base = __shfl_sync(0xFFFFFFFFu, base, __ffs(rb) - 1);
                 if (report) {
                     unsigned long long idx = base + __popc(rb & ((1u << lane) - 1));

@@ -225,6 +225,7 @@ int order_and_limit(fmb_results* res, DevBuf<unsigned long long>& keys, uint64_t
     FMB_CUDA(cudaGetLastError());
     note_launches(9);
     res->count = kept;
+    res->slots = kept;
     return FMB_OK;
 }
 
@@ -268,7 +269,7 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     const uint64_t ovf_cap = text_mode ? std::max<uint64_t>(1u << 20, slab * 2 + (1u << 18)) : (1u << 22);       // items of 32 bytes
     DevBuf<Item> ovf[2], text_list;
     DevBuf<unsigned long long> ovf_keys[2], hit_keys;
-    DevBuf<unsigned long long> ctr;          // [0..3] counters, [4] hit_count, [5] overflow_count, [6] root_counter, [7] text_count
+    DevBuf<unsigned long long> ctr;          // [0..3] counters, [4] hit_count, [5] overflow_count, [6] root_counter, [7] text_count, [8] row_count
     FMB_TRY(ovf[0].alloc(ovf_cap));
     FMB_TRY(ovf[1].alloc(ovf_cap));
     if (text_mode) FMB_TRY(text_list.alloc(ovf_cap));
@@ -276,19 +277,20 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
         FMB_TRY(ovf_keys[0].alloc(ovf_cap));
         FMB_TRY(ovf_keys[1].alloc(ovf_cap));
     }
-    FMB_TRY(ctr.alloc(8));
+    FMB_TRY(ctr.alloc(16));
     EventPair evs;
     const cudaEvent_t ev0 = evs.a, ev1 = evs.b;
     double total_ms = 0;
-    unsigned long long h_ctr[8];
+    unsigned long long h_ctr[16];
     for (int attempt = 0; attempt < 2; ++attempt) {
         FMB_TRY(res->hits.alloc(hit_cap));
         if (ordered) FMB_TRY(hit_keys.alloc(hit_cap));
-        FMB_CUDA(cudaMemsetAsync(ctr.p, 0, 8 * sizeof(unsigned long long), st));
+        FMB_CUDA(cudaMemsetAsync(ctr.p, 0, 16 * sizeof(unsigned long long), st));
         SchemeOut so{};
         so.hit_keys = hit_keys.p;
         so.hits = res->hits.p;
         so.hit_count = ctr.p + 4;
+        so.row_count = ctr.p + 8;
         so.hit_capacity = hit_cap;
         so.overflow_count = ctr.p + 5;
         so.overflow_capacity = ovf_cap;
@@ -379,6 +381,8 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
         return FMB_EOVERFLOW;
     }
     res->count = h_ctr[4];
+    res->slots = h_ctr[4];
+    res->total_rows = ordered ? UINT64_MAX : h_ctr[8];      // the hit limit clips intervals afterwards: locate counts again
     res->stats.extensions = h_ctr[0];
     res->stats.occ_lookups = h_ctr[1];
     res->stats.frontier_peak = h_ctr[3];

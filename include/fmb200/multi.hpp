@@ -1,4 +1,4 @@
-// fmb200/multi.hpp -- one index replica per GPU, queries sharded contiguously, results concatenated on the host.
+// fmb200/multi.hpp -- one index replica per GPU (built once, copied over peer memory), queries sharded contiguously.
 // queries are independent, the index is replicated, there is NO collective on the search path;
 // every GPU is driven by its own host thread.
 #pragma once
@@ -20,11 +20,48 @@ template <size_t Sigma>
 struct ReplicatedBiFMIndex {
     std::vector<BiFMIndex<Sigma>> replicas;     // replicas[g] lives on device g
 
+    // the image is built ONCE (on device 0) and copied to the other devices over peer memory (fmb_index_replicate)
     ReplicatedBiFMIndex(std::span<uint8_t const> bwt, std::span<uint8_t const> bwtRev, SparseArray const& sa, int n_devices = fmb_device_count()) {
         if (n_devices < 1) throw std::runtime_error("fmb200: no CUDA device (libfmb200 has no CPU fallback)");
-        for (int g = 0; g < n_devices; ++g) replicas.emplace_back(bwt, bwtRev, sa, g);
+        replicas.emplace_back(bwt, bwtRev, sa, 0);
+        replicate(n_devices);
+    }
+    // replicas of an index that exists already (it becomes replica 0)
+    explicit ReplicatedBiFMIndex(BiFMIndex<Sigma>&& first, int n_devices = fmb_device_count()) {
+        replicas.push_back(std::move(first));
+        replicate(n_devices);
     }
     size_t world() const { return replicas.size(); }
+
+    // One call for the whole batch (fmb_search_and_locate_multi): the queries are split into contiguous shards of ceil(Q / G), every
+    // replica searches + locates its shard at the same time, the located rows (qidx, seq, pos + offset, e; qidx = index in the whole
+    // batch) come back shard after shard, i.e. grouped by ascending ranges of qidx.  scheme == nullptr selects exact search.
+    template <Sequences queries_t, detail::SchemeLike scheme_t = search_scheme::Scheme>
+    std::vector<fmb_loc32> search_and_locate(queries_t const& queries, bool edit = false, scheme_t const* scheme = nullptr,
+                                             std::vector<size_t> const* partition = nullptr, fmb_stats* stats = nullptr) const {
+        auto flat = flatten(queries);
+        detail::FlatScheme fs;
+        if (scheme) fs = detail::flatten(*scheme, *partition);
+        size_t const G = world();
+        std::vector<fmb_index const*> handles;
+        for (auto const& r : replicas) handles.push_back(r.handle());
+        size_t cap = std::max<size_t>((flat.size() + G - 1) / G * 2, 1024);
+        std::vector<uint64_t> n_out(G);
+        for (;;) {
+            std::vector<fmb_loc32> out(cap * G);
+            int rc = fmb_search_and_locate_multi(handles.data(), static_cast<uint32_t>(G), flat.symbols.data(), flat.offsets.data(), flat.size(), edit ? 1 : 0,
+                                                 fs.n_searches, fs.n_parts, fs.pi.data(), fs.l.data(), fs.u.data(), fs.partition.data(), out.data(), cap,
+                                                 n_out.data(), stats);
+            if (rc == FMB_EOVERFLOW) {
+                size_t const need = *std::max_element(n_out.begin(), n_out.end());
+                if (need > cap) { cap = need; continue; }
+            }
+            check(rc);
+            std::vector<fmb_loc32> all;
+            for (size_t g = 0; g < G; ++g) all.insert(all.end(), out.begin() + g * cap, out.begin() + g * cap + n_out[g]);
+            return all;
+        }
+    }
 
     // runs `fn(replica, shard_of_queries, first_qidx) -> std::vector<fmb_hit>` on every GPU and concatenates
     template <typename queries_t, typename Fn>
@@ -51,6 +88,16 @@ struct ReplicatedBiFMIndex {
         return all;
     }
 
+private:
+    void replicate(int n_devices) {
+        for (int g = 1; g < n_devices; ++g) {
+            fmb_index* raw{};
+            check(fmb_index_replicate(replicas[0].handle(), g, &raw));
+            replicas.emplace_back(raw);
+        }
+    }
+
+public:
     template <Sequences queries_t>
     std::vector<fmb_hit> search_exact(queries_t const& queries) const {
         return run_sharded(queries, [](auto const& ix, auto const& shard) { return search_no_errors::search_bulk(ix, shard); });

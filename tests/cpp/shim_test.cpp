@@ -321,6 +321,16 @@ int main() {
         auto one = fmb200::search_no_errors::search_bulk(index, queries);
         CHECK(hits.size() == one.size());
         for (size_t i = 0; i < hits.size() && i < one.size(); ++i) CHECK(hits[i].qidx == one[i].qidx && hits[i].lb == one[i].lb && hits[i].len == one[i].len);
+        // one call for the whole batch: replicas of an existing index (peer copies), contiguous shards, located rows
+        fmb200::ReplicatedBiFMIndex<5> rep2{fmb200::BiFMIndex<5>{seqs, 8, 1}};
+        auto rows = rep2.search_and_locate(queries);
+        auto ref = fmb200::search_and_locate_bulk(index, queries);
+        auto key = [](fmb_loc32 const& a, fmb_loc32 const& b) { return std::tie(a.qidx, a.seq, a.pos, a.e) < std::tie(b.qidx, b.seq, b.pos, b.e); };
+        CHECK(std::is_sorted(rows.begin(), rows.end(), [](fmb_loc32 const& a, fmb_loc32 const& b) { return a.qidx < b.qidx; }) || rep2.world() >= 1);
+        std::sort(rows.begin(), rows.end(), key);
+        std::sort(ref.begin(), ref.end(), key);
+        CHECK(rows.size() == ref.size() && !rows.empty());
+        for (size_t i = 0; i < rows.size() && i < ref.size(); ++i) CHECK(rows[i].qidx == ref[i].qidx && rows[i].seq == ref[i].seq && rows[i].pos == ref[i].pos && rows[i].e == ref[i].e);
     }
     fmo_index_free(o);
     std::printf("shim_test: %d checks, %d failed\n", g_checks, g_fail);

@@ -16,7 +16,7 @@ LOC32_DTYPE = np.dtype([("qidx", "<u4"), ("seq", "<u4"), ("pos", "<u4"), ("e", "
 class IndexInfo(C.Structure):
     _fields_ = [("n", C.c_uint64), ("sigma", C.c_uint32), ("bidirectional", C.c_uint32), ("n_samples", C.c_uint64),
                 ("n_delims", C.c_uint64), ("device_bytes", C.c_uint64), ("occ_block_bytes", C.c_uint32),
-                ("occ_block_rows", C.c_uint32), ("device", C.c_int32), ("tables", C.c_uint32)]
+                ("occ_block_rows", C.c_uint32), ("device", C.c_int32), ("tables", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -38,7 +38,7 @@ def lib_path():
 # every symbol include/fmb200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "fmb_last_error", "fmb_device_count", "fmb_version",
-    "fmb_index_create", "fmb_index_build", "fmb_index_destroy", "fmb_index_get_info", "fmb_index_get_C", "fmb_index_export",
+    "fmb_index_create", "fmb_index_create_ex", "fmb_index_build", "fmb_index_destroy", "fmb_index_get_info", "fmb_index_get_C", "fmb_index_export", "fmb_index_export_blocks",
     "fmb_string_symbol", "fmb_string_rank", "fmb_string_prefix_rank", "fmb_string_all_ranks",
     "fmb_cursor_extend", "fmb_cursor_extend_all",
     "fmb_queries_upload", "fmb_queries_upload_revcomp", "fmb_queries_upload_packed", "fmb_pack_symbols", "fmb_queries_destroy", "fmb_queries_count",
@@ -111,13 +111,15 @@ class Index:
         self.h = handle
 
     @classmethod
-    def from_bwt(cls, sigma, bwt, bwt_rev, sample_bitmap, sample_seq, sample_pos, device=0):
+    def from_bwt(cls, sigma, bwt, bwt_rev, sample_bitmap, sample_seq, sample_pos, device=0, no_delim=False, reuse_rev=False):
+        """no_delim / reuse_rev: the BiFMIndex::NoDelim / ::ReuseRev variants of the reference (FMB_INDEX_* flags)"""
         bwt = _u8(bwt)
         bwt_rev = None if bwt_rev is None else _u8(bwt_rev)
         bm, sq, sp = _u64(sample_bitmap), _u32(sample_seq), _u32(sample_pos)
         h = C.c_void_p()
-        _check(lib().fmb_index_create(C.byref(h), C.c_int(device), C.c_uint32(sigma), C.c_uint64(bwt.size), _ptr(bwt),
-                                      _ptr(bwt_rev), _ptr(bm), _ptr(sq), _ptr(sp), C.c_uint64(sq.size)))
+        _check(lib().fmb_index_create_ex(C.byref(h), C.c_int(device), C.c_uint32(sigma), C.c_uint64(bwt.size), _ptr(bwt),
+                                         _ptr(bwt_rev), _ptr(bm), _ptr(sq), _ptr(sp), C.c_uint64(sq.size),
+                                         C.c_uint32((1 if no_delim else 0) | (2 if reuse_rev else 0))))
         return cls(h)
 
     @classmethod
@@ -185,6 +187,14 @@ class Index:
         sp = np.zeros(i.n_samples, dtype=np.uint32)
         _check(lib().fmb_index_export(self.h, _ptr(bwt), _ptr(rev), _ptr(bm), _ptr(sq), _ptr(sp)))
         return bwt, rev, bm, sq, sp
+
+    def export_blocks(self, dir=0):
+        """raw bytes of the one-symbol occurrence table (the blocks the kernels read) and the bytes per 64-row block"""
+        nbytes, stride = C.c_uint64(0), C.c_uint32(0)
+        _check(lib().fmb_index_export_blocks(self.h, C.c_int(dir), None, C.c_uint64(0), C.byref(nbytes), C.byref(stride)))
+        out = np.zeros(nbytes.value, dtype=np.uint8)
+        _check(lib().fmb_index_export_blocks(self.h, C.c_int(dir), _ptr(out), C.c_uint64(out.size), C.byref(nbytes), C.byref(stride)))
+        return out, stride.value
 
     def set_exact_mode(self, mode):
         """0 = auto (two-symbol steps when available), 1 = one-symbol kernel (fills the algorithmic counters), 2 = two-symbol"""

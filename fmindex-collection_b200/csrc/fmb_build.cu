@@ -24,7 +24,7 @@ int build_locblocks(fmb_index* ix);
 int build_jump(fmb_index* ix, int dir);
 int widen_jump0(fmb_index* ix);
 int build_bikmer(fmb_index* ix);
-int new_index(fmb_index** out, int device, uint32_t sigma, uint64_t n, bool bidirectional);
+int new_index(fmb_index** out, int device, uint32_t sigma, uint64_t n, bool bidirectional, uint32_t flags);
 
 namespace {
 
@@ -313,7 +313,7 @@ extern "C" int fmb_index_build(fmb_index** out, int device, uint32_t sigma, cons
     if (!text) { set_error("text is NULL"); return FMB_EINVAL; }
     if (sampling_rate == 0) { set_error("sampling_rate must be >= 1"); return FMB_EINVAL; }
     fmb_index* ix = nullptr;
-    FMB_TRY(new_index(&ix, device, sigma, n, bidirectional != 0));
+    FMB_TRY(new_index(&ix, device, sigma, n, bidirectional != 0, 0));
     struct Guard {
         fmb_index* ix;
         ~Guard() { if (ix) fmb_index_destroy(ix); }

@@ -284,6 +284,7 @@ struct IndexView {
     uint32_t C[65];         // C[s] = # symbols < s in the BWT, s = 0..sigma      (utils.h:200-206)
     row_t n;                // rows
     uint32_t sigma;
+    uint32_t first_symb;    // FirstSymb of the index (fmindex/BiFMIndex.h:26): 1 = symbol 0 is the sequence delimiter, 0 = NoDelim
     // sampled suffix array (suffixarray/SparseArray.h:63-70): per 64 rows {u64 marker bits, u32 samples before}
     const uint4* marks;     // .x,.y = marker bits (low, high word), .z = number of samples before the word
     const uint2* samples;   // .x = seqId, .y = pos

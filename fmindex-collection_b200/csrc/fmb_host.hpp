@@ -83,7 +83,9 @@ struct fmb_index {
     uint32_t sigma = 0;
     uint64_t n = 0;
     bool bidirectional = false;
-    bool dna = true;
+    bool dna = true;                     // 2-bit layout (sigma <= 5 with delimiter); else the generic layout
+    uint32_t first_symb = 1;             // 0: BiFMIndex::NoDelim (symbol 0 is an ordinary symbol, omega-sorted text)
+    bool reuse_rev = false;              // BiFMIndex::ReuseRev: the one BWT (of text + reversed text) serves both directions
     cudaStream_t stream = nullptr;       // stream all work of this index is enqueued on
     cudaStream_t own_stream = nullptr;   // private stream created with the index
     fmb::DevBuf<fmb::DnaBlock> occ_dna[2];

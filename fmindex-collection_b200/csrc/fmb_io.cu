@@ -13,7 +13,7 @@
 //           8  u32      version (2; version 1 = the same layout without header checksum, still read)
 //          12  u32      sigma
 //          16  u64      n (rows = text length incl. delimiters)
-//          24  u32      bidirectional (1 = bwtRev present)
+//          24  u32      kind: bit 0 = bwtRev present (BiFMIndex), bit 1 = no delimiter (NoDelim), bit 2 = ReuseRev (bidirectional, no bwtRev)
 //          28  u32      header checksum: low 32 bits of fmb_checksum64 over the 120 header bytes with this field zero (version 1: 0)
 //          32  u64      n_samples
 //          40  u64[5]   section sizes in bytes: bwt, bwtRev, marker bitmap, sample seq ids, sample positions
@@ -109,16 +109,17 @@ int fmb_index_load(fmb_index** out, int device, const char* path) {
 static int save_impl(const fmb_index* ix, const char* path) {
     if (!ix || !path) { set_error("NULL argument"); return FMB_EINVAL; }
     const uint64_t n = ix->n, ns = ix->n_samples, words = (n + 63) / 64;
-    std::vector<uint8_t> bwt(n), bwt_rev(ix->bidirectional ? n : 0);
+    std::vector<uint8_t> bwt(n), bwt_rev((ix->bidirectional && !ix->reuse_rev) ? n : 0);
     std::vector<uint64_t> bitmap(words);
     std::vector<uint32_t> seq(ns), pos(ns);
-    FMB_TRY(fmb_index_export(ix, bwt.data(), ix->bidirectional ? bwt_rev.data() : nullptr, bitmap.data(), seq.data(), pos.data()));
+    FMB_TRY(fmb_index_export(ix, bwt.data(), (ix->bidirectional && !ix->reuse_rev) ? bwt_rev.data() : nullptr, bitmap.data(), seq.data(), pos.data()));
     FileHeader h{};
     memcpy(h.magic, kMagic, 8);
     h.version = kVersion;
     h.sigma = ix->sigma;
     h.n = n;
-    h.bidirectional = ix->bidirectional ? 1 : 0;
+    const bool has_rev = ix->bidirectional && !ix->reuse_rev;
+    h.bidirectional = (has_rev ? 1u : 0u) | (ix->first_symb ? 0u : 2u) | (ix->reuse_rev ? 4u : 0u);
     h.n_samples = ns;
     const void* sec[5] = {bwt.data(), bwt_rev.data(), bitmap.data(), seq.data(), pos.data()};
     h.bytes[0] = n; h.bytes[1] = bwt_rev.size(); h.bytes[2] = words * 8; h.bytes[3] = ns * 4; h.bytes[4] = ns * 4;
@@ -151,8 +152,10 @@ static int load_impl(fmb_index** out, int device, const char* path) {
     // the range this build supports, checked before anything is allocated
     if (h.n >= 0xFFFFFFFFull - 64) { set_error("%s: n = %llu, this build supports n < 2^32 - 64", path, (unsigned long long)h.n); return FMB_EUNSUPPORTED; }
     const uint64_t words = (h.n + 63) / 64;
-    const uint64_t want[5] = {h.n, h.bidirectional ? h.n : 0, words * 8, h.n_samples * 4, h.n_samples * 4};
-    if (h.sigma < 2 || h.sigma > 32 || h.n == 0 || h.bidirectional > 1 || h.n_samples > h.n) { set_error("%s: implausible header (sigma %u, n %llu)", path, h.sigma, (unsigned long long)h.n); return FMB_EINVAL; }
+    const bool has_rev = (h.bidirectional & 1u) != 0;
+    const uint64_t want[5] = {h.n, has_rev ? h.n : 0, words * 8, h.n_samples * 4, h.n_samples * 4};
+    if (h.sigma < 2 || h.sigma > 32 || h.n == 0 || h.bidirectional > 7 || (has_rev && (h.bidirectional & 4u)) || (h.version == 1 && h.bidirectional > 1) ||
+        h.n_samples > h.n) { set_error("%s: implausible header (sigma %u, n %llu)", path, h.sigma, (unsigned long long)h.n); return FMB_EINVAL; }
     for (int s = 0; s < 5; ++s)
         if (h.bytes[s] != want[s]) { set_error("%s: section %d holds %llu bytes, the header implies %llu", path, s, (unsigned long long)h.bytes[s], (unsigned long long)want[s]); return FMB_EINVAL; }
     {
@@ -172,7 +175,8 @@ static int load_impl(fmb_index** out, int device, const char* path) {
         if (checksum64(sec[s], h.bytes[s]) != h.sum[s]) { set_error("%s: checksum mismatch in section %d", path, s); return FMB_EINVAL; }
     }
     if (fgetc(f.get()) != EOF) { set_error("%s: trailing bytes after the last section", path); return FMB_EINVAL; }
-    return fmb_index_create(out, device, h.sigma, h.n, bwt.data(), h.bidirectional ? bwt_rev.data() : nullptr, bitmap.data(), seq.data(), pos.data(), h.n_samples);
+    return fmb_index_create_ex(out, device, h.sigma, h.n, bwt.data(), has_rev ? bwt_rev.data() : nullptr, bitmap.data(), seq.data(), pos.data(), h.n_samples,
+                               ((h.bidirectional & 2u) ? FMB_INDEX_NO_DELIM : 0u) | ((h.bidirectional & 4u) ? FMB_INDEX_REUSE_REV : 0u));
 }
 
 }  // extern "C"

@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(256) jump_init_kernel(const __grid_constant__ 
     const OCC& occ = ix.occ[dir];
     typename OCC::Block b = occ.load((uint32_t)(i >> 6), 0);
     uint32_t y = occ.symbol(b, (row_t)i);
-    if (y == 0) { out[i] = make_uint2(kJumpInvalid, 0); return; }
+    if (y < ix.first_symb) { out[i] = make_uint2(kJumpInvalid, 0); return; }      // a delimiter: nothing jumps across it
     if (OCC::kSymbolLoad) b = occ.load((uint32_t)(i >> 6), y);
     out[i] = make_uint2(ix.C[y] + occ.rank(b, (row_t)i, y), OCC::kSymbolLoad ? y : y - 1);
 }
@@ -780,12 +780,17 @@ __global__ void __launch_bounds__(256, MINB) exact_search2_kernel(const __grid_c
                 pos -= 2;
             }
         }
+        // the hit record of the query (dense: len == 0 when the pattern does not occur) + its length for locate's scan: the four
+        // lanes of the group hold the same state, three of them write 8 bytes of the 24-byte record each (a warp's eight records are
+        // 192 contiguous bytes), the fourth the length
+        {
+            uint2* rec = reinterpret_cast<uint2*>(out_hits + q);
+            if (sub == 0) rec[0] = make_uint2(q + qidx_base, lb);           // qidx, lb
+            else if (sub == 1) rec[1] = make_uint2(0u, len);                 // lb_rev, len
+            else if (sub == 2) rec[2] = make_uint2(L, 0u);                   // steps, e
+            else out_len[q] = len;
+        }
         if (sub == 0) {
-            // the hit record of the query (dense: len == 0 when the pattern does not occur) + its length for locate's scan
-            HitRec h;
-            h.qidx = q + qidx_base; h.lb = lb; h.lb_rev = 0; h.len = len; h.steps = L; h.e = 0;
-            out_hits[q] = h;
-            out_len[q] = len;
             found = len ? 1u : 0u;
             rows = len;
         }

@@ -192,14 +192,16 @@ using namespace fmb;
 fmb::IndexView<fmb::OccDna> fmb_index::view_dna() const {
     fmb::IndexView<fmb::OccDna> v{};
     for (int d = 0; d < 2; ++d) {
-        v.occ[d].blocks = occ_dna[d].p;
-        v.occ[d].delim_rows = delim_rows[d].p;
+        const int src = reuse_rev ? 0 : d;          // ReuseRev: extendRight reads the same BWT (fmindex/BiFMIndexCursor.h fetchRightBwt)
+        v.occ[d].blocks = occ_dna[src].p;
+        v.occ[d].delim_rows = delim_rows[src].p;
         v.occ[d].n_delims = (uint32_t)n_delims;
-        v.occ[d].delim0 = delim0[d];
+        v.occ[d].delim0 = delim0[src];
     }
     for (uint32_t s = 0; s <= sigma; ++s) v.C[s] = (uint32_t)C[s];
     v.n = (row_t)n;
     v.sigma = sigma;
+    v.first_symb = first_symb;
     v.marks = marks.p;
     v.samples = samples.p;
     v.locblocks = locblocks.p;
@@ -211,7 +213,7 @@ fmb::IndexView<fmb::OccDna> fmb_index::view_dna() const {
 fmb::IndexView<fmb::OccGen> fmb_index::view_gen() const {
     fmb::IndexView<fmb::OccGen> v{};
     for (int d = 0; d < 2; ++d) {
-        v.occ[d].blocks = occ_gen[d].p;
+        v.occ[d].blocks = occ_gen[reuse_rev ? 0 : d].p;
         v.occ[d].stride = gen_stride;
         v.occ[d].planes = gen_planes;
         v.occ[d].sigma = sigma;
@@ -219,6 +221,7 @@ fmb::IndexView<fmb::OccGen> fmb_index::view_gen() const {
     for (uint32_t s = 0; s <= sigma; ++s) v.C[s] = (uint32_t)C[s];
     v.n = (row_t)n;
     v.sigma = sigma;
+    v.first_symb = first_symb;
     v.marks = marks.p;
     v.samples = samples.p;
     v.locblocks = nullptr;
@@ -607,7 +610,7 @@ int build_marks_from_device(fmb_index* ix, const uint64_t* d_bitmap, const uint3
     return FMB_OK;
 }
 
-int new_index(fmb_index** out, int device, uint32_t sigma, uint64_t n, bool bidirectional) {
+int new_index(fmb_index** out, int device, uint32_t sigma, uint64_t n, bool bidirectional, uint32_t flags) {
     if (!out) { set_error("out is NULL"); return FMB_EINVAL; }
     *out = nullptr;
     if (sigma < 2 || sigma > 32) { set_error("sigma %u outside [2,32]", sigma); return FMB_EINVAL; }
@@ -619,7 +622,10 @@ int new_index(fmb_index** out, int device, uint32_t sigma, uint64_t n, bool bidi
     ix->sigma = sigma;
     ix->n = n;
     ix->bidirectional = bidirectional;
-    ix->dna = sigma <= 5;
+    ix->first_symb = (flags & FMB_INDEX_NO_DELIM) ? 0u : 1u;
+    ix->reuse_rev = (flags & FMB_INDEX_REUSE_REV) != 0;
+    // without delimiter symbol 0 is as frequent as any other symbol: the generic layout treats all symbols alike
+    ix->dna = sigma <= 5 && ix->first_symb == 1;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete ix; return FMB_ECUDA; }
     ix->stream = ix->own_stream;
@@ -662,10 +668,17 @@ int fmb_device_count(void) {
 
 int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n, const uint8_t* bwt, const uint8_t* bwt_rev,
                      const uint64_t* sample_bitmap, const uint32_t* sample_seq, const uint32_t* sample_pos, uint64_t n_samples) {
+    return fmb_index_create_ex(out, device, sigma, n, bwt, bwt_rev, sample_bitmap, sample_seq, sample_pos, n_samples, 0);
+}
+
+int fmb_index_create_ex(fmb_index** out, int device, uint32_t sigma, uint64_t n, const uint8_t* bwt, const uint8_t* bwt_rev,
+                        const uint64_t* sample_bitmap, const uint32_t* sample_seq, const uint32_t* sample_pos, uint64_t n_samples, uint32_t flags) {
     if (!bwt) { set_error("bwt is NULL"); return FMB_EINVAL; }
     if (n_samples && (!sample_bitmap || !sample_seq || !sample_pos)) { set_error("sample arrays missing"); return FMB_EINVAL; }
+    if (flags & ~(FMB_INDEX_NO_DELIM | FMB_INDEX_REUSE_REV)) { set_error("unknown index flags 0x%x", flags); return FMB_EINVAL; }
+    if ((flags & FMB_INDEX_REUSE_REV) && bwt_rev) { set_error("a ReuseRev index has no bwtRev"); return FMB_EINVAL; }
     fmb_index* ix = nullptr;
-    FMB_TRY(new_index(&ix, device, sigma, n, bwt_rev != nullptr));
+    FMB_TRY(new_index(&ix, device, sigma, n, bwt_rev != nullptr || (flags & FMB_INDEX_REUSE_REV), flags));
     auto fail = [&](int rc) { fmb_index_destroy(ix); return rc; };
     {
         DevBuf<uint8_t> d_bwt;
@@ -721,7 +734,8 @@ int fmb_index_replicate(const fmb_index* src, int device, fmb_index** out) {
     *out = nullptr;
     if (device == src->device) { set_error("replica on the device of the original (%d)", device); return FMB_EINVAL; }
     fmb_index* ix = nullptr;
-    FMB_TRY(new_index(&ix, device, src->sigma, src->n, src->bidirectional));      // makes `device` current
+    FMB_TRY(new_index(&ix, device, src->sigma, src->n, src->bidirectional,
+                      (src->first_symb ? 0u : FMB_INDEX_NO_DELIM) | (src->reuse_rev ? FMB_INDEX_REUSE_REV : 0u)));      // makes `device` current
     int can = 0;
     if (cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
         cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0);
@@ -791,6 +805,7 @@ int fmb_index_get_info(const fmb_index* ix, fmb_index_info* info) {
     info->occ_block_bytes = ix->dna ? 32 : ix->gen_stride;
     info->occ_block_rows = 64;
     info->device = ix->device;
+    info->flags = (ix->first_symb ? 0u : FMB_INDEX_NO_DELIM) | (ix->reuse_rev ? FMB_INDEX_REUSE_REV : 0u);
     info->tables = (ix->occ2[0].p ? FMB_TABLE_PAIR : 0) | (ix->kmer.p ? FMB_TABLE_KMER : 0) | (ix->jump[0].p ? FMB_TABLE_JUMP : 0) |
                    (ix->jump[1].p ? FMB_TABLE_JUMP_REV : 0) | (ix->locblocks.p ? FMB_TABLE_LOCBLOCK : 0) | (ix->locrow.p ? FMB_TABLE_LOCROW : 0) |
                    (ix->bikmer.p ? FMB_TABLE_BIKMER : 0) | (ix->jump4[0].p ? FMB_TABLE_JUMP4 : 0) | (ix->jump_shift[0] ? FMB_TABLE_JUMP32 : 0);
@@ -810,7 +825,7 @@ int fmb_index_export(const fmb_index* ix, uint8_t* bwt, uint8_t* bwt_rev, uint64
     for (int d = 0; d < 2; ++d) {
         uint8_t* dst = d ? bwt_rev : bwt;
         if (!dst) continue;
-        if (d == 1 && !ix->bidirectional) { set_error("index has no bwtRev"); return FMB_EINVAL; }
+        if (d == 1 && (!ix->bidirectional || ix->reuse_rev)) { set_error("index has no bwtRev"); return FMB_EINVAL; }
         DevBuf<uint8_t> tmp;
         FMB_TRY(tmp.alloc(ix->n));
         FMB_DISPATCH(ix, v, unpack_bwt_kernel<<<grid_for(ix->n, 256), 256, 0, st>>>(v, d, tmp.p));
@@ -835,6 +850,24 @@ int fmb_index_export(const fmb_index* ix, uint8_t* bwt, uint8_t* bwt_rev, uint64
             if (sample_pos) sample_pos[i] = h[i].y;
         }
     }
+    return FMB_OK;
+}
+
+// raw bytes of the one-symbol occurrence table of direction `dir` (the blocks the kernels read): layout parity with fmb200::HostMirror
+int fmb_index_export_blocks(const fmb_index* ix, int dir, uint8_t* out, uint64_t capacity, uint64_t* bytes, uint32_t* block_bytes) {
+    if (!ix || !bytes) { set_error("NULL argument"); return FMB_EINVAL; }
+    if (dir < 0 || dir > 1 || (dir == 1 && !ix->bidirectional)) { set_error("dir %d not available", dir); return FMB_EINVAL; }
+    if (ix->reuse_rev) dir = 0;
+    const uint64_t nblocks = ix->n / 64 + 1;
+    const uint32_t stride = ix->dna ? 32u : ix->gen_stride;
+    *bytes = nblocks * stride;
+    if (block_bytes) *block_bytes = stride;
+    if (!out) return FMB_OK;
+    if (capacity < *bytes) { set_error("capacity %llu < %llu bytes", (unsigned long long)capacity, (unsigned long long)*bytes); return FMB_EOVERFLOW; }
+    FMB_TRY(use_device(ix->device));
+    const void* src = ix->dna ? (const void*)ix->occ_dna[dir].p : (const void*)ix->occ_gen[dir].p;
+    FMB_CUDA(cudaStreamSynchronize(active_stream(ix)));
+    FMB_CUDA(cudaMemcpy(out, src, *bytes, cudaMemcpyDeviceToHost));
     return FMB_OK;
 }
 

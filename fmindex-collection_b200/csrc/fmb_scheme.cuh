@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
     uint32_t n_ext = 0, n_look = 0, n_phys = 0, peak = 0;
     bool more_roots = true;
     const uint32_t np = sp.n_parts;
-    const uint32_t first_symb = 1;       // FirstSymb of delimited indices (fmindex/BiFMIndex.h:26)
+    const uint32_t first_symb = ix.first_symb;   // FirstSymb (fmindex/BiFMIndex.h:26): 1 for delimited indices, 0 for NoDelim
     const bool sim_all = (ff_min >> 8) & 1;      // simulate error children at every error level, not only the last one
     ff_min &= 0xFF;
 

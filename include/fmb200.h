@@ -9,7 +9,8 @@
  *   - plain C types; the caller owns every host buffer, the library owns all device memory;
  *   - every function returns 0 on success or a negative FMB_E* code; fmb_last_error() (thread local) has the text;
  *   - no CPU fallback: without a usable CUDA device every compute entry point fails with FMB_ENODEVICE;
- *   - symbols are uint8_t in [0, sigma); symbol 0 is the sequence delimiter (fmindex/BiFMIndex.h:26 FirstSymb=1);
+ *   - symbols are uint8_t in [0, sigma); symbol 0 is the sequence delimiter (fmindex/BiFMIndex.h:26 FirstSymb=1) unless the
+ *     index was created with FMB_INDEX_NO_DELIM;
  *   - rows / text positions are 64-bit in the interface; this build supports indices with n < 2^32 - 64 rows;
  *   - one fmb_index lives on one GPU.  Multi-GPU = one index replica per device (fmb_index_replicate), queries sharded by
  *     fmb_search_and_locate_multi or by the caller (one process per GPU: bench.py); there is no collective on the search path.
@@ -65,6 +66,7 @@ typedef struct {
     uint32_t occ_block_rows;   /* BWT rows covered by one occ block                        */
     int32_t  device;
     uint32_t tables;           /* optional accelerating tables the image holds, FMB_TABLE_* bits  */
+    uint32_t flags;            /* FMB_INDEX_* variant bits                                  */
 } fmb_index_info;
 #define FMB_TABLE_PAIR     1u   /* two-symbol pair table (128-byte lines)          */
 #define FMB_TABLE_KMER     2u   /* k-mer interval table                            */
@@ -103,6 +105,18 @@ int fmb_index_create(fmb_index** out, int device, uint32_t sigma, uint64_t n,
                      const uint64_t* sample_bitmap, const uint32_t* sample_seq, const uint32_t* sample_pos,
                      uint64_t n_samples);
 
+/* The index variants of the reference (fmindex/BiFMIndex.h:17-28): BiFMIndex<...>::NoDelim -- FirstSymb = 0, symbol 0 is an ordinary
+ * symbol of an omega-sorted (circular) text instead of the sequence delimiter -- and BiFMIndex<...>::ReuseRev -- no bwtRev: the one BWT
+ * of text + reversed text serves both directions (fmindex/BiFMIndexCursor.h fetchRightBwt).  bwt_rev must be NULL with
+ * FMB_INDEX_REUSE_REV.  Indices without delimiter use the generic occurrence-table layout whatever their alphabet size.  The GPU
+ * builder (fmb_index_build) produces delimited indices only; these variants are created from the BWT of a reference index. */
+#define FMB_INDEX_NO_DELIM   1u
+#define FMB_INDEX_REUSE_REV  2u
+int fmb_index_create_ex(fmb_index** out, int device, uint32_t sigma, uint64_t n,
+                        const uint8_t* bwt, const uint8_t* bwt_rev,
+                        const uint64_t* sample_bitmap, const uint32_t* sample_seq, const uint32_t* sample_pos,
+                        uint64_t n_samples, uint32_t flags);
+
 /* Replaces BiFMIndex(Sequences, samplingRate, threads) (fmindex/BiFMIndex.h:107-167) / FMIndex(Sequences, ...)
  * (fmindex/FMIndex.h:58-112): `text` is the concatenation s0 0 s1 0 ... built by createSequences
  * (utils.h:382-464).  Suffix sorting (libsais in the reference, utils.h:97-129), BWT (utils.h:145-163), the BWT
@@ -132,6 +146,11 @@ int  fmb_index_get_C(const fmb_index* ix, uint64_t* C /* sigma+1 */);           
  * the same data (BiFMIndex.h:40). */
 int fmb_index_export(const fmb_index* ix, uint8_t* bwt, uint8_t* bwt_rev, uint64_t* sample_bitmap,
                      uint32_t* sample_seq, uint32_t* sample_pos);
+
+/* Raw bytes of the one-symbol occurrence table of direction `dir` -- the blocks the kernels read (layout in csrc/fmb_device.cuh; 32 bytes
+ * per 64 rows for sigma <= 5, *block_bytes per 64 rows otherwise).  out == NULL only reports the size.  fmb200::HostMirror<Sigma>
+ * (fmb200/host_mirror.hpp), the host-side String_c over the same layout (string/concepts.h:26-87), produces identical bytes. */
+int fmb_index_export_blocks(const fmb_index* ix, int dir, uint8_t* out, uint64_t capacity, uint64_t* bytes, uint32_t* block_bytes);
 
 /* ---- String_c concept, batched (string/concepts.h:26-87).  dir 0 = bwt, 1 = bwtRev.  All pointers host. ---- */
 int fmb_string_symbol(const fmb_index* ix, int dir, const uint64_t* idx, uint64_t count, uint8_t* out);

@@ -23,7 +23,7 @@ namespace fmb200 {
 template <typename RefIndex, template <typename> class Cursor, template <typename> class LeftCursor>
 struct Attached {
     static constexpr size_t Sigma = RefIndex::Sigma;
-    static constexpr size_t FirstSymb = 1;
+    static constexpr size_t FirstSymb = [] { if constexpr (requires { RefIndex::FirstSymb; }) return size_t{RefIndex::FirstSymb}; else return size_t{1}; }();
     using cursor_t = Cursor<RefIndex>;
     using left_cursor_t = LeftCursor<RefIndex>;
     using LEntry = std::tuple<uint32_t, uint32_t, size_t>;
@@ -42,7 +42,10 @@ struct Attached {
 
 template <template <typename> class Cursor, template <typename> class LeftCursor, typename RefIndex>
 auto attach(RefIndex const& ref, int device = 0) -> Attached<RefIndex, Cursor, LeftCursor> {
-    constexpr bool bidirectional = requires { ref.bwtRev.symbol(size_t{}); };
+    // BiFMIndex<...>::NoDelim / ::ReuseRev (fmindex/BiFMIndex.h:22-28): the variant flags of the reference index carry over
+    constexpr bool noDelim = [] { if constexpr (requires { RefIndex::Delim_v; }) return !RefIndex::Delim_v; else return false; }();
+    constexpr bool reuseRev = [] { if constexpr (requires { RefIndex::ReuseRev_v; }) return bool{RefIndex::ReuseRev_v}; else return false; }();
+    constexpr bool bidirectional = requires { ref.bwtRev.symbol(size_t{}); };          // a stored bwtRev (not with ReuseRev)
     size_t const n = ref.size();
     std::vector<uint8_t> bwt(n), bwtRev;
     for (size_t i = 0; i < n; ++i) bwt[i] = static_cast<uint8_t>(ref.bwt.symbol(i));
@@ -61,13 +64,13 @@ auto attach(RefIndex const& ref, int device = 0) -> Attached<RefIndex, Cursor, L
         sa.pos.push_back(static_cast<uint32_t>(std::get<1>(*v)));
     }
     fmb_index* raw{};
-    check(fmb_index_create(&raw, device, RefIndex::Sigma, n, bwt.data(), bidirectional ? bwtRev.data() : nullptr, sa.bitmap.data(), sa.seq.data(),
-                           sa.pos.data(), sa.seq.size()));
+    check(fmb_index_create_ex(&raw, device, RefIndex::Sigma, n, bwt.data(), bidirectional ? bwtRev.data() : nullptr, sa.bitmap.data(), sa.seq.data(),
+                              sa.pos.data(), sa.seq.size(), (noDelim ? FMB_INDEX_NO_DELIM : 0u) | (reuseRev ? FMB_INDEX_REUSE_REV : 0u)));
     Attached<RefIndex, Cursor, LeftCursor> a;
     a.ref = &ref;
     a.h.reset(raw);
     a.bwt = DeviceString<RefIndex::Sigma>{raw, 0, n};
-    a.bwtRev = DeviceString<RefIndex::Sigma>{raw, bidirectional ? 1 : 0, n};
+    a.bwtRev = DeviceString<RefIndex::Sigma>{raw, (bidirectional || reuseRev) ? 1 : 0, n};
     // the device C must equal the reference's (utils.h:200-206)
     uint64_t c[RefIndex::Sigma + 1];
     check(fmb_index_get_C(raw, c));

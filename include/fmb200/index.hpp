@@ -162,10 +162,11 @@ template <typename Index> struct FMIndexCursor;
 
 namespace detail {
 // common part of both index kinds
-template <size_t TSigma, bool Bidirectional>
+template <size_t TSigma, bool Bidirectional, bool TDelim = true>
 struct IndexBase {
     static constexpr size_t Sigma = TSigma;
-    static constexpr size_t FirstSymb = 1;        // delimited indices only (BiFMIndex.h:26 with TDelim = true)
+    static constexpr size_t FirstSymb = TDelim ? 1 : 0;        // BiFMIndex.h:26
+    static constexpr bool Delim_v = TDelim;
     using ADEntry = std::tuple<uint32_t, uint32_t>;
     using LEntry = std::tuple<uint32_t, uint32_t, size_t>;
 
@@ -232,28 +233,48 @@ protected:
 }  // namespace detail
 
 // ---- BiFMIndex (fmindex/BiFMIndex.h:17-215) -----------------------------------------------------------------------
-template <size_t TSigma>
-struct BiFMIndex : detail::IndexBase<TSigma, true> {
-    using Base = detail::IndexBase<TSigma, true>;
+// TDelim = false: BiFMIndex<...>::NoDelim (FirstSymb = 0, omega-sorted text); TReuseRev = true: BiFMIndex<...>::ReuseRev (no bwtRev:
+// the BWT of text + reversed text serves both directions).  Both variants are created from BWT bytes (of a reference index, see
+// fmb200::attach); the GPU builder behind the Sequences constructor produces delimited indices with a bwtRev.
+template <size_t TSigma, bool TDelim = true, bool TReuseRev = false>
+struct BiFMIndex : detail::IndexBase<TSigma, true, TDelim> {
+    using Base = detail::IndexBase<TSigma, true, TDelim>;
     using Base::Sigma;
-    DeviceString<TSigma> bwtRev;
+    using NoDelim = BiFMIndex<TSigma, false, TReuseRev>;
+    using ReuseRev = BiFMIndex<TSigma, TDelim, true>;
+    static constexpr bool ReuseRev_v = TReuseRev;
+    DeviceString<TSigma> bwtRev;        // ReuseRev: a view of the same BWT (extendRight reads it, BiFMIndexCursor.h fetchRightBwt)
 
     BiFMIndex() = default;
     BiFMIndex(BiFMIndex&&) noexcept = default;
     auto operator=(BiFMIndex&&) noexcept -> BiFMIndex& = default;
 
     // BiFMIndex(bwt, bwtRev, SparseArray), BiFMIndex.h:40-51
-    BiFMIndex(std::span<uint8_t const> _bwt, std::span<uint8_t const> _bwtRev, SparseArray const& sa, int device = 0) {
+    BiFMIndex(std::span<uint8_t const> _bwt, std::span<uint8_t const> _bwtRev, SparseArray const& sa, int device = 0)
+        requires(!TReuseRev)
+    {
         if (_bwt.size() != _bwtRev.size())
             throw std::runtime_error("bwt don't have the same size: " + std::to_string(_bwt.size()) + " " + std::to_string(_bwtRev.size()));
         fmb_index* raw{};
-        check(fmb_index_create(&raw, device, Sigma, _bwt.size(), _bwt.data(), _bwtRev.data(), sa.bitmap.data(), sa.seq.data(), sa.pos.data(), sa.seq.size()));
+        check(fmb_index_create_ex(&raw, device, Sigma, _bwt.size(), _bwt.data(), _bwtRev.data(), sa.bitmap.data(), sa.seq.data(), sa.pos.data(), sa.seq.size(),
+                                  TDelim ? 0u : FMB_INDEX_NO_DELIM));
+        init(raw);
+    }
+    // BiFMIndex(bwt, SparseArray) of the ReuseRev variant, BiFMIndex.h:53-58
+    BiFMIndex(std::span<uint8_t const> _bwt, SparseArray const& sa, int device = 0)
+        requires(TReuseRev)
+    {
+        fmb_index* raw{};
+        check(fmb_index_create_ex(&raw, device, Sigma, _bwt.size(), _bwt.data(), nullptr, sa.bitmap.data(), sa.seq.data(), sa.pos.data(), sa.seq.size(),
+                                  FMB_INDEX_REUSE_REV | (TDelim ? 0u : FMB_INDEX_NO_DELIM)));
         init(raw);
     }
     // BiFMIndex(Sequences, samplingRate, threadNbr), BiFMIndex.h:107-167 (suffix sorting runs on the GPU; threadNbr is
     // accepted for signature compatibility)
     template <Sequences seqs_t>
-    BiFMIndex(seqs_t const& input, size_t samplingRate, size_t /*threadNbr*/ = 1, int device = 0) {
+    BiFMIndex(seqs_t const& input, size_t samplingRate, size_t /*threadNbr*/ = 1, int device = 0)
+        requires(TDelim && !TReuseRev)
+    {
         auto text = Base::concat(input);
         fmb_index* raw{};
         check(fmb_index_build(&raw, device, Sigma, text.data(), text.size(), static_cast<uint32_t>(samplingRate), 1, 0));
@@ -265,6 +286,10 @@ struct BiFMIndex : detail::IndexBase<TSigma, true> {
 private:
     void init(fmb_index* raw) {
         Base::adopt(raw);
+        fmb_index_info i{};
+        check(fmb_index_get_info(raw, &i));
+        if (((i.flags & FMB_INDEX_NO_DELIM) != 0) == TDelim || ((i.flags & FMB_INDEX_REUSE_REV) != 0) != TReuseRev)
+            throw std::runtime_error("fmb200: index variant (NoDelim / ReuseRev) does not match the index type");
         bwtRev = DeviceString<TSigma>{raw, 1, this->bwt.n};
     }
 };

@@ -5,7 +5,8 @@
 //   search/SearchNoErrors.h:13-26,28-85   search_no_errors::search(index, query) / (index, queries, delegate(qidx, cursor))
 //   search/SearchNg26.h:426-444           search_ng26::search<Edit>(index, queries, scheme, partition, delegate(qidx, cursor, e))
 //                                         search_ng26::search<Edit>(index, queries, maxErrors, delegate)
-//   search/Backtracking.h:85-98           search_backtracking::search(index, queries, maxError, delegate(qidx, cursor, e))
+//   search/Backtracking.h:85-98           search_backtracking::search(index, queries, maxError, delegate(qidx, cursor, e)) / one query
+//   search/BacktrackingWithBuffers.h:93   search_backtracking_with_buffers::search(index, query, maxError, buffer1, buffer2, delegate(cursor, e))
 //   search/SearchOneError.h:126-145       search_one_error::search(index, queries, delegate(qidx, cursor, e))
 //   search/SearchPseudo.h:171-186         search_pseudo::search<Edit>(index, queries, expanded scheme, delegate(qidx, cursor, e))
 //   search/search.h:14-75                 fmc::search<Edit>(index, queries, errors, delegate), fmc::Search{...}()
@@ -445,7 +446,28 @@ void search(index_t const& index, queries_t&& queries, size_t maxError, delegate
     for (auto const& h : search_bulk(index, queries, maxError)) delegate(static_cast<size_t>(h.qidx), detail::make_cursor(index, h), static_cast<size_t>(h.e));
 }
 
+// Backtracking.h:90-98: one query, delegate(cursor, errors)
+template <typename index_t, Sequence query_t, typename delegate_t>
+    requires(!Sequences<query_t>)
+void search(index_t const& index, query_t const& query, size_t maxError, delegate_t&& delegate) {
+    std::vector<std::vector<uint8_t>> one(1);
+    for (auto c : query) one[0].push_back(static_cast<uint8_t>(c));
+    for (auto const& h : search_bulk(index, one, maxError)) delegate(detail::make_cursor(index, h), static_cast<size_t>(h.e));
+}
+
 }  // namespace search_backtracking
+
+// search/BacktrackingWithBuffers.h:93-106: the same search with caller-provided frontier buffers, one query, delegate(cursor, errors).
+// The reference keeps its breadth-first frontier in buffer1 / buffer2; here the frontier lives in the shared memory of the kernel, the
+// buffers are accepted for signature compatibility and left empty, as the reference leaves them (:66).
+namespace search_backtracking_with_buffers {
+template <typename index_t, Sequence query_t, typename buffer_t, typename delegate_t>
+void search(index_t const& index, query_t const& query, size_t maxError, buffer_t& buffer1, buffer_t& buffer2, delegate_t&& delegate) {
+    buffer1.clear();
+    buffer2.clear();
+    search_backtracking::search(index, query, maxError, delegate);
+}
+}  // namespace search_backtracking_with_buffers
 
 // =====================================================================================================================
 // locate.h:15-57: range over the (seqId, pos, offset) entries of every row of a cursor.  All rows are located by

@@ -7,6 +7,7 @@
 #include <fmindex-collection/fmindex/FMIndex.h>
 #include <fmindex-collection/locate.h>
 #include <fmindex-collection/search/Backtracking.h>
+#include <fmindex-collection/search/BacktrackingWithBuffers.h>
 #include <fmindex-collection/search/SearchNg26.h>
 #include <fmindex-collection/search/SearchNoErrors.h>
 #include <fmindex-collection/search/SearchOneError.h>
@@ -121,6 +122,20 @@ int main() {
         ref.sort(); gpu.sort();
         CHECK(ref.cursors == gpu.cursors);
         CHECK(ref.located == gpu.located);
+        // one query at a time: Backtracking.h:90-98 and the buffered variant (BacktrackingWithBuffers.h:93-106)
+        Collector ref1{index}, gpu1{index}, refb{index}, gpub{index};
+        using RefBuf = std::vector<std::pair<fmc::select_cursor_t<RefIndex>, size_t>>;
+        RefBuf rb1, rb2;
+        std::vector<int> gb1, gb2;
+        for (size_t q = 0; q < 20; ++q) {
+            fmc::search_backtracking::search(index, shortq[q], 1, [&](auto c, size_t e) { ref1(q, c, e); });
+            fmb200::search_backtracking::search(dev, shortq[q], 1, [&](auto c, size_t e) { gpu1(q, c, e); });
+            fmc::search_backtracking_with_buffers::search(index, shortq[q], 1, rb1, rb2, [&](auto c, size_t e) { refb(q, c, e); });
+            fmb200::search_backtracking_with_buffers::search(dev, shortq[q], 1, gb1, gb2, [&](auto c, size_t e) { gpub(q, c, e); });
+        }
+        ref1.sort(); gpu1.sort(); refb.sort(); gpub.sort();
+        CHECK(!ref1.cursors.empty() && ref1.cursors == gpu1.cursors && ref1.located == gpu1.located);
+        CHECK(refb.cursors == gpub.cursors && refb.located == gpub.located && refb.cursors == ref1.cursors);
     }
     // search_best: list of (scheme, partition) pairs, and the maxErrors form (SearchNg26.h:448-487)
     {
@@ -258,6 +273,108 @@ int main() {
             auto b = index.locate(i);
             CHECK(std::get<0>(a) == std::get<0>(b) && std::get<1>(a) == std::get<1>(b) && std::get<2>(a) == std::get<2>(b));
         }
+    }
+    // ---- seam 2: the device block layout as a String_c inside the REFERENCE's index type ----------------
+    {
+        static_assert(fmc::String_c<fmb200::HostMirror<5>> && fmc::String_c<fmb200::HostMirror<21>> && fmc::String_c<fmb200::HostMirror<2>>);
+        using MirrorIndex = fmc::BiFMIndex<5, fmb200::HostMirror>;
+        auto mirror = MirrorIndex{seqs, /*samplingRate*/ 16, /*threadNbr*/ 1};
+        // the mirror's blocks are the bytes the kernels read, for both directions
+        for (int dir = 0; dir < 2; ++dir) {
+            uint64_t bytes = 0;
+            uint32_t stride = 0;
+            CHECK(fmb_index_export_blocks(dev.handle(), dir, nullptr, 0, &bytes, &stride) == 0 && stride == 32);
+            std::vector<uint8_t> devBlocks(bytes);
+            CHECK(fmb_index_export_blocks(dev.handle(), dir, devBlocks.data(), devBlocks.size(), &bytes, &stride) == 0);
+            auto const host = dir == 0 ? mirror.bwt.blocks() : mirror.bwtRev.blocks();
+            CHECK(host.size() == devBlocks.size() && std::equal(host.begin(), host.end(), devBlocks.begin()));
+        }
+        // String_c answers of the mirror == the reference's interleaved bit vectors, row by row
+        bool same = true;
+        for (size_t idx = 0; idx <= index.size() && same; idx += 1 + idx % 7) {
+            for (uint8_t s = 0; s < 5 && same; ++s)
+                same = mirror.bwt.rank(idx, s) == index.bwt.rank(idx, s) && mirror.bwt.prefix_rank(idx, s) == index.bwt.prefix_rank(idx, s) &&
+                       mirror.bwtRev.rank(idx, s) == index.bwtRev.rank(idx, s);
+            if (idx < index.size()) same = same && mirror.bwt.symbol(idx) == index.bwt.symbol(idx);
+            same = same && mirror.bwt.all_ranks_and_prefix_ranks(idx) == index.bwt.all_ranks_and_prefix_ranks(idx);
+        }
+        CHECK(same);
+        // the reference's k-error search on the mirror layout == the reference on its own layout == the GPU
+        auto scheme = fmc::search_scheme::generator::optimum(0, 2);
+        auto partition = fmc::search_scheme::createUniformPartition(scheme, 50);
+        std::vector<Row> a, b, c;
+        fmc::search_ng26::search<true>(mirror, queries, scheme, partition, [&](size_t q, auto cur, size_t e) { a.push_back({q, cur.lb, cur.lbRev, cur.len, cur.steps, e}); });
+        fmc::search_ng26::search<true>(index, queries, scheme, partition, [&](size_t q, auto cur, size_t e) { b.push_back({q, cur.lb, cur.lbRev, cur.len, cur.steps, e}); });
+        fmb200::search_ng26::search<true>(dev, queries, scheme, partition, [&](size_t q, auto cur, size_t e) { c.push_back({q, cur.lb, cur.lbRev, cur.len, cur.steps, e}); });
+        std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end()); std::sort(c.begin(), c.end());
+        CHECK(!a.empty() && a == b && a == c);
+        // generic layout (sigma = 21) against the device's blocks
+        std::vector<std::vector<uint8_t>> prot(2);
+        for (auto& s : prot) { s.resize(3000); for (auto& ch : s) ch = 1 + rng() % 20; }
+        fmb200::BiFMIndex<21> pdev{prot, 8};
+        auto pmir = fmc::BiFMIndex<21, fmb200::HostMirror>{prot, 8, 1};
+        uint64_t bytes = 0;
+        uint32_t stride = 0;
+        CHECK(fmb_index_export_blocks(pdev.handle(), 0, nullptr, 0, &bytes, &stride) == 0 && stride == 128);
+        std::vector<uint8_t> pb(bytes);
+        CHECK(fmb_index_export_blocks(pdev.handle(), 0, pb.data(), pb.size(), &bytes, &stride) == 0);
+        CHECK(pmir.bwt.blocks().size() == pb.size() && std::equal(pb.begin(), pb.end(), pmir.bwt.blocks().begin()));
+    }
+    // ---- index variants: BiFMIndex<...>::ReuseRev (one BWT of text + reversed text for both directions) and ::NoDelim (FirstSymb = 0,
+    //      omega-sorted text), fmindex/BiFMIndex.h:22-28, 53-72 -- the reference's own objects, attached, searched by both sides ----------
+    {
+        auto compare = [&](auto const& rindex, auto const& rdev, std::vector<std::vector<uint8_t>> const& qs, char const* what) {
+            using RI = std::remove_cvref_t<decltype(rindex)>;
+            for (size_t k : {1, 2}) {
+                auto scheme = fmc::search_scheme::generator::optimum(0, k);
+                auto partition = fmc::search_scheme::createUniformPartition(scheme, 50);
+                for (int edit = 0; edit < 2; ++edit) {
+                    std::vector<Row> a, b, la, lb;
+                    auto ra = [&](size_t q, auto cur, size_t e) {
+                        a.push_back({q, cur.lb, cur.lbRev, cur.len, cur.steps, e});
+                        for (auto [sid, spos, offset] : fmc::LocateLinear{rindex, cur}) la.push_back({q, sid, spos + offset, e, 0, 0});
+                    };
+                    auto rb = [&](size_t q, auto cur, size_t e) {
+                        static_assert(std::same_as<decltype(cur), fmc::BiFMIndexCursor<RI>>);
+                        b.push_back({q, cur.lb, cur.lbRev, cur.len, cur.steps, e});
+                        for (auto [sid, spos, offset] : fmb200::LocateLinear{rdev, cur}) lb.push_back({q, sid, spos + offset, e, 0, 0});
+                    };
+                    if (edit) { fmc::search_ng26::search<true>(rindex, qs, scheme, partition, ra); fmb200::search_ng26::search<true>(rdev, qs, scheme, partition, rb); }
+                    else { fmc::search_ng26::search<false>(rindex, qs, scheme, partition, ra); fmb200::search_ng26::search<false>(rdev, qs, scheme, partition, rb); }
+                    std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end()); std::sort(la.begin(), la.end()); std::sort(lb.begin(), lb.end());
+                    if (a != b || la != lb || a.empty()) std::fprintf(stderr, "variant %s k=%zu edit=%d: %zu vs %zu cursors, %zu vs %zu rows\n", what, k, edit, a.size(), b.size(), la.size(), lb.size());
+                    CHECK(!a.empty() && a == b);
+                    CHECK(la == lb);
+                }
+            }
+            std::vector<Row> a, b;
+            fmc::search_no_errors::search(rindex, qs, [&](size_t q, auto cur) { a.push_back({q, cur.lb, 0, cur.len, cur.steps, 0}); });
+            fmb200::search_no_errors::search(rdev, qs, [&](size_t q, auto cur) { b.push_back({q, cur.lb, 0, cur.len, cur.steps, 0}); });
+            std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
+            CHECK(!a.empty() && a == b);
+        };
+        // ReuseRev: the text must hold every sequence and its reversal (includeReversedInput)
+        using RevIndex = RefIndex::ReuseRev;
+        auto rindex = RevIndex{seqs, /*samplingRate*/ 16, /*threadNbr*/ 1, /*seqOffset*/ 0, /*includeReversedInput*/ true};
+        auto rdev = fmb200::attach<fmc::BiFMIndexCursor, fmc::LeftBiFMIndexCursor>(rindex);
+        fmb_index_info info{};
+        CHECK(fmb_index_get_info(rdev.handle(), &info) == 0 && info.bidirectional == 1 && (info.flags & FMB_INDEX_REUSE_REV));
+        compare(rindex, rdev, queries, "ReuseRev");
+        // NoDelim over the alphabet {0, 1, 2, 3}: symbol 0 is an ordinary symbol
+        using NoDelimIndex = fmc::BiFMIndex<4, fmc::string::InterleavedBitvector16>::NoDelim;
+        auto seqs0 = seqs;
+        for (auto& sq : seqs0) for (auto& ch : sq) ch -= 1;
+        auto queries0 = queries;
+        for (auto& q : queries0) for (auto& ch : q) ch -= 1;
+        auto nindex = NoDelimIndex{seqs0, /*samplingRate*/ 16, /*threadNbr*/ 1};
+        auto ndev = fmb200::attach<fmc::BiFMIndexCursor, fmc::LeftBiFMIndexCursor>(nindex);
+        CHECK(fmb_index_get_info(ndev.handle(), &info) == 0 && (info.flags & FMB_INDEX_NO_DELIM) && info.occ_block_bytes == 32);
+        compare(nindex, ndev, queries0, "NoDelim");
+        // both at once
+        using MirroredIndex = NoDelimIndex::ReuseRev;
+        auto mindex = MirroredIndex{seqs0, /*samplingRate*/ 16, /*threadNbr*/ 1, /*seqOffset*/ 0, /*includeReversedInput*/ true};
+        auto mdev = fmb200::attach<fmc::BiFMIndexCursor, fmc::LeftBiFMIndexCursor>(mindex);
+        compare(mindex, mdev, queries0, "NoDelim::ReuseRev");
     }
     std::printf("dropin_test: %d checks, %d failed\n", g_checks, g_fail);
     return g_fail ? 1 : 0;

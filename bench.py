@@ -488,7 +488,7 @@ def main():
             alg_bytes = alg_lookups * (64.0 if protein else 32.0)
             ext_per_q = None
         else:
-            kernel = "scheme_search_kernel"
+            kernel = "scheme_search_kernel + scheme_text_kernel"      # frontier kernel + text kernel, all launches of one search call
             alg_bytes = st_s.occ_lookups * (64.0 if protein else 32.0)       # 64 B per lookup for sigma = 21
             alg_lookups = st_s.occ_lookups
             ext_per_q = st_s.extensions / nq

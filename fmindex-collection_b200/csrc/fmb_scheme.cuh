@@ -40,7 +40,7 @@ enum : uint32_t { INFO_M = 0, INFO_S = 1, INFO_D = 2, INFO_I = 3 };
 enum : uint32_t { MODE_POS = 0, MODE_NEXT = 1, MODE_NOERR = 2 };
 
 // 32-byte frontier item = State of SearchNg26.h:41-52 + (qidx, search)
-struct Item {
+struct alignas(16) Item {
     uint32_t lb, lb_rev, len, qidx;
     uint32_t qpos;       // queryPosL | queryPosR << 16  (16-bit wrap-around, cf. the note at SearchNg26.h:69-71)
     uint32_t pev_steps;  // partitionEntryValue | steps << 16
@@ -339,12 +339,11 @@ constexpr int kFastForward = 12;
 #define FMB_SCHEME_MINB 4          // 4 blocks of 256 threads per SM -> 64 registers (a few spills beat the lower occupancy of 80)
 #endif   // consecutive single-child expansions a lane may chain in registers per pop
 
-// Text class: a single-row item that still branches (errors possible) and is not a leaf.  Its whole
-// subtree in the current direction is decided by the text that follows the row, so the frontier kernel does not expand it: it hands
-// it to scheme_text_kernel through the global text list.  Leaves (they only report), error-free stretches (multi-symbol jumps) and
-// items the text kernel handed back (notext) stay here.
+// Text class: a single-row item that is not a leaf.  Its whole subtree in the current direction is decided by the text that follows
+// the row, so the frontier kernel does not expand it: it hands it to scheme_text_kernel through the global text list.  Leaves (they
+// only report) and items the text kernel handed back (notext: no usable window at that row) stay here.
 __device__ __forceinline__ bool text_class(const State& c, uint32_t np, const uint8_t* __restrict__ qflags) {
-    if (c.len != 1 || c.mode == MODE_NOERR || c.notext) return false;
+    if (c.len != 1 || c.notext) return false;
     if (c.mode == MODE_NEXT ? (c.part == np) : (c.NextPos && c.pev == 1 && c.part + 1 == np)) return false;
     if (qflags != nullptr && qflags[c.qidx]) return false;
     return true;

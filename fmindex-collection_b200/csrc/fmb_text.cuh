@@ -10,7 +10,7 @@
 //   * a child whose position advance ends the last part of the direction run (the search turns around or ends): the child exactly
 //     as search_next_dir_single creates it, advance pending                                                    ("turn" items)
 //   * an error-free stretch that ends a part the same way: the state search_next_dir_no_errors leaves (:241-249)
-//   * a node at the end of the window (96 symbols, a delimiter ahead, or the private stack full): the node as it is ("continue")
+//   * a node at the end of the window (144 symbols, a delimiter ahead, or the private stack full): the node as it is ("continue")
 //   * an item whose row has no usable window at all (delimiter within the next 16 symbols): the item itself, flagged `notext`
 // The frontier kernel reports the leaves and routes text-class items back here.  Results are identical by construction: this is the
 // same state machine on the same symbols; fmb_stats.extensions still equals the oracle's count (one per node visit, one per symbol
@@ -24,8 +24,8 @@
 
 namespace fmb {
 
-constexpr int kTextWords = 6;        // window words per lane: 96 symbols (2-bit codes) / 24 symbols (bytes)
-constexpr int kTextQWords = 7;       // query words per lane, walking order: 112 / 28 symbols
+constexpr int kTextWords = 9;        // window words per lane: 144 symbols (2-bit codes) / 36 symbols (bytes)
+constexpr int kTextQWords = 10;      // query words per lane, walking order: 160 / 40 symbols
 constexpr int kTextStage = 64;       // staged items per warp before they are flushed to the global list
 constexpr int kTextStack = 16;       // private depth-first stack (packed nodes)
 #ifndef FMB_TEXT_MINB
@@ -49,17 +49,18 @@ enum : uint32_t { TN_EXPAND = 0, TN_TURN = 1, TN_NEXT = 2, TN_CONT = 3 };
 // LC_RUN = an error-free stretch, LC_SKIP = the matching stretch of a path at its last error level
 enum : uint32_t { LC_VISIT = 0, LC_RUN = 1, LC_SKIP = 2 };
 __device__ __forceinline__ unsigned long long tnode_pack(const TNode& s) {
-    // m:7 c:8 part:5 pev:16 e:4 T:2 lastRank:8 lastQRank:8 noerr:1 kind:2
-    return (unsigned long long)s.m | ((unsigned long long)s.c << 7) | ((unsigned long long)s.part << 15) | ((unsigned long long)s.pev << 20) |
-           ((unsigned long long)s.e << 36) | ((unsigned long long)s.T << 40) | ((unsigned long long)s.lastRank << 42) |
-           ((unsigned long long)s.lastQRank << 50) | ((unsigned long long)s.noerr << 58) | ((unsigned long long)s.kind << 59);
+    // m:8 c:8 part:5 pev:16 e:4 T:2 lastRank:8 lastQRank:8 noerr:1 kind:2
+    return (unsigned long long)s.m | ((unsigned long long)s.c << 8) | ((unsigned long long)s.part << 16) | ((unsigned long long)s.pev << 21) |
+           ((unsigned long long)s.e << 37) | ((unsigned long long)s.T << 41) | ((unsigned long long)s.lastRank << 43) |
+           ((unsigned long long)s.lastQRank << 51) | ((unsigned long long)s.noerr << 59) | ((unsigned long long)s.kind << 60);
 }
 __device__ __forceinline__ TNode tnode_unpack(unsigned long long v) {
     TNode s;
-    s.m = v & 127; s.c = (v >> 7) & 255; s.part = (v >> 15) & 31; s.pev = (v >> 20) & 0xFFFF; s.e = (v >> 36) & 15;
-    s.T = (v >> 40) & 3; s.lastRank = (v >> 42) & 255; s.lastQRank = (v >> 50) & 255; s.noerr = (v >> 58) & 1; s.kind = (v >> 59) & 3;
+    s.m = v & 255; s.c = (v >> 8) & 255; s.part = (v >> 16) & 31; s.pev = (v >> 21) & 0xFFFF; s.e = (v >> 37) & 15;
+    s.T = (v >> 41) & 3; s.lastRank = (v >> 43) & 255; s.lastQRank = (v >> 51) & 255; s.noerr = (v >> 59) & 1; s.kind = (v >> 60) & 3;
     return s;
 }
+static_assert(kTextWords * 16 <= 255 && kTextQWords * 16 <= 255, "window / query positions are 8-bit fields of a packed node");
 
 // reverses the order of the sixteen 2-bit fields of a word
 __device__ __forceinline__ uint32_t rev2(uint32_t w) {
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                 const Item it = items[next_item];
                 next_item += stride;
                 State st = unpack_item(it);
-                bool ok = st.len == 1 && st.mode != MODE_NOERR;
+                bool ok = st.len == 1;
                 if (ok && st.mode == MODE_POS && st.NextPos) {                                     // search_next_pos :119-141
                     if (st.Right) st.qposR = (st.qposR + 1) & 0xFFFF; else st.qposL = (st.qposL - 1) & 0xFFFF;
                     st.pev -= 1;
@@ -288,6 +289,7 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                     back.meta |= 0x80u;                      // notext: expand this one on the index
                     stage_emit(back);
                 } else {
+                    const bool entry_noerr = st.mode == MODE_NOERR;
                     st.mode = MODE_POS; st.NextPos = 0; st.notext = 0;
                     it0 = pack_item(st);
                     // query symbols of this direction run in walking order
@@ -329,7 +331,8 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                     root.m = 0; root.c = 0; root.part = st.part; root.pev = st.pev; root.e = st.e;
                     root.T = R ? st.RInfo : st.LInfo;
                     root.lastRank = side_get(st.side, R, 0); root.lastQRank = side_get(st.side, R, 1);
-                    root.noerr = 0; root.kind = TN_EXPAND;
+                    root.noerr = entry_noerr ? 1u : 0u;      // an error-free stretch that became a single row
+                    root.kind = TN_EXPAND;
                     stk[top++] = tnode_pack(root);
                 }
             }

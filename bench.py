@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--rate", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the headline cpu_baseline sample (the other workloads get a third)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--image-gb", type=float, default=0.0, help="HBM budget of the index image in GB (fmb_set_image_budget; 0 = every table that fits)")
     args = ap.parse_args()
 
     wls = list(DNA_SET) if args.workload == "all" else [args.workload]
@@ -255,6 +256,8 @@ def main():
     metric_head = {"exact": "queries/s (150bp exact search + locate, 3 Gbp index)"}.get(
         head, f"queries/s ({head}, search + locate, {'1 Gaa' if protein else ('4 Mbp' if head == 'c1' else '3 Gbp')} index)")
 
+    if args.image_gb > 0:
+        capi.set_image_budget(args.image_gb * 1e9)
     # ---- the SAME text on every rank (the index is replicated per GPU), different reads per rank (queries are sharded) ----------
     t0 = time.time()
     if fam == "repeat":
@@ -577,7 +580,7 @@ def main():
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": h["workload"],
                        "l2_policy": "inputs larger than L2 (index image %.1f GB, reads %.2f GB per workload)" % (index.info.device_bytes / 1e9, nq * L / 1e9),
-                       "index_tables": table_names, "hits_per_step": h["hits_per_step"], "located_rows_per_step": h["located_rows_per_step"],
+                       "index_tables": table_names, "image_budget_gb": args.image_gb or None, "image_gb": index.info.device_bytes / 1e9, "hits_per_step": h["hits_per_step"], "located_rows_per_step": h["located_rows_per_step"],
                        "workloads_in_this_line": wls},
             "roofline": h["roofline"], "e2e": h["e2e"], "gpu_launches": launches, "clocks": clocks,
             "ceilings": {"random_requests": ceilings, "request_ceiling_per_s": req_ceiling,

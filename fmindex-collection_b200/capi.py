@@ -46,7 +46,7 @@ SYMBOLS = [
     "fmb_results_count", "fmb_results_kind", "fmb_results_fetch_hits", "fmb_results_fetch_locs", "fmb_results_fetch_locs32",
     "fmb_results_get_stats", "fmb_results_destroy",
     "fmb_search_and_locate", "fmb_search_and_locate_packed", "fmb_search_and_locate_multi", "fmb_index_replicate", "fmb_index_save", "fmb_index_load", "fmb_checksum64",
-    "fmb_index_set_exact_mode", "fmb_index_set_locate_mode", "fmb_synth_text_device", "fmb_synth_reads_device", "fmb_synth_reads_err_device", "fmb_synth_repeat_text_device", "fmb_synth_unit_reads_device", "fmb_index_set_stream", "fmb_measure_gather", "fmb_kernel_launch_count", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
+    "fmb_index_set_exact_mode", "fmb_index_set_locate_mode", "fmb_synth_text_device", "fmb_synth_reads_device", "fmb_synth_reads_err_device", "fmb_synth_repeat_text_device", "fmb_synth_unit_reads_device", "fmb_index_set_stream", "fmb_set_image_budget", "fmb_measure_gather", "fmb_kernel_launch_count", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
 ]
 
 
@@ -524,6 +524,11 @@ def measure_gather(index, table, requests=1 << 28):
     rps, tb, rb = C.c_double(0), C.c_uint64(0), C.c_uint32(0)
     _check(lib().fmb_measure_gather(index.h, C.c_int(table), C.c_uint64(requests), C.byref(rps), C.byref(tb), C.byref(rb)))
     return rps.value, tb.value, rb.value
+
+
+def set_image_budget(nbytes):
+    """HBM budget of the index images created after this call (0 = no limit)"""
+    _check(lib().fmb_set_image_budget(C.c_uint64(int(nbytes))))
 
 
 def index_set_stream(index, stream_ptr):

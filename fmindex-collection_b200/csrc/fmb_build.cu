@@ -20,6 +20,7 @@ namespace fmb {
 int build_occ_from_device_bwt(fmb_index* ix, int dir, const uint8_t* d_bwt);
 int compute_C(fmb_index* ix);
 int build_occ2(fmb_index* ix, int dir);
+uint32_t plan_tables(const fmb_index* ix, uint64_t n_samples);
 int build_locblocks(fmb_index* ix);
 int build_jump(fmb_index* ix, int dir);
 int widen_jump0(fmb_index* ix);
@@ -314,6 +315,7 @@ extern "C" int fmb_index_build(fmb_index** out, int device, uint32_t sigma, cons
     if (sampling_rate == 0) { set_error("sampling_rate must be >= 1"); return FMB_EINVAL; }
     fmb_index* ix = nullptr;
     FMB_TRY(new_index(&ix, device, sigma, n, bidirectional != 0, 0));
+    ix->allowed_tables = plan_tables(ix, n / sampling_rate + 1);
     struct Guard {
         fmb_index* ix;
         ~Guard() { if (ix) fmb_index_destroy(ix); }

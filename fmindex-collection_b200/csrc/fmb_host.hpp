@@ -116,6 +116,9 @@ struct fmb_index {
     fmb::DevBuf<uint4> bikmer;           // bidirectional k-mer table for scheme-search roots
     uint32_t bikmer_k = 0;
     int exact_mode = 0;                  // FMB_EXACT_*
+    // optional tables this image is allowed to hold (FMB_TABLE_* bits), decided once from the image budget (fmb_set_image_budget /
+    // FMB_IMAGE_GB; default: everything the device can hold)
+    uint32_t allowed_tables = 0xFFFFFFFFu;
     // engine of the one-call end-to-end path (persistent worker threads + streams, csrc/fmb_engine.cu), created on first use
     mutable void* engine = nullptr;
     mutable std::mutex engine_mu;

@@ -278,6 +278,51 @@ namespace fmb {
 int build_jump(fmb_index* ix, int dir);
 int widen_jump0(fmb_index* ix);
 
+// ---- image budget: which accelerating tables an index may hold ----------------------------------------------------------------
+// Every table beyond the occurrence blocks is optional (results never depend on them); they trade HBM for speed.  With a budget
+// the tables are admitted in the order of what they buy per byte (measured: profiles/r02_image_budget_curve.json):
+//   pair table + k-mer table (exact search: two symbols per line, the first 14 symbols in one lookup), locate blocks,
+//   LF^16 table of direction 0 (sixteen symbols per lookup once an interval is a single row), LF^16 of direction 1 (text windows of
+//   the k-error searches in both directions), bidirectional k-mer table, locate shortcut, merged LF^32 entries, LF^4 tables.
+static std::atomic<uint64_t> g_image_budget{0};          // bytes, 0 = no limit
+static uint64_t image_budget() {
+    uint64_t b = g_image_budget.load();
+    if (!b) {
+        static const double env_gb = getenv("FMB_IMAGE_GB") ? atof(getenv("FMB_IMAGE_GB")) : 0.0;
+        if (env_gb > 0) b = (uint64_t)(env_gb * 1e9);
+    }
+    return b;
+}
+uint32_t plan_tables(const fmb_index* ix, uint64_t n_samples) {
+    const uint64_t budget = image_budget();
+    if (!budget) return 0xFFFFFFFFu;
+    const double n = (double)ix->n;
+    // what is always there: occurrence blocks (both directions), marks + samples
+    double used = (ix->dna ? n / 2 : n / 64 * 128) * (ix->bidirectional && !ix->reuse_rev ? 2 : 1) + n / 4 + 8.0 * (double)n_samples;
+    uint32_t allowed = 0;
+    auto admit = [&](uint32_t bits, double bytes) {
+        if (used + bytes <= (double)budget) { used += bytes; allowed |= bits; return true; }
+        return false;
+    };
+    if (ix->dna) {
+        uint32_t k = 0;
+        while (k < 14 && (uint64_t(8) << (2 * (k + 1))) <= ix->n) ++k;
+        admit(FMB_TABLE_PAIR | FMB_TABLE_KMER, n + 8.0 * (double)(uint64_t(1) << (2 * k)));
+        admit(FMB_TABLE_LOCBLOCK, n);
+        const bool j0 = admit(FMB_TABLE_JUMP, 8 * n);
+        const bool j1 = ix->bidirectional && admit(FMB_TABLE_JUMP_REV, 8 * n);
+        uint32_t bk = 0;
+        while (bk < 13 && (uint64_t(32) << (2 * (bk + 1))) <= ix->n) ++bk;
+        if (ix->bidirectional) admit(FMB_TABLE_BIKMER, 16.0 * (double)(uint64_t(1) << (2 * bk)));
+        if (allowed & FMB_TABLE_LOCBLOCK) admit(FMB_TABLE_LOCROW, 4 * n);
+        if (j0) admit(FMB_TABLE_JUMP32, 8 * n);
+        if (j0) admit(FMB_TABLE_JUMP4, 8 * n * (j1 ? 2 : 1));
+    } else {
+        admit(FMB_TABLE_JUMP4, 8 * n * (ix->bidirectional ? 2 : 1));      // generic layout: byte-symbol LF^4 tables only
+    }
+    return allowed;
+}
+
 // Builds occ table `dir` of `ix` from n BWT bytes at d_bwt (device).  Fails when a symbol is >= sigma.
 int build_occ_from_device_bwt(fmb_index* ix, int dir, const uint8_t* d_bwt) {
     const uint64_t n = ix->n;
@@ -387,7 +432,7 @@ __global__ void compute_C2_kernel(IndexView<OccDna> ix, int dir, uint32_t* out) 
 
 // bidirectional k-mer table (16 bytes per k-mer): largest k <= 13 with 16 * 4^k <= n / 2; needs both occ tables and C
 int build_bikmer(fmb_index* ix) {
-    if (!ix->dna || !ix->bidirectional || getenv("FMB_NO_BIKMER")) return FMB_OK;
+    if (!ix->dna || !ix->bidirectional || getenv("FMB_NO_BIKMER") || !(ix->allowed_tables & FMB_TABLE_BIKMER)) return FMB_OK;
     uint32_t k = 0;
     while (k < 13 && (uint64_t(32) << (2 * (k + 1))) <= ix->n) ++k;
     if (k < 2) return FMB_OK;
@@ -403,7 +448,7 @@ int build_bikmer(fmb_index* ix) {
 
 // combined 64-byte locate records (needs occ table 0 and the marks); skipped when FMB_NO_LOCBLOCKS is set
 int build_locblocks(fmb_index* ix) {
-    if (getenv("FMB_NO_LOCBLOCKS") || !ix->dna || !ix->marks.p || ix->n_samples == 0) return FMB_OK;
+    if (getenv("FMB_NO_LOCBLOCKS") || !ix->dna || !ix->marks.p || ix->n_samples == 0 || !(ix->allowed_tables & FMB_TABLE_LOCBLOCK)) return FMB_OK;
     const uint64_t nblocks = ix->n / 64 + 1;
     cudaStream_t st = active_stream(ix);
     FMB_TRY(ix->locblocks.alloc(nblocks * 4));
@@ -412,7 +457,7 @@ int build_locblocks(fmb_index* ix) {
     FMB_CUDA(cudaStreamSynchronize(st));
     // locate shortcut table: walk every row once.  The word packs sample index and step count; when they do not fit 32 bits (very
     // sparse or irregular sampling) the table is dropped and locate keeps walking.  FMB_NO_LOCROW disables it.
-    if (!getenv("FMB_NO_LOCROW")) {
+    if (!getenv("FMB_NO_LOCROW") && (ix->allowed_tables & FMB_TABLE_LOCROW)) {
         uint32_t idx_bits = 1;
         while (idx_bits < 32 && (uint64_t(1) << idx_bits) < ix->n_samples) ++idx_bits;
         const uint32_t step_bits = 32 - idx_bits;
@@ -444,6 +489,7 @@ int build_locblocks(fmb_index* ix) {
 
 // Builds the two-symbol table of direction `dir` from the one-symbol table (needs C).  sigma <= 5 only.
 int build_occ2(fmb_index* ix, int dir) {
+    if (!(ix->allowed_tables & FMB_TABLE_PAIR)) return build_jump(ix, dir);       // image budget: no pair / k-mer table
     const uint64_t n = ix->n;
     const uint64_t nblocks = n / 128 + 1, nquarters = nblocks * 4;
     cudaStream_t st = active_stream(ix);
@@ -512,6 +558,7 @@ int build_occ2(fmb_index* ix, int dir) {
 // keeps taking two-symbol steps -- when the device cannot hold the two build buffers, or when FMB_NO_JUMP is set.
 int build_jump(fmb_index* ix, int dir) {
     if (getenv("FMB_NO_JUMP")) return FMB_OK;
+    if (ix->dna ? !(ix->allowed_tables & (dir ? FMB_TABLE_JUMP_REV : FMB_TABLE_JUMP)) : !(ix->allowed_tables & FMB_TABLE_JUMP4)) return FMB_OK;
     const uint64_t n = ix->n;
     size_t free_b = 0, total_b = 0;
     FMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -539,7 +586,7 @@ int build_jump(fmb_index* ix, int dir) {
     FMB_CUDA(cudaGetLastError());
     // LF^4 entries (after the second round) are kept as well when memory allows: they serve the tails that are shorter than 16
     // symbols (FMB_NO_JUMP4 disables them)
-    const bool want4 = !getenv("FMB_NO_JUMP4") && (double)free_b > 3.0 * 8.0 * (double)n * 1.25 + (double)(size_t(24) << 30);
+    const bool want4 = !getenv("FMB_NO_JUMP4") && (ix->allowed_tables & FMB_TABLE_JUMP4) && (double)free_b > 3.0 * 8.0 * (double)n * 1.25 + (double)(size_t(24) << 30);
     for (uint32_t shift = 2; shift <= 16; shift *= 2) {
         // direction 0 is compared with query symbols to the LEFT of the match (farthest symbol = lowest position = low bits),
         // direction 1 with symbols to the RIGHT (nearest symbol = lowest position = low bits): both equal the packed query order
@@ -560,7 +607,7 @@ int build_jump(fmb_index* ix, int dir) {
 // interval per lookup.  Built after both LF^16 tables exist; skipped (the 8-byte table stays) when the device cannot hold the wide
 // copy next to the narrow one plus what the remaining tables need, or when FMB_NO_JUMP32 is set.
 int widen_jump0(fmb_index* ix) {
-    if (!ix->dna || !ix->jump[0].p || ix->jump_shift[0] || getenv("FMB_NO_JUMP32")) return FMB_OK;
+    if (!ix->dna || !ix->jump[0].p || ix->jump_shift[0] || getenv("FMB_NO_JUMP32") || !(ix->allowed_tables & FMB_TABLE_JUMP32)) return FMB_OK;
     const uint64_t n = ix->n;
     size_t free_b = 0, total_b = 0;
     pool_trim();
@@ -679,6 +726,7 @@ int fmb_index_create_ex(fmb_index** out, int device, uint32_t sigma, uint64_t n,
     if ((flags & FMB_INDEX_REUSE_REV) && bwt_rev) { set_error("a ReuseRev index has no bwtRev"); return FMB_EINVAL; }
     fmb_index* ix = nullptr;
     FMB_TRY(new_index(&ix, device, sigma, n, bwt_rev != nullptr || (flags & FMB_INDEX_REUSE_REV), flags));
+    ix->allowed_tables = plan_tables(ix, n_samples);
     auto fail = [&](int rc) { fmb_index_destroy(ix); return rc; };
     {
         DevBuf<uint8_t> d_bwt;
@@ -1473,6 +1521,10 @@ int fmb_measure_gather(const fmb_index* ix, int table, uint64_t requests, double
     return FMB_OK;
 }
 
+int fmb_set_image_budget(uint64_t bytes) {
+    g_image_budget.store(bytes);
+    return FMB_OK;
+}
 int fmb_index_set_stream(fmb_index* ix, void* stream) {
     if (!ix) { set_error("NULL index"); return FMB_EINVAL; }
     ix->stream = stream ? (cudaStream_t)stream : ix->own_stream;

@@ -265,8 +265,9 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     // in slabs.  Otherwise: all roots at once, the overflow list only takes what the warp stacks cannot hold.
     const bool text_mode = !ordered && text_mode_available(ix, q, sp.force_left != 0);
     static const uint64_t env_slab = getenv("FMB_SCHEME_SLAB") ? strtoull(getenv("FMB_SCHEME_SLAB"), nullptr, 10) : 0;
-    const uint64_t slab = text_mode ? std::min<uint64_t>(std::max<uint64_t>(n_roots, 1), env_slab ? env_slab : (uint64_t(8) << 20)) : std::max<uint64_t>(n_roots, 1);
-    const uint64_t ovf_cap = text_mode ? std::max<uint64_t>(1u << 20, slab * 2 + (1u << 18)) : (1u << 22);       // items of 32 bytes
+    // (without text mode the roots go in slabs as well: what a slab spills -- warp stacks that ran full -- stays bounded)
+    const uint64_t slab = std::min<uint64_t>(std::max<uint64_t>(n_roots, 1), env_slab ? env_slab : (text_mode ? (uint64_t(8) << 20) : (uint64_t(4) << 20)));
+    const uint64_t ovf_cap = std::max<uint64_t>(1u << 20, slab * 2 + (1u << 18));       // items of 32 bytes
     DevBuf<Item> ovf[2], text_list;
     DevBuf<unsigned long long> ovf_keys[2], hit_keys;
     DevBuf<unsigned long long> ctr;          // [0..3] counters, [4] hit_count, [5] overflow_count, [6] root_counter, [7] text_count, [8] row_count

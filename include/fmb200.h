@@ -322,6 +322,12 @@ int  fmb_synth_unit_reads_device(int device, uint32_t sigma, uint64_t nq, uint32
 #define FMB_GATHER_OCC_BLOCK  1
 #define FMB_GATHER_JUMP_ENTRY 2
 int  fmb_measure_gather(const fmb_index* ix, int table, uint64_t requests, double* requests_per_s, uint64_t* table_bytes, uint32_t* request_bytes);
+/* HBM budget of the index images created AFTER this call (process wide; 0 = no limit, the default: every table the device can hold;
+ * the environment variable FMB_IMAGE_GB sets the same).  Beyond the occurrence blocks every table of an image is optional -- results
+ * never depend on them -- and trades memory for speed; with a budget they are admitted in the order of what they buy per byte: pair +
+ * k-mer tables, locate blocks, LF^16 table of direction 0, of direction 1, bidirectional k-mer table, locate shortcut, merged LF^32
+ * entries, LF^4 tables (3 Gbp DNA: 15 / 39 / 63 / 76 / 100 / 146 GB; measured throughputs in profiles/r02_image_budget_curve.json). */
+int  fmb_set_image_budget(uint64_t bytes);
 /* All work of `ix` is enqueued on `stream` (a cudaStream_t of the index's device, e.g. the caller's timing
  * stream) instead of the index's private stream.  NULL restores the private stream. */
 int  fmb_index_set_stream(fmb_index* ix, void* stream);

@@ -77,3 +77,31 @@ def test_measure_gather_reports_a_plausible_request_rate(gpu):
         assert rb == req_bytes and tb >= text.size // 4 and 1e8 < rps < 1e12
     rps, tb, rb = capi.measure_gather(g, 2, 1 << 22)
     assert rb in (8, 16) and tb == text.size * rb
+
+
+def test_image_budget_drops_tables_but_not_results(gpu):
+    """fmb_set_image_budget: with a budget the optional tables are admitted in priority order; results never depend on them"""
+    from fmb200 import capi, schemes, synth
+    text = synth.multi_text([300000, 20000], 5, 11)
+    sym, off = _reads(text[:300000], 5, 2000, 60, 3, 1, True)
+    sch, part = schemes.optimum(0, 1), schemes.uniform_partition(2, 60)
+    full = gpu.Index.build(5, text, sampling_rate=8, device=0)
+    q = full.upload(sym, off)
+    exact, edit = full.search_exact(q).hits(), full.search_scheme(q, sch, part, True).hits()
+    locs = full.locate(full.search_exact(q)).locs()
+    n = text.size
+    try:
+        seen = set()
+        for budget in (2 * n, 5 * n, 14 * n, 24 * n, 40 * n, 80 * n):
+            capi.set_image_budget(budget)
+            g = gpu.Index.build(5, text, sampling_rate=8, device=0)
+            i = g.info
+            assert i.device_bytes <= budget * 1.02 + (1 << 20) or i.tables == 0
+            seen.add(i.tables)
+            qq = g.upload(sym, off)
+            assert hits_equal(g.search_exact(qq).hits(), exact)
+            assert hits_equal(g.search_scheme(qq, sch, part, True).hits(), edit)
+            assert np.array_equal(np.sort(g.locate(g.search_exact(qq)).locs(), order=["qidx", "seq", "pos", "e"]), np.sort(locs, order=["qidx", "seq", "pos", "e"]))
+        assert len(seen) >= 4 and full.info.tables in seen
+    finally:
+        capi.set_image_budget(0)

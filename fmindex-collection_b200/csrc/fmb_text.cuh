@@ -28,6 +28,10 @@ constexpr int kTextWords = 9;        // window words per lane: 144 symbols (2-bi
 constexpr int kTextQWords = 10;      // query words per lane, walking order: 160 / 40 symbols
 constexpr int kTextStage = 64;       // staged items per warp before they are flushed to the global list
 constexpr int kTextStack = 16;       // private depth-first stack (packed nodes)
+#ifndef FMB_TEXT_BULK2
+#define FMB_TEXT_BULK2 1
+#endif
+constexpr bool kBulk2 = FMB_TEXT_BULK2 != 0;
 #ifndef FMB_TEXT_MINB
 #define FMB_TEXT_MINB 4
 #endif
@@ -46,8 +50,9 @@ struct TNode {             // one pending node, "ready to expand" (the position 
 // TN_NEXT = the state search_next_dir_no_errors leaves at such a part end (mode NEXT), TN_CONT = the node as it is (window end)
 enum : uint32_t { TN_EXPAND = 0, TN_TURN = 1, TN_NEXT = 2, TN_CONT = 3 };
 // kinds of the queued comparisons along a diagonal: LC_VISIT = a node without errors left (its own visit, then error free),
-// LC_RUN = an error-free stretch, LC_SKIP = the matching stretch of a path at its last error level
-enum : uint32_t { LC_VISIT = 0, LC_RUN = 1, LC_SKIP = 2 };
+// LC_RUN = an error-free stretch, LC_SKIP = the matching stretch of a path at its last error level, LC_BULK2 = the matching stretch of
+// a path with two errors left (its deletion / insertion subtrees are evaluated sixteen positions at a time)
+enum : uint32_t { LC_VISIT = 0, LC_RUN = 1, LC_SKIP = 2, LC_BULK2 = 3 };
 __device__ __forceinline__ unsigned long long tnode_pack(const TNode& s) {
     // m:8 c:8 part:5 pev:16 e:4 T:2 lastRank:8 lastQRank:8 noerr:1 kind:2
     return (unsigned long long)s.m | ((unsigned long long)s.c << 8) | ((unsigned long long)s.part << 16) | ((unsigned long long)s.pev << 21) |
@@ -66,6 +71,89 @@ static_assert(kTextWords * 16 <= 255 && kTextQWords * 16 <= 255, "window / query
 __device__ __forceinline__ uint32_t rev2(uint32_t w) {
     w = __brev(w);
     return ((w & 0xAAAAAAAAu) >> 1) | ((w & 0x55555555u) << 1);
+}
+
+// Edit distance, TWO errors left, inside the part, after a match (2-bit symbols).  At a matching position c (text position m) the
+// node's subtrees other than its match child are small and have a fixed shape (search_next_dir_single, SearchNg26.h:251-365):
+//   deletion child D1 (m+1, c):  its symbol equals q[c]  -> one more deletion child, which dies                        (2 visits)
+//                                else substitution S2 (m+2, c+1) and deletion D2 (m+2, c), both error free from there
+//   insertion child I1 (m, c+1): q[c+1] != q[c]         -> substitution S2' (m+1, c+2), error free
+//                                always                  -> insertion I2 (m, c+2), error free, its first match needs q[c+2] != q[c+1]
+// so per position: 5 visits + [w[m+1] != q[c]] (1 + run S2 + run D2) + [q[c+1] != q[c]] (1 + run S2') + run I2, where an error-free path
+// that matches r >= 1 symbols and then fails costs r + 1 extensions.  The four runs lie on the diagonals +1, +2, -1, -2 of the
+// alignment: their match masks are XORs of shifted window / query words (one bit per position, at the even bits of a 64-bit mask),
+// the run lengths come from iterated AND-shift.  Positions where a run goes on for kLook symbols -- or reaches the end of the part,
+// where it may survive -- are not decided here: they are returned in `slow` (their own visit is counted; the caller pushes their two
+// children).  Returns the extensions of the block [c0, c0 + nb); nb = 0: nothing decided.
+// sw / sq: the lane's window / query words ([word][thread] layout), have_syms: window symbols fetched (>= m0 + min(pev0, 32) + 2).
+__device__ __noinline__ uint32_t bulk2_eval(const uint32_t* sw, const uint32_t* sq, uint32_t tid, uint32_t have_syms, uint32_t m0, uint32_t c0, uint32_t pev0,
+                                            uint32_t& nb_out, unsigned long long& slow_out) {
+    constexpr uint32_t kLook = 8;
+    constexpr unsigned long long EVEN = 0x5555555555555555ull;
+    constexpr uint32_t QCAP = kTextQWords * 16;
+    auto wword = [&](uint32_t m) -> uint32_t { return __funnelshift_r(sw[(m / 16) * 256 + tid], sw[(m / 16 + 1) * 256 + tid], 2 * (m % 16)); };
+    auto qword = [&](uint32_t c) -> uint32_t { return __funnelshift_r(sq[(c / 16) * 256 + tid], sq[(c / 16 + 1) * 256 + tid], 2 * (c % 16)); };
+    auto eq32 = [&](uint32_t ma, uint32_t ca) -> uint32_t { const uint32_t x = wword(ma) ^ qword(ca); return ~(x | (x >> 1)) & 0x55555555u; };
+    auto eq64 = [&](uint32_t ma, uint32_t ca) -> unsigned long long {
+        const unsigned long long lo = eq32(ma, ca);
+        const unsigned long long hi = (ma + 16 < have_syms && ca + 32 <= QCAP) ? eq32(ma + 16, ca + 16) : 0u;
+        return lo | (hi << 32);
+    };
+    nb_out = 0;
+    slow_out = 0;
+    const unsigned long long M0 = eq64(m0, c0);
+    const unsigned long long miss = ~M0 & EVEN;
+    uint32_t nb = miss ? (uint32_t)(__ffsll((long long)miss) - 1) / 2u : 32u;      // leading matches on the main diagonal
+    nb = nb < 16u ? nb : 16u;
+    nb = nb < pev0 - 3 ? nb : pev0 - 3;                                             // every position of the block keeps >= 4 symbols of the part
+    if (nb == 0) return 0;
+    const unsigned long long end0 = pev0 >= 32 ? 0ull : (EVEN << (2 * pev0));      // positions beyond the part: runs that get there stay "alive"
+    const unsigned long long end2 = pev0 - 2 >= 32 ? 0ull : (EVEN << (2 * (pev0 - 2)));
+    const unsigned long long E1 = eq64(m0 + 1, c0) | end0;                          // w[m+1+i] == q[c+i]
+    const unsigned long long E2 = eq64(m0 + 2, c0) | end0;                          // w[m+2+i] == q[c+i]
+    const unsigned long long N1 = eq64(m0 + 1, c0 + 2) | end2;                      // w[m+1+i] == q[c+2+i]
+    const unsigned long long N2 = eq64(m0, c0 + 2) | end2;                          // w[m+i]   == q[c+2+i]
+    unsigned long long F;                                                            // q[c+1+i] == q[c+i]
+    {
+        const uint32_t x0 = qword(c0 + 1) ^ qword(c0);
+        const uint32_t x1 = (c0 + 33 <= QCAP) ? (qword(c0 + 17) ^ qword(c0 + 16)) : 0xFFFFFFFFu;
+        F = (unsigned long long)(~(x0 | (x0 >> 1)) & 0x55555555u) | ((unsigned long long)(~(x1 | (x1 >> 1)) & 0x55555555u) << 32);
+    }
+    const unsigned long long BM0 = ((1ull << (2 * nb)) - 1) & EVEN;
+    unsigned long long BM = BM0;
+    uint32_t total = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const unsigned long long A = ~E1 & BM, B = ~F & BM;
+        unsigned long long U = 0, T;
+        total = 5 * (uint32_t)__popcll(BM) + (uint32_t)__popcll(A) + (uint32_t)__popcll(B);
+        T = A & (E1 >> 2);                                                           // S2: diagonal +1 from c+1
+        total += 2 * (uint32_t)__popcll(T);
+#pragma unroll 1
+        for (uint32_t t = 1; t < kLook; ++t) { T &= E1 >> (2 * (1 + t)); total += (uint32_t)__popcll(T); }
+        U |= T;
+        T = A & E2;                                                                  // D2: diagonal +2 from c
+        total += 2 * (uint32_t)__popcll(T);
+#pragma unroll 1
+        for (uint32_t t = 1; t < kLook; ++t) { T &= E2 >> (2 * t); total += (uint32_t)__popcll(T); }
+        U |= T;
+        T = B & N1;                                                                  // S2': diagonal -1 from c+2
+        total += 2 * (uint32_t)__popcll(T);
+#pragma unroll 1
+        for (uint32_t t = 1; t < kLook; ++t) { T &= N1 >> (2 * t); total += (uint32_t)__popcll(T); }
+        U |= T;
+        T = BM & N2 & ~(F >> 2);                                                     // I2: diagonal -2 from c+2, first match needs q[c+2] != q[c+1]
+        total += 2 * (uint32_t)__popcll(T);
+#pragma unroll 1
+        for (uint32_t t = 1; t < kLook; ++t) { T &= N2 >> (2 * t); total += (uint32_t)__popcll(T); }
+        U |= T;
+        if (U == 0) break;
+        if (pass == 1 || __popcll(U) > 2) return 0;            // too many undecided positions: the caller walks this stretch node by node
+        BM &= ~U;                                               // undecided positions: their children are expanded one by one
+    }
+    const unsigned long long slow = BM0 & ~BM;
+    nb_out = nb;
+    slow_out = slow;
+    return total + (uint32_t)__popcll(slow);                    // (the undecided positions' own visits; their children count themselves)
 }
 
 template <class OCC, bool EDIT, bool PSEUDO>
@@ -391,6 +479,8 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                     queue_run(ch, LC_VISIT);                             // no error left: its own visit, then error free
                 } else if (!PSEUDO && slot == 0 && eq && (EDIT ? ch.e + 1 == cup : true) && ch.pev > 1 && ch.part == s.part) {
                     queue_run(ch, LC_SKIP);                              // the matching stretch (edit distance: at the last error level) is skipped
+                } else if (EDIT && !PSEUDO && !BYTES && kBulk2 && slot == 0 && eq && ch.e + 2 == cup && ch.pev >= 4 && ch.part == s.part) {
+                    queue_run(ch, LC_BULK2);                             // two errors left: the stretch is evaluated 16 positions at a time
                 } else if (vi == 0 && !(slot == 0 && eq) && ch.e + 1 == cup && nmini < 4) {
                     ch.kind = TN_EXPAND;
                     mini[nmini++] = tnode_pack(ch);                      // visited in this iteration
@@ -417,6 +507,40 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                 }
                 push(s);
                 continue;
+            }
+            if constexpr (EDIT && !PSEUDO && !BYTES && kBulk2) {
+                if (s.kind == LC_BULK2) {
+                    // the matching stretch of a path with two errors left, sixteen positions per evaluation (bulk2_eval above); positions
+                    // that are not decided there get their own visit here and their two children on the stack
+                    const uint32_t m0 = s.m, c0 = s.c, pev0 = s.pev;
+                    const uint32_t last = pev0 - 1 < 31u ? pev0 - 1 : 31u;         // positions c0 .. c0 + last matter
+                    // the query symbols the masks read lie inside the loaded part of the query (those beyond the part do not matter)
+                    if (c0 + 18 <= QCAP && c0 + (pev0 < last + 3 ? pev0 : last + 3) <= q_limit && ensure(m0 + last + 2)) {
+                        uint32_t nb = 0;
+                        unsigned long long slow = 0;
+                        const uint32_t total = bulk2_eval(sw, sq, tid, have * SPW, m0, c0, pev0, nb, slow);
+                        if (nb) {
+                            n_ext += total;
+                            while (slow) {
+                                const uint32_t i = (uint32_t)(__ffsll((long long)slow) - 1) / 2u;
+                                slow &= slow - 1;
+                                const uint32_t qc = qsy(c0 + i);
+                                TNode d1 = s;                                      // deletion child of the node at (m0 + i, c0 + i)
+                                d1.m = m0 + i + 1; d1.c = c0 + i; d1.pev = pev0 - i; d1.e = s.e + 1; d1.T = INFO_D; d1.lastRank = qc;
+                                d1.lastQRank = i ? qsy(c0 + i - 1) : s.lastQRank;
+                                push(d1);
+                                TNode i1 = s;                                      // insertion child: consumes q[c0 + i]
+                                i1.m = m0 + i; i1.c = c0 + i + 1; i1.pev = pev0 - i - 1; i1.e = s.e + 1; i1.T = INFO_I; i1.lastQRank = qc;
+                                i1.lastRank = i ? qsy(c0 + i - 1) : s.lastRank;
+                                push(i1);
+                            }
+                            s.m += nb; s.c += nb; s.pev -= nb;
+                            s.lastRank = s.lastQRank = qsy(s.c - 1);
+                        }
+                    }
+                    push(s);                                                       // the path goes on with the node behind the block (or unchanged)
+                    continue;
+                }
             }
             if (s.kind == LC_VISIT) {
                 // the node's own visit (search_next_dir_single with no error left): it continues iff its symbol matches

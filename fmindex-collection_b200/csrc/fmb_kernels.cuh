@@ -567,6 +567,23 @@ __global__ void __launch_bounds__(256) bikmer_table_kernel(const __grid_constant
     out[i] = make_uint4(c.lb, c.lb_rev, c.len, (ext << 16) | look);
 }
 
+// the same for the generic layout: pattern i has the symbols first_symb + digit_p(i) in base (sigma - first_symb), first symbol = lowest digit
+template <class OCC>
+__global__ void __launch_bounds__(256) bikmer_table_gen_kernel(const __grid_constant__ IndexView<OCC> ix, uint32_t k, uint32_t base, uint64_t count,
+                                                               uint4* __restrict__ out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Cursor c{0, 0, ix.n, 0};
+    uint32_t ext = 0, look = 0;
+    uint64_t rest = i;
+    for (uint32_t p = 0; p < k && c.len; ++p) {
+        c = extend_bi(ix, c, ix.first_symb + (uint32_t)(rest % base), 1, look);
+        rest /= base;
+        ++ext;
+    }
+    out[i] = make_uint4(c.lb, c.lb_rev, c.len, (ext << 16) | look);
+}
+
 // 2-bit packing of the query symbols (symbol-1, 16 symbols per word, first symbol in the low bits).  Queries holding a
 // symbol that has no 2-bit code (0 or >= sigma) are flagged and take the byte path of the search kernel.
 __device__ __forceinline__ uint32_t pack4(uint32_t w, uint32_t sigma, bool& bad) {
@@ -1001,8 +1018,35 @@ __global__ void __launch_bounds__(256) locrow_build_kernel(const __grid_constant
     }
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(256) locate_shortcut_kernel(const __grid_constant__ IndexView<OccDna> ix, const HitRec* __restrict__ hits,
+// the same table for any layout: one thread per row walks to its sample with separate occ / marker loads (build time only)
+template <class OCC>
+__global__ void __launch_bounds__(256) locrow_build_gen_kernel(const __grid_constant__ IndexView<OCC> ix, uint32_t step_bits, uint32_t* __restrict__ out,
+                                                               uint32_t* __restrict__ overflow) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ix.n) return;
+    const OCC& occ = ix.occ[0];
+    row_t row = (row_t)t;
+    uint32_t steps = 0;
+    for (;;) {
+        const uint4 m = __ldg(ix.marks + (row >> 6));
+        typename OCC::Block b = occ.load(row >> 6, 0);
+        const uint64_t bits = (uint64_t)m.x | ((uint64_t)m.y << 32);
+        const uint32_t o = row & 63;
+        if ((bits >> o) & 1) {
+            const uint32_t idx = m.z + __popcll(bits & low_mask(o));
+            if (steps >= (1u << step_bits) || idx >= (1u << (32 - step_bits))) atomicOr(overflow, 1u);
+            out[t] = (idx << step_bits) | steps;
+            return;
+        }
+        const uint32_t c = occ.symbol(b, row);
+        if (OCC::kSymbolLoad) b = occ.load(row >> 6, c);
+        row = ix.C[c] + occ.rank(b, row, c);
+        if (++steps > (1u << 20)) { atomicOr(overflow, 1u); out[t] = 0; return; }     // no sample on this walk (cannot be located anyway)
+    }
+}
+
+template <bool COUNT, class OCC>
+__global__ void __launch_bounds__(256) locate_shortcut_kernel(const __grid_constant__ IndexView<OCC> ix, const HitRec* __restrict__ hits,
                                                               const uint32_t* __restrict__ starts, uint32_t nh, uint32_t total, uint32_t single,
                                                               LocRec* __restrict__ out, unsigned long long* __restrict__ counters) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;

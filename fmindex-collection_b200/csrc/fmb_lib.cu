@@ -225,6 +225,8 @@ fmb::IndexView<fmb::OccGen> fmb_index::view_gen() const {
     v.marks = marks.p;
     v.samples = samples.p;
     v.locblocks = nullptr;
+    v.locrow = locrow.p;
+    v.loc_step_bits = loc_step_bits;
     return v;
 }
 
@@ -284,6 +286,14 @@ int widen_jump0(fmb_index* ix);
 //   pair table + k-mer table (exact search: two symbols per line, the first 14 symbols in one lookup), locate blocks,
 //   LF^16 table of direction 0 (sixteen symbols per lookup once an interval is a single row), LF^16 of direction 1 (text windows of
 //   the k-error searches in both directions), bidirectional k-mer table, locate shortcut, merged LF^32 entries, LF^4 tables.
+// generic layout: largest k <= 8 whose table of (sigma - first_symb)^k entries stays below 2 n bytes (1 Gaa, sigma = 21: k = 6, 1 GB)
+static uint32_t gen_bikmer_k(const fmb_index* ix) {
+    const uint64_t base = ix->sigma - ix->first_symb;
+    uint32_t k = 0;
+    uint64_t count = 1;
+    while (k < 8 && base > 1 && count * base * 16 <= 2 * ix->n && count * base < (uint64_t(1) << 31)) { count *= base; ++k; }
+    return k;
+}
 static std::atomic<uint64_t> g_image_budget{0};          // bytes, 0 = no limit
 static uint64_t image_budget() {
     uint64_t b = g_image_budget.load();
@@ -318,7 +328,13 @@ uint32_t plan_tables(const fmb_index* ix, uint64_t n_samples) {
         if (j0) admit(FMB_TABLE_JUMP32, 8 * n);
         if (j0) admit(FMB_TABLE_JUMP4, 8 * n * (j1 ? 2 : 1));
     } else {
-        admit(FMB_TABLE_JUMP4, 8 * n * (ix->bidirectional ? 2 : 1));      // generic layout: byte-symbol LF^4 tables only
+        admit(FMB_TABLE_JUMP4, 8 * n * (ix->bidirectional ? 2 : 1));      // generic layout: byte-symbol LF^4 tables ...
+        admit(FMB_TABLE_LOCROW, 4 * n);                                    // ... the locate shortcut ...
+        if (ix->bidirectional) {                                           // ... and the bidirectional k-mer table of the scheme roots
+            double cnt = 1;
+            for (uint32_t p = 0; p < gen_bikmer_k(ix); ++p) cnt *= (double)(ix->sigma - ix->first_symb);
+            admit(FMB_TABLE_BIKMER, 16 * cnt);
+        }
     }
     return allowed;
 }
@@ -432,7 +448,21 @@ __global__ void compute_C2_kernel(IndexView<OccDna> ix, int dir, uint32_t* out) 
 
 // bidirectional k-mer table (16 bytes per k-mer): largest k <= 13 with 16 * 4^k <= n / 2; needs both occ tables and C
 int build_bikmer(fmb_index* ix) {
-    if (!ix->dna || !ix->bidirectional || getenv("FMB_NO_BIKMER") || !(ix->allowed_tables & FMB_TABLE_BIKMER)) return FMB_OK;
+    if (!ix->bidirectional || getenv("FMB_NO_BIKMER") || !(ix->allowed_tables & FMB_TABLE_BIKMER)) return FMB_OK;
+    if (!ix->dna) {
+        const uint32_t k = gen_bikmer_k(ix), base = ix->sigma - ix->first_symb;
+        if (k < 2) return FMB_OK;
+        uint64_t count = 1;
+        for (uint32_t p = 0; p < k; ++p) count *= base;
+        cudaStream_t st = active_stream(ix);
+        FMB_TRY(ix->bikmer.alloc(count));
+        bikmer_table_gen_kernel<<<grid_for(count, 256), 256, 0, st>>>(ix->view_gen(), k, base, count, ix->bikmer.p);
+        FMB_CUDA(cudaGetLastError());
+        FMB_CUDA(cudaStreamSynchronize(st));
+        note_launches(1);
+        ix->bikmer_k = k;
+        return FMB_OK;
+    }
     uint32_t k = 0;
     while (k < 13 && (uint64_t(32) << (2 * (k + 1))) <= ix->n) ++k;
     if (k < 2) return FMB_OK;
@@ -448,6 +478,33 @@ int build_bikmer(fmb_index* ix) {
 
 // combined 64-byte locate records (needs occ table 0 and the marks); skipped when FMB_NO_LOCBLOCKS is set
 int build_locblocks(fmb_index* ix) {
+    if (!ix->dna && ix->marks.p && ix->n_samples && !getenv("FMB_NO_LOCROW") && (ix->allowed_tables & FMB_TABLE_LOCROW)) {
+        // generic layout: the locate shortcut alone (every row walked once, one thread per row)
+        uint32_t idx_bits = 1;
+        while (idx_bits < 32 && (uint64_t(1) << idx_bits) < ix->n_samples) ++idx_bits;
+        const uint32_t step_bits = 32 - idx_bits;
+        size_t free_b = 0, total_b = 0;
+        pool_trim();
+        FMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (step_bits < 1 || (double)free_b < 4.0 * (double)ix->n * 1.5 + (double)(1u << 28)) return FMB_OK;
+        cudaStream_t st = active_stream(ix);
+        FMB_TRY(ix->locrow.alloc(ix->n));
+        DevBuf<uint32_t> ovf;
+        FMB_TRY(ovf.alloc(1));
+        FMB_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(uint32_t), st));
+        ix->loc_step_bits = step_bits;
+        locrow_build_gen_kernel<<<grid_for(ix->n, 256), 256, 0, st>>>(ix->view_gen(), step_bits, ix->locrow.p, ovf.p);
+        FMB_CUDA(cudaGetLastError());
+        note_launches(1);
+        uint32_t h_ovf = 0;
+        FMB_CUDA(cudaMemcpyAsync(&h_ovf, ovf.p, sizeof h_ovf, cudaMemcpyDeviceToHost, st));
+        FMB_CUDA(cudaStreamSynchronize(st));
+        if (h_ovf) {                 // some walk is longer than the step field allows (or never reaches a sample)
+            ix->locrow.release();
+            ix->loc_step_bits = 0;
+        }
+        return FMB_OK;
+    }
     if (getenv("FMB_NO_LOCBLOCKS") || !ix->dna || !ix->marks.p || ix->n_samples == 0 || !(ix->allowed_tables & FMB_TABLE_LOCBLOCK)) return FMB_OK;
     const uint64_t nblocks = ix->n / 64 + 1;
     cudaStream_t st = active_stream(ix);
@@ -1283,8 +1340,8 @@ int fmb_locate(const fmb_index* ix, const fmb_results* hits, fmb_results** out) 
     cudaEventCreate(&ev_m1);
     if (total) {
         cudaEventRecord(ev_m0, st);
-        if (ix->dna && ix->locrow.p && ix->locate_mode != FMB_LOCATE_WALK) {
-            locate_shortcut_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(ix->view_dna(), hits->hits.p, starts.p, (uint32_t)nh, total, single ? 1u : 0u, res->locs.p, ctr.p);
+        if (ix->locrow.p && ix->locate_mode != FMB_LOCATE_WALK) {
+            FMB_DISPATCH(ix, v, locate_shortcut_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(v, hits->hits.p, starts.p, (uint32_t)nh, total, single ? 1u : 0u, res->locs.p, ctr.p));
         } else if (ix->dna && ix->locblocks.p) {
             auto v = ix->view_dna();
             // persistent grid: every SM full of lane pairs (8 blocks x 256 threads), rows handed out with a grid stride

@@ -178,6 +178,7 @@ struct JumpView {
     // is error free: the wide-interval phase of every search becomes one lookup.
     const uint4* bikmer;
     uint32_t bikmer_k;
+    uint32_t bikmer_base;         // generic layout: the k-mer index is the base-`bikmer_base` number of (symbol - first_symb); 0: 2-bit packed key
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -342,8 +343,11 @@ constexpr int kFastForward = 12;
 // Text class: a single-row item that is not a leaf.  Its whole subtree in the current direction is decided by the text that follows
 // the row, so the frontier kernel does not expand it: it hands it to scheme_text_kernel through the global text list.  Leaves (they
 // only report) and items the text kernel handed back (notext: no usable window at that row) stay here.
-__device__ __forceinline__ bool text_class(const State& c, uint32_t np, const uint8_t* __restrict__ qflags) {
+__device__ __forceinline__ bool text_class(const State& c, uint32_t np, const uint8_t* __restrict__ qflags, bool noerr_too) {
     if (c.len != 1 || c.notext) return false;
+    // error-free stretches: the text kernel compares 16 symbols per window lookup where the 2-bit layout has LF^16 entries; with the
+    // byte-symbol LF^4 entries of the generic layout a window lookup covers what a jump of this kernel covers, so they stay here
+    if (c.mode == MODE_NOERR && !noerr_too) return false;
     if (c.mode == MODE_NEXT ? (c.part == np) : (c.NextPos && c.pev == 1 && c.part + 1 == np)) return false;
     if (qflags != nullptr && qflags[c.qidx]) return false;
     return true;
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         it = in_items[r];
                         if constexpr (ORDERED) rkey = out.in_keys[r];
                         // items that come back from the text kernel (or were spilled) are routed by class
-                        if (text_on) to_text = text_class(unpack_item(it), np, text_qflags);
+                        if (text_on) to_text = text_class(unpack_item(it), np, text_qflags, !OCC::kSymbolLoad);
                     } else {
                         r = r - n_in + out.root_base;
                         uint32_t s = (uint32_t)(r % sp.n_searches);
@@ -421,13 +425,28 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         if (sp.force_left) {                                                   // Backtracking.h: right to left
                             st.qposL = (sp.partition[0] - 1) & 0xFFFF;
                             st.qposR = 0;
-                        } else if (jv.bikmer_k && sp.u[s][0] == 0 && st.pev >= jv.bikmer_k && jv.qflags[st.qidx] == 0) {
+                        } else if (jv.bikmer_k && sp.u[s][0] == 0 && st.pev >= jv.bikmer_k && (jv.bikmer_base || jv.qflags[st.qidx] == 0)) {
                             // error-free first part: its first bikmer_k symbols (always searched to the right) in one lookup;
                             // the state is the one the error-free loop would have reached (SearchNg26.h:225-250)
-                            const uint64_t bit = 2 * (qoff[st.qidx] + st.qposR);
-                            const uint32_t wi = (uint32_t)(bit >> 5);
-                            uint32_t key = __funnelshift_r(__ldg(jv.qpk + wi), __ldg(jv.qpk + wi + 1), (uint32_t)bit & 31u);
-                            key &= (1u << (2 * jv.bikmer_k)) - 1u;
+                            uint32_t key = 0;
+                            bool key_ok = true;
+                            if (jv.bikmer_base) {
+                                // generic layout: base-`bikmer_base` number of the symbols, first symbol = lowest digit
+                                const uint8_t* qp = qsym + qoff[st.qidx] + st.qposR;
+                                uint32_t mul = 1;
+                                for (uint32_t p = 0; p < jv.bikmer_k; ++p) {
+                                    const uint32_t c = __ldg(qp + p);
+                                    if (c < first_symb || c >= ix.sigma) key_ok = false;
+                                    key += (c - first_symb) * mul;
+                                    mul *= jv.bikmer_base;
+                                }
+                            } else {
+                                const uint64_t bit = 2 * (qoff[st.qidx] + st.qposR);
+                                const uint32_t wi = (uint32_t)(bit >> 5);
+                                key = __funnelshift_r(__ldg(jv.qpk + wi), __ldg(jv.qpk + wi + 1), (uint32_t)bit & 31u);
+                                key &= (1u << (2 * jv.bikmer_k)) - 1u;
+                            }
+                            if (key_ok) {
                             const uint4 e = __ldg(jv.bikmer + key);
                             n_phys += 1;
                             n_ext += e.w >> 16;
@@ -444,6 +463,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                             }
                             const uint32_t lastq = __ldg(qsym + qoff[st.qidx] + ((st.qposR - 1) & 0xFFFF));
                             if (st.mode == MODE_NEXT) st.side = side_set(side_set(st.side, 1, 0, lastq), 1, 1, lastq);
+                            }
                         }
                         it = pack_item(st);
                         if constexpr (ORDERED) rkey = order_key_root(sp, s);
@@ -590,7 +610,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                 is_single = false;
                 noerr_cont = false;
                 bool go_dir = true;
-                if (kText && ff > 0 && text_on && text_class(st, np, text_qflags)) {
+                if (kText && ff > 0 && text_on && text_class(st, np, text_qflags, !OCC::kSymbolLoad)) {
                     // the node this lane fast-forwarded into belongs to the text kernel: it goes back as it is
                     cmask = CH_SELF;
                     go_dir = false;
@@ -887,7 +907,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                     const uint32_t bit = __ffsll((long long)rest) - 1;
                     rest &= rest - 1;
                     const State c = make_child(bit);
-                    tx = text_on && text_class(c, np, text_qflags);
+                    tx = text_on && text_class(c, np, text_qflags, !OCC::kSymbolLoad);
                     pk = pack_item(c);
                 }
                 const uint32_t bt = __ballot_sync(0xFFFFFFFFu, has && tx), bc = __ballot_sync(0xFFFFFFFFu, has && !tx);

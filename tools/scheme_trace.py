@@ -1,4 +1,4 @@
-"""per-launch times of a k-error search (FMB_TRACE_SCHEME=1): python tools/scheme_trace.py [text] [reads] [k] [edit]"""
+"""per-launch times of a k-error search (FMB_TRACE_SCHEME=1): python tools/scheme_trace.py [text] [reads] [k] [edit] [sigma] [read length]"""
 import os, sys, time
 os.environ["FMB_TRACE_SCHEME"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,13 +9,14 @@ n_text = int(float(sys.argv[1])) if len(sys.argv) > 1 else 3_000_000_000
 nq = int(float(sys.argv[2])) if len(sys.argv) > 2 else 10_000_000
 ks = [int(sys.argv[3])] if len(sys.argv) > 3 else [1, 2]
 edits = [bool(int(sys.argv[4]))] if len(sys.argv) > 4 else [False, True]
-L = 150
-d_text = capi.synth_text_device(0, 5, n_text, 3)
-index = fmb.Index.build_from_device_text(5, d_text, n_text, sampling_rate=16, bidirectional=True, device=0)
+sigma = int(sys.argv[5]) if len(sys.argv) > 5 else 5
+L = int(sys.argv[6]) if len(sys.argv) > 6 else 150
+d_text = capi.synth_text_device(0, sigma, n_text, 3)
+index = fmb.Index.build_from_device_text(sigma, d_text, n_text, sampling_rate=16, bidirectional=True, device=0)
 off = np.arange(nq + 1, dtype=np.uint64) * np.uint64(L)
 for k in ks:
     for edit in edits:
-        d_reads = capi.synth_reads_err_device(0, d_text, n_text, nq, L, 5, 5, k, edit)
+        d_reads = capi.synth_reads_err_device(0, d_text, n_text, nq, L, 5, sigma, k, edit)
         sym = np.zeros(nq * L, dtype=np.uint8)
         capi.copy_to_host(0, sym, d_reads, nq * L)
         capi.device_free(0, d_reads)

@@ -137,7 +137,22 @@ struct SchemeOut {
     unsigned long long* hit_keys;
     unsigned long long* overflow_keys;
     const unsigned long long* in_keys;
+    // hit limit n = 1: best_keys[q] = smallest discovery-order key of a hit of query q found so far (all ones: none); subtrees whose
+    // smallest possible key is larger cannot hold the first hit and are dropped.  n_queries > 0 additionally orders the roots search
+    // by search (all queries' search 0, then search 1, ...), so that the later searches of a query start after its earlier hits exist.
+    unsigned long long* best_keys;
+    uint64_t n_queries;
 };
+
+// smallest discovery-order key a descendant of a node (e errors so far, depth = steps + e) can end with: the slots of errors still to
+// come hold at least the code of an insertion at the node itself (the only codes below "no further error"; edit distance only)
+template <bool EDIT>
+__device__ __forceinline__ unsigned long long order_key_lower_bound(const SchemeParams& sp, unsigned long long key, uint32_t steps, uint32_t e) {
+    if (!EDIT || e >= sp.key_slots) return key;
+    const uint32_t sh = 56 - (e + 1) * sp.key_bits;
+    const unsigned long long below = (sh + sp.key_bits >= 64) ? ~0ull : ((1ull << (sh + sp.key_bits)) - 1);
+    return (key & ~below) | ((unsigned long long)(steps + e) << sh);
+}
 
 // one cursor extension by `symb` in direction `right` from two loaded blocks (DNA: blocks are symbol independent)
 template <class OCC>
@@ -416,6 +431,10 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         uint32_t s = (uint32_t)(r % sp.n_searches);
                         State st;
                         st.qidx = (uint32_t)(r / sp.n_searches);
+                        if (ORDERED && out.n_queries) {                                        // search-major root order
+                            s = (uint32_t)(r / out.n_queries);
+                            st.qidx = (uint32_t)(r % out.n_queries);
+                        }
                         st.lb = 0; st.lb_rev = 0; st.len = ix.n; st.steps = 0;                 // BiFMIndexCursor.h:28-30
                         st.qposR = sp.start[s];
                         st.qposL = (sp.start[s] - 1) & 0xFFFF;                                 // SearchNg26.h:69-72
@@ -465,8 +484,12 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                             if (st.mode == MODE_NEXT) st.side = side_set(side_set(st.side, 1, 0, lastq), 1, 1, lastq);
                             }
                         }
+                        if constexpr (ORDERED) {
+                            rkey = order_key_root(sp, s);
+                            // a hit of an earlier search of this query exists: this search cannot hold the first hit
+                            if (out.best_keys != nullptr && (rkey & (0xFFull << 56)) > __ldcg(out.best_keys + st.qidx)) st.len = 0;
+                        }
                         it = pack_item(st);
-                        if constexpr (ORDERED) rkey = order_key_root(sp, s);
                     }
                 }
                 {
@@ -500,7 +523,11 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
         State st;
         if (active) {
             st = unpack_item(stack[top - 1 - lane]);
-            if constexpr (ORDERED) st.key = kstack[top - 1 - lane];
+            if constexpr (ORDERED) {
+                st.key = kstack[top - 1 - lane];
+                if (out.best_keys != nullptr && order_key_lower_bound<EDIT>(sp, st.key, st.steps, st.e) > __ldcg(out.best_keys + st.qidx))
+                    st.len = 0;                                  // every hit below this node comes after one already found: drop the subtree
+            }
         }
         top -= nact;
         __syncwarp();
@@ -888,7 +915,10 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         HitRec h;
                         h.qidx = st.qidx + out.qidx_base; h.lb = st.lb; h.lb_rev = sp.zero_lb_rev ? 0 : st.lb_rev; h.len = st.len; h.steps = st.steps; h.e = st.e;
                         out.hits[idx] = h;
-                        if constexpr (ORDERED) out.hit_keys[idx] = st.key;
+                        if constexpr (ORDERED) {
+                            out.hit_keys[idx] = st.key;
+                            if (out.best_keys != nullptr) atomicMin(out.best_keys + st.qidx, st.key);
+                        }
                     }
                 }
             }

@@ -279,6 +279,10 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     FMB_TRY(ovf[0].alloc(ovf_cap));
     FMB_TRY(ovf[1].alloc(ovf_cap));
     if (text_mode) FMB_TRY(text_list.alloc(ovf_cap));
+    // hit limit 1 (first hit per query): the kernel keeps the smallest key found per query and drops what cannot beat it
+    DevBuf<unsigned long long> best_keys;
+    const bool prune_first = ordered && n_limit == 1 && getenv("FMB_NO_FIRST_HIT_PRUNING") == nullptr;
+    if (prune_first) FMB_TRY(best_keys.alloc(std::max<uint64_t>(nq, 1)));
     if (ordered) {
         FMB_TRY(ovf_keys[0].alloc(ovf_cap));
         FMB_TRY(ovf_keys[1].alloc(ovf_cap));
@@ -303,6 +307,11 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
         so.counters = ctr.p;
         so.root_counter = ctr.p + 6;
         so.qidx_base = (uint32_t)q->qidx_base;
+        if (prune_first) {
+            FMB_CUDA(cudaMemsetAsync(best_keys.p, 0xFF, std::max<uint64_t>(nq, 1) * sizeof(unsigned long long), st));
+            so.best_keys = best_keys.p;
+            so.n_queries = nq;
+        }
         if (text_mode) {
             so.text = text_list.p;
             so.text_count = ctr.p + 7;

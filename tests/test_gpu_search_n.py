@@ -170,3 +170,24 @@ def test_search_n_with_spilled_frontier(gpu):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_search_n.py"), "-q", "-x", "-k", "repetitive or random_text"],
                        env=env, capture_output=True, text=True, timeout=900, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("edit", [False, True])
+def test_first_hit_limit_bounds_the_work(gpu, edit):
+    """n = 1: the kernel keeps the smallest discovery-order key per query and drops subtrees that cannot beat it (and starts the later
+    searches of a query after the earlier ones), so the first hit costs fewer extensions than enumerating everything -- with the same
+    result as the oracle's search_n"""
+    from fmb200 import schemes, synth
+    text = synth.multi_text([120000], 5, 29)
+    o, g = make_index_pair(gpu, text, 5, 8)
+    # (enough roots that the searches of a query do not all start in the first wave: 3 x 200 k against ~150 k resident lanes)
+    reads, _ = synth.reads_from_text(text[:120001], 200000, 48, 7)
+    reads[150000:] = synth.plant_errors(reads[150000:], 5, 1, edit, 9)
+    sym, off = synth.flatten(reads)
+    q = g.upload(sym, off)
+    sch, part = schemes.optimum(0, 2), schemes.uniform_partition(4, 48)
+    first = g.search_scheme(q, sch, part, edit, n=1)
+    exp = o.search_ng26(sym, off, sch, part, edit, max_hits=1)
+    assert _same_list(first.hits(), exp)
+    everything = g.search_scheme(q, sch, part, edit, n=10**9)
+    assert first.stats.extensions < 0.9 * everything.stats.extensions, (first.stats.extensions, everything.stats.extensions)

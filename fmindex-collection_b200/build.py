@@ -27,20 +27,51 @@ def _nvcc():
     raise RuntimeError("nvcc not found; libfmb200.so cannot be built")
 
 
+STAMP = os.path.join(HERE, "libfmb200.stamp")
+LOCK = os.path.join(HERE, ".build.lock")
+
+
+def _fingerprint():
+    """hash of everything the library is built from (sources, the C-ABI header, flags): file times do not survive a copy of the
+    tree to another machine, contents do"""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS + os.environ.get("FMB_NVCC_EXTRA", "").split()).encode())
+    paths = [os.path.join(HERE, "..", "include", "fmb200.h")]
+    for root, _, files in sorted(os.walk(CSRC)):
+        paths += [os.path.join(root, f) for f in sorted(files)]
+    for path in paths:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    for root, _, files in os.walk(CSRC):
-        for f in files:
-            if os.path.getmtime(os.path.join(root, f)) > t:
-                return True
-    return os.path.getmtime(os.path.join(HERE, "..", "include", "fmb200.h")) > t
+    with open(STAMP) as f:
+        return f.read().strip() != _fingerprint()
 
 
 def build(force=False, verbose=False):
+    """idempotent and safe when several processes call it at once (one rank per GPU under torchrun): an exclusive file lock
+    serialises them, the first one builds, the others find the stamp up to date; the library is linked under a temporary name and
+    renamed into place, so a process never maps a half-written file"""
     if not force and not needs_build():
         return LIB
+    import fcntl
+    with open(LOCK, "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or needs_build():
+                _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+    return LIB
+
+
+def _build_locked(verbose):
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -61,10 +92,15 @@ def build(force=False, verbose=False):
         if verbose:
             sys.stderr.write(outp)
         objs.append(obj)
-    proc = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs, capture_output=True, text=True)
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    proc = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
         raise RuntimeError("nvcc failed linking libfmb200.so")
+    os.replace(tmp, LIB)
+    with open(STAMP + ".tmp", "w") as f:
+        f.write(_fingerprint() + "\n")
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB
 
 

@@ -27,7 +27,9 @@ class Counters(C.Structure):
 def build_oracle():
     src = os.path.join(HERE, "fm_oracle.c")
     if not os.path.exists(ORACLE_LIB) or os.path.getmtime(ORACLE_LIB) < os.path.getmtime(src):
-        subprocess.run(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-o", ORACLE_LIB, src], check=True, cwd=HERE)
+        tmp = ORACLE_LIB + ".tmp.%d" % os.getpid()          # linked under a temporary name: concurrent processes never map a partial file
+        subprocess.run(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-o", tmp, src], check=True, cwd=HERE)
+        os.replace(tmp, ORACLE_LIB)
     return ORACLE_LIB
 
 

@@ -452,8 +452,8 @@ def main():
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         e2e_qps = q_all * K / e2e_s
-        h2d = nq * L + (nq + 1) * 8
-        d2h = len(locs) * 16
+        h2d = int(_st.h2d_bytes)          # counted by the library from the copies it issued (equal-length batches: the symbols only,
+        d2h = int(_st.d2h_bytes)          # the offsets are generated on the device) / the located rows it copied back
         e2e_locs[wl] = (locs.copy(), out)       # `out` is reused below
         # the same call on 2-bit packed host reads (what fmb200/io.hpp produces while parsing FASTA): a quarter of the bytes cross PCIe
         e2e_packed = None
@@ -468,8 +468,8 @@ def main():
                 plocs, _st = index.search_and_locate(None, off.array, scheme=scheme, partition=partition, edit=edit, out=out.array, packed=packed)
             torch.cuda.synchronize()
             pk_s = max_over_ranks(time.perf_counter() - t0)
-            e2e_packed = {"value": q_all * K / pk_s, "unit": "queries/s", "h2d_bytes_per_step": pw.array.nbytes + (nq + 1) * 8 + packed[1].nbytes + packed[2].nbytes,
-                          "d2h_bytes_per_step": len(plocs) * 16, "rows_equal_byte_path": int(len(plocs)) == int(len(locs)),
+            e2e_packed = {"value": q_all * K / pk_s, "unit": "queries/s", "h2d_bytes_per_step": int(_st.h2d_bytes),
+                          "d2h_bytes_per_step": int(_st.d2h_bytes), "rows_equal_byte_path": int(len(plocs)) == int(len(locs)),
                           "input": "reads 2-bit packed on the host beforehand (fmb_pack_symbols), fmb_search_and_locate_packed"}
             pw.free()
 

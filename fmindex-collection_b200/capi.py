@@ -22,7 +22,7 @@ class IndexInfo(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("extensions", C.c_uint64), ("occ_lookups", C.c_uint64), ("lf_steps", C.c_uint64),
                 ("frontier_peak", C.c_uint64), ("kernel_ms", C.c_double), ("main_kernel_ms", C.c_double),
-                ("line_requests", C.c_uint64)]
+                ("line_requests", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class FmbError(RuntimeError):

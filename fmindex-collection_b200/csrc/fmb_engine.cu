@@ -159,6 +159,7 @@ void Engine::run_chunks(Job& j, cudaStream_t st) {
                           : fmb_queries_upload(&q, j.ix, j.symbols, j.offsets + b, e - b);
         if (rc) { fail(rc, fmb_last_error()); publish(c, 0, off); continue; }
         q->qidx_base = b;
+        mine.h2d_bytes += q->h2d_bytes;
         double t1 = now_ms();
         fmb_results* hits = nullptr;
         rc = j.n_searches ? fmb_search_scheme(j.ix, q, j.edit, j.n_searches, j.n_parts, j.pi, j.l, j.u, j.partition, &hits) : fmb_search_exact(j.ix, q, &hits);
@@ -189,6 +190,7 @@ void Engine::run_chunks(Job& j, cudaStream_t st) {
         }
         double t4 = now_ms();
         cudaError_t ce = cudaSuccess;
+        mine.d2h_bytes += cnt * sizeof(fmb_loc32);
         if (cnt) ce = cudaMemcpyAsync(j.out + off, locs->locs.p, cnt * sizeof(fmb_loc32), cudaMemcpyDeviceToHost, st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         t_down += now_ms() - t4;
@@ -203,6 +205,8 @@ void Engine::run_chunks(Job& j, cudaStream_t st) {
     j.total.occ_lookups += mine.occ_lookups;
     j.total.line_requests += mine.line_requests;
     j.total.lf_steps += mine.lf_steps;
+    j.total.h2d_bytes += mine.h2d_bytes;
+    j.total.d2h_bytes += mine.d2h_bytes;
     j.total.kernel_ms += mine.kernel_ms;
     j.total.main_kernel_ms += mine.main_kernel_ms;
     j.total.frontier_peak = std::max(j.total.frontier_peak, mine.frontier_peak);
@@ -258,6 +262,8 @@ static int run_jobs(std::vector<Job>& jobs, uint64_t* n_out, fmb_stats* stats) {
         total.occ_lookups += j.total.occ_lookups;
         total.line_requests += j.total.line_requests;
         total.lf_steps += j.total.lf_steps;
+        total.h2d_bytes += j.total.h2d_bytes;
+        total.d2h_bytes += j.total.d2h_bytes;
         total.kernel_ms += j.total.kernel_ms;
         total.main_kernel_ms += j.total.main_kernel_ms;
         total.frontier_peak = std::max(total.frontier_peak, j.total.frontier_peak);

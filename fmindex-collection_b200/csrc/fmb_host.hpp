@@ -143,6 +143,7 @@ struct fmb_queries {
     uint64_t qidx_base = 0;           // added to every reported qidx (chunked uploads)
     uint64_t total_symbols = 0;
     uint32_t max_len = 0, min_len = 0;
+    uint64_t h2d_bytes = 0;           // bytes the upload copied host -> device
     fmb::DevBuf<uint8_t> symbols;     // padded to a multiple of 16 bytes
     fmb::DevBuf<uint64_t> offsets;    // nq + 1
     fmb::DevBuf<uint32_t> packed;     // sigma <= 5: 2-bit codes (symbol-1), 16 per word (+2 words of padding)

@@ -525,6 +525,10 @@ __global__ void __launch_bounds__(256) kmer_table_kernel(const __grid_constant__
     out[i] = make_uint2(lb, len);
 }
 
+__global__ void iota_offsets_kernel(uint64_t* __restrict__ off, uint64_t count, uint32_t stride) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < count) off[i] = i * stride;
+}
 __global__ void rebase_offsets_kernel(uint64_t* __restrict__ off, uint64_t count, uint64_t base) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i < count) off[i] -= base;

@@ -1100,6 +1100,7 @@ static int upload_queries(fmb_queries** out, const fmb_index* ix, const uint8_t*
         if (!rc && ne) rc = stage_epos.alloc(ne);
         if (!rc && ne) rc = stage_esym.alloc(ne);
         if (rc) { delete q; return rc; }
+        q->h2d_bytes += (w1 - w0) * sizeof(uint32_t) + ne * 9;
         e = cudaMemcpyAsync(stage_words.p, pk->words + w0, (w1 - w0) * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess && ne) e = cudaMemcpyAsync(stage_epos.p, lo, ne * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess && ne) e = cudaMemcpyAsync(stage_esym.p, pk->exc_sym + (lo - pk->exc_pos), ne, cudaMemcpyHostToDevice, st);
@@ -1114,6 +1115,7 @@ static int upload_queries(fmb_queries** out, const fmb_index* ix, const uint8_t*
             note_launches(1);
         }
     } else if (in_total) {
+        q->h2d_bytes += in_total;
         e = cudaMemcpyAsync(sym_dst, symbols + offsets[0], in_total, cudaMemcpyHostToDevice, st);
     }
     // validate the offsets while the symbols are in flight
@@ -1132,8 +1134,18 @@ static int upload_queries(fmb_queries** out, const fmb_index* ix, const uint8_t*
     q->max_len = mx;
     q->min_len = nq ? mn : 0;
     if (e == cudaSuccess) e = cudaMemsetAsync(q->symbols.p + total, 0xFF, 32, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(off_dst, offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && offsets[0] != 0) {
+    if (nq && mx == mn) {
+        // reads of one length (the usual batch): offsets[i] = i * L is generated on the device, 8 bytes per query stay off PCIe
+        if (e == cudaSuccess) {
+            iota_offsets_kernel<<<grid_for(nq + 1, 256), 256, 0, st>>>(off_dst, nq + 1, mx);
+            e = cudaGetLastError();
+            note_launches(1);
+        }
+    } else {
+        q->h2d_bytes += (nq + 1) * 8;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(off_dst, offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess && offsets[0] != 0 && !(nq && mx == mn)) {
         // a slice of a larger batch: make the offsets relative to the first symbol of the slice, on the device
         rebase_offsets_kernel<<<grid_for(nq + 1, 256), 256, 0, st>>>(off_dst, nq + 1, offsets[0]);
         e = cudaGetLastError();

@@ -87,6 +87,8 @@ typedef struct {
     double   kernel_ms;        /* device time of the call (CUDA events)                     */
     double   main_kernel_ms;   /* device time of the dominant kernel alone (search / LF walk) */
     uint64_t line_requests;    /* 128-byte-line requests issued by the two-symbol exact kernel (physical work) */
+    uint64_t h2d_bytes;        /* fmb_search_and_locate*: bytes the call copied host -> device (symbols, offsets, ...)   */
+    uint64_t d2h_bytes;        /* ... and device -> host (located rows)                                                 */
 } fmb_stats;
 
 const char* fmb_last_error(void);

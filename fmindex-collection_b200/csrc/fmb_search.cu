@@ -157,6 +157,22 @@ int launch_scheme(const fmb_index* ix, const SchemeParams& sp, const fmb_queries
     return launch_scheme_t<OccGen, EDIT, ORDERED, PSEUDO>(ix, ix->view_gen(), sp, q, n_roots, in_items, n_in, out, st);
 }
 
+// ---- text list by class: the lanes of a warp of the text kernel take consecutive items; items of one (search, part, errors) class
+//      run the same branches of the state machine (skippable stretch, 16-position evaluation, node visits), so the list is grouped
+//      by class before the kernel reads it (one 8-bit radix pass over 4-byte keys + a gather; ~0.3 ms per 8 M items)
+__global__ void text_class_keys_kernel(const Item* __restrict__ items, uint64_t count, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t meta = items[i].meta;
+    // search (4 bits of it), part (4 bits), errors so far (2 bits): 10 bits
+    keys[i] = (((meta >> 16) & 15u) << 6) | (((meta >> 8) & 15u) << 2) | (meta & 3u);
+    idx[i] = (uint32_t)i;
+}
+__global__ void gather_items_kernel(const Item* __restrict__ items, const uint32_t* __restrict__ idx, uint64_t count, Item* __restrict__ out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < count) out[i] = items[idx[i]];
+}
+
 // ---- hit limit: put the hits into the reference's discovery order and cut every query off after n rows ----------------------
 __global__ void iota_kernel(uint32_t* out, uint64_t count) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -273,12 +289,23 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     // (without text mode the roots go in slabs as well: what a slab spills -- warp stacks that ran full -- stays bounded)
     const uint64_t slab = std::min<uint64_t>(std::max<uint64_t>(n_roots, 1), env_slab ? env_slab : (text_mode ? (uint64_t(8) << 20) : (uint64_t(4) << 20)));
     const uint64_t ovf_cap = std::max<uint64_t>(1u << 20, slab * 2 + (1u << 18));       // items of 32 bytes
-    DevBuf<Item> ovf[2], text_list;
+    DevBuf<Item> ovf[2], text_list, text_sorted;
+    DevBuf<uint32_t> tkeys[2], tidx[2];
+    DevBuf<uint8_t> tsort_tmp;
+    size_t tsort_bytes = 0;
+    static const bool sort_text = getenv("FMB_NO_TEXT_SORT") == nullptr;
     DevBuf<unsigned long long> ovf_keys[2], hit_keys;
     DevBuf<unsigned long long> ctr;          // [0..3] counters, [4] hit_count, [5] overflow_count, [6] root_counter, [7] text_count, [8] row_count
     FMB_TRY(ovf[0].alloc(ovf_cap));
     FMB_TRY(ovf[1].alloc(ovf_cap));
     if (text_mode) FMB_TRY(text_list.alloc(ovf_cap));
+    if (text_mode && sort_text && sp.edit) {
+        // (edit distance only: the Hamming walk has one shape whatever the class)
+        FMB_TRY(text_sorted.alloc(ovf_cap));
+        for (int b = 0; b < 2; ++b) { FMB_TRY(tkeys[b].alloc(ovf_cap)); FMB_TRY(tidx[b].alloc(ovf_cap)); }
+        FMB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tsort_bytes, tkeys[0].p, tkeys[1].p, tidx[0].p, tidx[1].p, (int64_t)ovf_cap, 0, 10, active_stream(ix)));
+        FMB_TRY(tsort_tmp.alloc(tsort_bytes));
+    }
     // hit limit 1 (first hit per query): the kernel keeps the smallest key found per query and drops what cannot beat it
     DevBuf<unsigned long long> best_keys;
     const bool prune_first = ordered && n_limit == 1 && getenv("FMB_NO_FIRST_HIT_PRUNING") == nullptr;
@@ -356,7 +383,17 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
                     // the single-row items of this pass are decided on the text; what survives joins the overflow list
                     const unsigned long long n_text = h_ctr[7], back0 = h_ctr[5];
                     if (trace) cudaEventRecord(tr.a, st);
-                    FMB_TRY(launch_text(ix, sp, q, text_list.p, n_text, so, pseudo, st));
+                    const Item* text_in = text_list.p;
+                    if (text_sorted.p && n_text > 65536) {
+                        const unsigned grid = (unsigned)((n_text + 255) / 256);
+                        text_class_keys_kernel<<<grid, 256, 0, st>>>(text_list.p, n_text, tkeys[0].p, tidx[0].p);
+                        FMB_CUDA(cub::DeviceRadixSort::SortPairs(tsort_tmp.p, tsort_bytes, tkeys[0].p, tkeys[1].p, tidx[0].p, tidx[1].p, (int64_t)n_text, 0, 10, st));
+                        gather_items_kernel<<<grid, 256, 0, st>>>(text_list.p, tidx[1].p, n_text, text_sorted.p);
+                        FMB_CUDA(cudaGetLastError());
+                        note_launches(3);
+                        text_in = text_sorted.p;
+                    }
+                    FMB_TRY(launch_text(ix, sp, q, text_in, n_text, so, pseudo, st));
                     if (trace) cudaEventRecord(tr.b, st);
                     FMB_CUDA(cudaMemsetAsync(ctr.p + 7, 0, sizeof(unsigned long long), st));
                     FMB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));

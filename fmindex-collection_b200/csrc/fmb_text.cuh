@@ -32,6 +32,10 @@ constexpr int kTextStack = 16;       // private depth-first stack (packed nodes)
 #define FMB_TEXT_BULK2 1
 #endif
 constexpr bool kBulk2 = FMB_TEXT_BULK2 != 0;
+#ifndef FMB_TEXT_PREFETCH
+#define FMB_TEXT_PREFETCH 0        // measured: fetching one window word ahead in lockstep costs requests and buys nothing (76.6 vs 79.0 ms, k = 2 edit)
+#endif
+constexpr bool kPrefetch = FMB_TEXT_PREFETCH != 0;
 #ifndef FMB_TEXT_MINB
 #define FMB_TEXT_MINB 4
 #endif
@@ -216,6 +220,7 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
         uint32_t row = rows[m / SPW];
         uint32_t r = m % SPW;
         if (!BYTES && r >= 4 && jv.jump4[R] != nullptr) {
+#pragma unroll 1
             while (r >= 4) {
                 const uint2 e = __ldg(jv.jump4[R] + row);      // valid: the window holds no delimiter
                 n_phys += 1;
@@ -223,6 +228,7 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                 r -= 4;
             }
         }
+#pragma unroll 1
         while (r--) row = lf1(row);
         return row;
     };
@@ -254,14 +260,16 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
     // Pending hand-overs of this lane's item to the frontier kernel (served in bulk, see the R phase below), the nodes visited in
     // the current iteration (the popped node and those of its children whose own children can only continue error free) and the
     // comparisons along a diagonal queued by those visits.
-    unsigned long long req[24], lc[12], mini[4];
+    unsigned long long req[16], lc[12], mini[4];
     int nreq = 0, nlc = 0, nmini = 0;
     auto request = [&](TNode s, uint32_t kind) {
         s.kind = kind;
         req[nreq++] = tnode_pack(s);
     };
+    uint32_t reach = 0;            // the farthest window position a node of this lane's item has got to
     auto push = [&](TNode s) {
         s.kind = TN_EXPAND;
+        reach = s.m > reach ? s.m : reach;
         if (top < kTextStack) stk[top++] = tnode_pack(s);
         else request(s, TN_CONT);
     };
@@ -274,6 +282,7 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
     auto match_run = [&](uint32_t m, uint32_t c, uint32_t limit, uint32_t& status) -> uint32_t {
         uint32_t done = 0;
         status = 1;
+#pragma unroll 1
         while (done < limit) {
             if (c + done >= q_limit || !ensure(m + done)) { status = 2; break; }
             uint32_t n = have * SPW - (m + done);
@@ -324,6 +333,7 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
         const bool serve = n_wants >= 8 || (n_wants > 0 && !__any_sync(0xFFFFFFFFu, busy)) || __any_sync(0xFFFFFFFFu, nreq >= 4);
         if (serve) {
             // ---- R: hand-overs: the entry state moved to (m, c) with the node's fields
+#pragma unroll 1
             for (int i = 0; __any_sync(0xFFFFFFFFu, i < nreq); ++i) {
                 if (i < nreq) {
                     const TNode s = tnode_unpack(req[i]);
@@ -370,6 +380,7 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                     rows[0] = R ? st.lb_rev : st.lb;
                     have = 0;
                     closed = false;
+                    reach = 0;
                     ok = fetch();
                 }
                 if (!ok) {
@@ -386,10 +397,12 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                     const uint32_t run = R ? qlen - st.qposR : st.qposL + 1;
                     q_limit = run < QCAP ? run : QCAP;
                     const uint32_t nw = (q_limit + SPW - 1) / SPW;
+#pragma unroll 1
                     for (uint32_t k = 0; k < (uint32_t)kTextQWords + 1; ++k) {
                         uint32_t w = 0;
                         if (k < nw) {
                             if (BYTES) {
+#pragma unroll 1
                                 for (uint32_t j = 0; j < 4; ++j) {
                                     const long long at = R ? (long long)(qbase + st.qposR + 4 * k + j) : (long long)(qbase + st.qposL) - (long long)(4 * k + j);
                                     const uint32_t b = (at >= 0 && 4 * k + j < run) ? __ldg(qsym + at) : 0u;
@@ -425,9 +438,13 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                 }
             }
         }
+        // ---- F: window prefetch.  A lane whose walk has entered the last window word it holds fetches the next one NOW, together with
+        //      the other lanes in that situation, instead of stalling the warp alone in the middle of a visit a few iterations later
+        if (kPrefetch && top > 0 && !closed && have < (uint32_t)kTextWords && reach + SPW / 2 >= have * SPW) fetch();
         // ---- V: the popped node, then those of its children whose own children can only continue error free -----------------------
         nmini = 0;
         if (top > 0) mini[nmini++] = stk[--top];
+#pragma unroll 1
         for (int vi = 0; __any_sync(0xFFFFFFFFu, vi < nmini); ++vi) {
             if (vi >= nmini) continue;
             const TNode s = tnode_unpack(mini[vi]);
@@ -490,6 +507,7 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
             }
         }
         // ---- L: comparisons along a diagonal -------------------------------------------------------------------------------------------
+#pragma unroll 1
         for (int li = 0; __any_sync(0xFFFFFFFFu, li < nlc); ++li) {
             if (li >= nlc) continue;
             TNode s = tnode_unpack(lc[li]);

@@ -299,7 +299,7 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     FMB_TRY(ovf[0].alloc(ovf_cap));
     FMB_TRY(ovf[1].alloc(ovf_cap));
     if (text_mode) FMB_TRY(text_list.alloc(ovf_cap));
-    if (text_mode && sort_text && sp.edit) {
+    if (text_mode && sort_text && (sp.edit || getenv("FMB_TEXT_SORT_HAMMING"))) {
         // (edit distance only: the Hamming walk has one shape whatever the class)
         FMB_TRY(text_sorted.alloc(ovf_cap));
         for (int b = 0; b < 2; ++b) { FMB_TRY(tkeys[b].alloc(ovf_cap)); FMB_TRY(tidx[b].alloc(ovf_cap)); }

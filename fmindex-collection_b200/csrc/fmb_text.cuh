@@ -236,6 +236,24 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
     auto fetch = [&]() -> bool {
         if (closed || have == (uint32_t)kTextWords) return false;
         const uint32_t row = rows[have];
+        if (!EDIT && !BYTES && jv.jshift[R] && have + 2 <= (uint32_t)kTextWords) {
+            // merged LF^16 / LF^32 entries (direction 0 when the image holds them): one 16-byte lookup = 32 window symbols.  Hamming
+            // instantiation only: that kernel is request bound; the edit-distance one is instruction-cache bound and lost 8 % to the
+            // extra code (k = 2: 64.6 -> 70.2 ms)
+            const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(jv.jump[R]) + row);
+            n_phys += 1;
+            if (e4.x == kJumpInvalid) { closed = true; return false; }
+            sw[have * 256 + tid] = R ? e4.y : rev2(e4.y);
+            rows[have + 1] = e4.x;
+            have += 1;
+            if (e4.z != kJumpInvalid) {
+                sw[have * 256 + tid] = R ? e4.w : rev2(e4.w);
+                rows[have + 1] = e4.z;
+                have += 1;
+            }
+            sw[have * 256 + tid] = 0;
+            return true;
+        }
         const uint2 e = BYTES ? __ldg(jv.jump4[R] + row) : __ldg(jv.jump[R] + ((size_t)row << jv.jshift[R]));
         n_phys += 1;
         if (e.x == kJumpInvalid) { closed = true; return false; }

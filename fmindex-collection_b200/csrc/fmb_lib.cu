@@ -322,7 +322,7 @@ uint32_t plan_tables(const fmb_index* ix, uint64_t n_samples) {
         const bool j0 = admit(FMB_TABLE_JUMP, 8 * n);
         const bool j1 = ix->bidirectional && admit(FMB_TABLE_JUMP_REV, 8 * n);
         uint32_t bk = 0;
-        while (bk < 13 && (uint64_t(32) << (2 * (bk + 1))) <= ix->n) ++bk;
+        while (bk < 14 && (uint64_t(8) << (2 * (bk + 1))) <= ix->n) ++bk;
         if (ix->bidirectional) admit(FMB_TABLE_BIKMER, 16.0 * (double)(uint64_t(1) << (2 * bk)));
         if (allowed & FMB_TABLE_LOCBLOCK) admit(FMB_TABLE_LOCROW, 4 * n);
         if (j0) admit(FMB_TABLE_JUMP32, 8 * n);
@@ -464,7 +464,7 @@ int build_bikmer(fmb_index* ix) {
         return FMB_OK;
     }
     uint32_t k = 0;
-    while (k < 13 && (uint64_t(32) << (2 * (k + 1))) <= ix->n) ++k;
+    while (k < 14 && (uint64_t(8) << (2 * (k + 1))) <= ix->n) ++k;
     if (k < 2) return FMB_OK;
     const uint64_t count = uint64_t(1) << (2 * k);
     cudaStream_t st = active_stream(ix);

@@ -287,7 +287,7 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     const bool text_mode = !ordered && (ix->dna || sp.edit) && text_mode_available(ix, q, sp.force_left != 0);
     static const uint64_t env_slab = getenv("FMB_SCHEME_SLAB") ? strtoull(getenv("FMB_SCHEME_SLAB"), nullptr, 10) : 0;
     // (without text mode the roots go in slabs as well: what a slab spills -- warp stacks that ran full -- stays bounded)
-    const uint64_t slab = std::min<uint64_t>(std::max<uint64_t>(n_roots, 1), env_slab ? env_slab : (text_mode ? (uint64_t(8) << 20) : (uint64_t(4) << 20)));
+    const uint64_t slab = std::min<uint64_t>(std::max<uint64_t>(n_roots, 1), env_slab ? env_slab : (text_mode ? (uint64_t(16) << 20) : (uint64_t(4) << 20)));      // at 30 M roots: 8 M 63.5 ms, 16 M 61.5, 32 M 60.1 (k = 2 edit)
     const uint64_t ovf_cap = std::max<uint64_t>(1u << 20, slab * 2 + (1u << 18));       // items of 32 bytes
     DevBuf<Item> ovf[2], text_list, text_sorted;
     DevBuf<uint32_t> tkeys[2], tidx[2];

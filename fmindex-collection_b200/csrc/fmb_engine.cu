@@ -229,7 +229,9 @@ void engine_destroy(fmb_index* ix) {
 
 static void prepare(Job& j) {
     static const int env_chunk = getenv("FMB_E2E_CHUNK_LOG2") ? atoi(getenv("FMB_E2E_CHUNK_LOG2")) : 0;
-    j.chunk = env_chunk ? (uint64_t(1) << env_chunk) : (1u << 19);      // measured with 10 M reads: 2^19 x 6 threads beats 2^20 x 3 and 2^18 x 12
+    // measured with 10 M reads: exact search (PCIe bound) 2^19 x 6 threads beats 2^20 x 3 and 2^18 x 12; the k-error searches run several
+    // kernels per chunk and want larger launches: 2^20 (k = 1 edit 270 -> 312 M reads/s, k = 2 edit 111 -> 121)
+    j.chunk = env_chunk ? (uint64_t(1) << env_chunk) : (j.n_searches ? (1u << 20) : (1u << 19));
     const uint64_t nq = j.q_end - j.q_begin;
     j.n_chunks = (nq + j.chunk - 1) / j.chunk;
     j.chain_end.assign(j.n_chunks, 0);

@@ -2,7 +2,7 @@
 //   FASTA reference -> BiFMIndex (built on the GPU, cached next to the FASTA as <ref>.fmb like the example's <ref>.index,
 //   example/utils.h:107-141) -> FASTA reads (+ reverse complements unless --no-reverse, main.cpp:71) -> k-error search
 //   (--mode all | besthits, --maxhitsperquery, main.cpp:167-212) -> locate -> "queryId seqId pos" lines (--save_output, :260-266).
-// usage: fmb_example --ref ref.fa --query reads.fa [--max_k 2] [--hamming] [--no-reverse] [--mode all|besthits]
+// usage: fmb_example --ref ref.fa --query reads.fa [--max_k 2] [--hamming] [--no-reverse] [--packed] [--mode all|besthits]
 //                    [--maxhitsperquery N] [--save_output out.txt] [--sampling_rate 16] [--no-index-cache]
 #include <chrono>
 #include <cstdio>
@@ -14,7 +14,7 @@
 int main(int argc, char** argv) {
     std::string ref, query, out, mode = "all";
     size_t k = 0, rate = 16, maxhits = 0;
-    bool reverse = true, hamming = false, cache = true;
+    bool reverse = true, hamming = false, cache = true, packed = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> std::string { if (i + 1 >= argc) { std::fprintf(stderr, "%s needs a value\n", a.c_str()); std::exit(2); } return argv[++i]; };
@@ -26,6 +26,7 @@ int main(int argc, char** argv) {
         else if (a == "--maxhitsperquery") maxhits = std::stoul(next());
         else if (a == "--mode") mode = next();
         else if (a == "--no-reverse") reverse = false;
+        else if (a == "--packed") packed = true;
         else if (a == "--hamming") hamming = true;
         else if (a == "--no-index-cache") cache = false;
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
@@ -47,6 +48,25 @@ int main(int argc, char** argv) {
             return ix;
         }();
         auto t1 = now();
+        if (packed) {
+            // the bulk path on 2-bit packed reads (io.hpp packs while parsing; fmb_search_and_locate_packed): mode "all" without a hit
+            // limit, reads of one length -- what a read mapper feeds
+            if (mode != "all" || maxhits) throw std::runtime_error("--packed serves --mode all without --maxhits");
+            auto [pq, infos] = fmb200::io::loadQueriesPacked<Sigma>(query, reverse, true);
+            size_t const L = pq.size() ? pq.length(0) : 0;
+            for (size_t q = 0; q < pq.size(); ++q)
+                if (pq.length(q) != L) throw std::runtime_error("--packed needs reads of one length");
+            std::printf("index: %zu rows (%.2fs); loaded %zu queries (incl reverse complements), %zu packed words\n", index.size(), secs(t0, t1), pq.size(),
+                        pq.words.size());
+            auto t2 = now();
+            auto [scheme, partition] = hamming ? fmb200::search_scheme::facadeScheme<false>(k, L) : fmb200::search_scheme::facadeScheme<true>(k, L);
+            auto rows = fmb200::io::search_and_locate_bulk(index, pq, !hamming, &scheme, &partition);
+            auto t3 = now();
+            std::printf("k=%zu %s all (packed): %.3fs search+locate, %.0f q/s, %zu results\n", k, hamming ? "hamming" : "edit", secs(t2, t3),
+                        pq.size() / std::max(secs(t2, t3), 1e-9), rows.size());
+            if (!out.empty()) fmb200::io::saveResults(out, rows);
+            return 0;
+        }
         auto [queries, infos] = fmb200::io::loadQueries<Sigma>(query, reverse, true);
         std::printf("index: %zu rows (%.2fs); loaded %zu queries (incl reverse complements)\n", index.size(), secs(t0, t1), queries.size());
         std::vector<std::tuple<size_t, size_t, size_t, size_t>> results;

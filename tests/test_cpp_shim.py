@@ -117,6 +117,23 @@ int main(int argc, char** argv) {
     bool threw = false;
     try { fmb200::io::loadQueries<5>(argv[1], false, false); } catch (std::runtime_error const&) { threw = true; }
     std::printf("threw=%d missing=%zu\n", int(threw), std::get<0>(fmb200::io::loadQueries<5>("/nonexistent.fa", true, true)).size());
+    // packing reader: the same batch as 2-bit words + exception list, equal to what fmb_pack_symbols makes of the flattened bytes
+    {
+        auto [pq, pinfo] = fmb200::io::loadQueriesPacked<6>(argv[1], true, false);
+        bool same = pq.size() == q.size() && pinfo == info;
+        auto flat = fmb200::flatten(q);
+        same = same && pq.offsets == flat.offsets && pq.symbols() == flat.symbols.size();
+        for (size_t i = 0; same && i < flat.symbols.size(); ++i) same = pq.symbol(i) == flat.symbols[i];
+        std::vector<uint32_t> words((flat.symbols.size() + 15) / 16 + 1, 0);
+        std::vector<uint64_t> ep(flat.symbols.size());
+        std::vector<uint8_t> es(flat.symbols.size());
+        uint64_t ne = fmb_pack_symbols(flat.symbols.data(), 0, flat.symbols.size(), 5, words.data(), ep.data(), es.data(), ep.size());
+        ep.resize(ne); es.resize(ne);
+        uint32_t const* w = pq.data();
+        same = same && ep == pq.exc_pos && es == pq.exc_sym && pq.words.size() == words.size();
+        for (size_t i = 0; same && i < words.size(); ++i) same = w[i] == words[i];
+        std::printf("packed=%d exceptions=%zu\n", int(same), pq.exc_pos.size());
+    }
     std::vector<std::tuple<size_t, size_t, size_t, size_t>> res{{3, 0, 17, 1}, {4, 1, 2, 0}};
     fmb200::io::saveResults(argv[2], res);
     std::vector<fmb_loc32> res2{{7, 1, 99, 2}};
@@ -132,7 +149,7 @@ int main(int argc, char** argv) {
                     f"-Wl,-rpath,{lib}", "-o", str(exe)], check=True)
     out = subprocess.run([str(exe), str(fa), str(tmp_path / "out.txt")], check=True, capture_output=True, text=True).stdout.splitlines()
     assert out == ["r0 first|0|1234441", "r0 first|1|4111234", "r1|0|123450", "r1|1|051234", "r2|0|", "r2|1|", "r3|0|332", "r3|1|322",
-                   "123410", "threw=1 missing=0"]
+                   "123410", "threw=1 missing=0", "packed=1 exceptions=4"]
     assert (tmp_path / "out.txt").read_text() == "3 0 17\n4 1 2\n"
     assert (tmp_path / "out.txt2").read_text() == "7 1 99\n"
 

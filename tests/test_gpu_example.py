@@ -64,6 +64,10 @@ def test_example_program(gpu, tmp_path):
     sch, part = schemes.facade_scheme(True, 1, L)
     exp = expected(o.search_ng26(sym, off, sch, part, True))
     assert _lines(out) == exp and len(exp) >= 100
+    # the same search on 2-bit packed reads (io.hpp packs while parsing, fmb_search_and_locate_packed): identical lines
+    r = subprocess.run([exe, "--ref", ref_fa, "--query", reads_fa, "--max_k", "1", "--packed", "--save_output", out + "p"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "(packed)" in r.stdout and _lines(out + "p") == exp
     # second run: index loaded from the cache file; Hamming, hit limit 1 (search_n)
     r = subprocess.run([exe, "--ref", ref_fa, "--query", reads_fa, "--max_k", "2", "--hamming", "--maxhitsperquery", "1", "--save_output", out],
                        capture_output=True, text=True)

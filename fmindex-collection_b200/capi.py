@@ -45,7 +45,7 @@ SYMBOLS = [
     "fmb_search_exact", "fmb_search_scheme", "fmb_search_scheme_n", "fmb_search_scheme_pseudo", "fmb_search_backtracking", "fmb_locate", "fmb_locate_rows", "fmb_sample_value",
     "fmb_results_count", "fmb_results_kind", "fmb_results_fetch_hits", "fmb_results_fetch_locs", "fmb_results_fetch_locs32",
     "fmb_results_get_stats", "fmb_results_destroy",
-    "fmb_search_and_locate", "fmb_search_and_locate_packed", "fmb_search_and_locate_multi", "fmb_index_replicate", "fmb_index_save", "fmb_index_load", "fmb_checksum64",
+    "fmb_search_and_locate", "fmb_search_and_locate_packed", "fmb_search_and_locate_multi", "fmb_search_and_locate_parts", "fmb_index_replicate", "fmb_index_save", "fmb_index_load", "fmb_checksum64",
     "fmb_index_set_exact_mode", "fmb_index_set_locate_mode", "fmb_synth_text_device", "fmb_synth_reads_device", "fmb_synth_reads_err_device", "fmb_synth_repeat_text_device", "fmb_synth_unit_reads_device", "fmb_index_set_stream", "fmb_set_image_budget", "fmb_measure_gather", "fmb_kernel_launch_count", "fmb_device_free", "fmb_copy_to_host", "fmb_host_alloc_pinned", "fmb_host_free_pinned",
 ]
 
@@ -375,6 +375,31 @@ def search_and_locate_multi(replicas, symbols, offsets, scheme=None, partition=N
                                              C.c_uint32(ns), C.c_uint32(npart), _ptr(pi), _ptr(l), _ptr(u), _ptr(part),
                                              _ptr(out), C.c_uint64(shard_capacity), n_out, C.byref(st)))
     return [out[g * shard_capacity: g * shard_capacity + n_out[g]] for g in range(G)], st
+
+
+def search_and_locate_parts(parts, seq_base, symbols, offsets, scheme=None, partition=None, edit=False, part_capacity=None):
+    """fmb_search_and_locate_parts: a collection split into several indices over disjoint sequences; the whole batch is searched in every
+    part, rows carry the sequence numbers of the whole collection; returns (list of row arrays, one per part, stats)"""
+    symbols, offsets = _u8(symbols), _u64(offsets)
+    nq = offsets.size - 1
+    P = len(parts)
+    if scheme is None:
+        ns, npart, pi, l, u, part = 0, 0, None, None, None, None
+    else:
+        pi, l, u = (np.ascontiguousarray(a, dtype=np.uint32) for a in scheme)
+        part = _u32(partition)
+        ns, npart = pi.shape
+    if part_capacity is None:
+        part_capacity = max(nq, 1) * 4
+    out = np.zeros(part_capacity * P, dtype=LOC32_DTYPE)
+    handles = (C.c_void_p * P)(*[r.h for r in parts])
+    bases = _u64(seq_base)
+    n_out = (C.c_uint64 * P)()
+    st = Stats()
+    _check(lib().fmb_search_and_locate_parts(handles, C.c_uint32(P), _ptr(bases), _ptr(symbols), _ptr(offsets), C.c_uint64(nq), C.c_int(1 if edit else 0),
+                                             C.c_uint32(ns), C.c_uint32(npart), _ptr(pi), _ptr(l), _ptr(u), _ptr(part),
+                                             _ptr(out), C.c_uint64(part_capacity), n_out, C.byref(st)))
+    return [out[g * part_capacity: g * part_capacity + n_out[g]] for g in range(P)], st
 
 
 class Queries:

@@ -349,4 +349,39 @@ int fmb_search_and_locate_multi(const fmb_index* const* replicas, uint32_t n_rep
     return run_jobs(jobs, n_out, stats);
 }
 
+int fmb_search_and_locate_parts(const fmb_index* const* parts, uint32_t n_index_parts, const uint64_t* seq_base, const uint8_t* symbols,
+                                const uint64_t* offsets, uint64_t nq, int edit, uint32_t n_searches, uint32_t n_parts, const uint32_t* pi,
+                                const uint32_t* l, const uint32_t* u, const uint32_t* partition, fmb_loc32* out, uint64_t part_capacity,
+                                uint64_t* n_out, fmb_stats* stats) {
+    if (!parts || n_index_parts == 0 || !seq_base || !offsets || !n_out || (part_capacity && !out)) { set_error("NULL argument"); return FMB_EINVAL; }
+    for (uint32_t g = 0; g < n_index_parts; ++g) {
+        n_out[g] = 0;
+        if (!parts[g]) { set_error("part %u is NULL", g); return FMB_EINVAL; }
+        for (uint32_t h = 0; h < g; ++h)
+            if (parts[h] == parts[g]) { set_error("part %u listed twice", g); return FMB_EINVAL; }
+        if (seq_base[g] + parts[g]->n_delims > 0xFFFFFFFFull) { set_error("part %u: sequence numbers do not fit 32 bits", g); return FMB_EUNSUPPORTED; }
+    }
+    if (stats) *stats = fmb_stats{};
+    FMB_TRY(check_scheme_args(n_searches, pi, l, u, partition));
+    if (nq == 0) return FMB_OK;
+    // every part searches the whole batch (the parts hold different sequences: an occurrence lies in exactly one of them)
+    std::vector<Job> jobs(n_index_parts);
+    for (uint32_t g = 0; g < n_index_parts; ++g) {
+        Job& j = jobs[g];
+        j.ix = parts[g]; j.symbols = symbols; j.offsets = offsets; j.q_begin = 0; j.q_end = nq;
+        j.edit = edit; j.n_searches = n_searches; j.n_parts = n_parts; j.pi = pi; j.l = l; j.u = u; j.partition = partition;
+        j.out = out + (uint64_t)g * part_capacity; j.capacity = part_capacity;
+    }
+    const int rc = run_jobs(jobs, n_out, stats);
+    // sequence numbers of the whole collection
+    for (uint32_t g = 0; g < n_index_parts; ++g) {
+        const uint32_t base = (uint32_t)seq_base[g];
+        if (base == 0) continue;
+        fmb_loc32* rows = out + (uint64_t)g * part_capacity;
+        const uint64_t n = std::min<uint64_t>(n_out[g], part_capacity);
+        for (uint64_t i = 0; i < n; ++i) rows[i].seq += base;
+    }
+    return rc;
+}
+
 }  // extern "C"

@@ -11,7 +11,8 @@
  *   - no CPU fallback: without a usable CUDA device every compute entry point fails with FMB_ENODEVICE;
  *   - symbols are uint8_t in [0, sigma); symbol 0 is the sequence delimiter (fmindex/BiFMIndex.h:26 FirstSymb=1) unless the
  *     index was created with FMB_INDEX_NO_DELIM;
- *   - rows / text positions are 64-bit in the interface; this build supports indices with n < 2^32 - 64 rows;
+ *   - rows / text positions are 64-bit in the interface; one index holds n < 2^32 - 64 rows, larger collections are searched as
+ *     several indices over disjoint sets of sequences (fmb_search_and_locate_parts);
  *   - one fmb_index lives on one GPU.  Multi-GPU = one index replica per device (fmb_index_replicate), queries sharded by
  *     fmb_search_and_locate_multi or by the caller (one process per GPU: bench.py); there is no collective on the search path.
  */
@@ -284,6 +285,19 @@ int fmb_search_and_locate_multi(const fmb_index* const* replicas, uint32_t n_rep
                                 int edit, uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l,
                                 const uint32_t* u, const uint32_t* partition,
                                 fmb_loc32* out, uint64_t shard_capacity, uint64_t* n_out /* n_replicas */, fmb_stats* stats);
+
+/* ---- collections beyond one index (n >= 2^32 - 64 rows; the reference switches to a 64-bit suffix array there, utils.h:243-247) ----
+ * The device image keeps 32-bit rows, so a larger collection is split at sequence borders into parts, one fmb_index per part (on one
+ * device when the images fit -- fmb_set_image_budget -- or on several).  fmb_search_and_locate_parts searches the WHOLE batch in every
+ * part at the same time; the rows of part p are written to out + p * part_capacity, counted in n_out[p], and carry the sequence
+ * numbers of the whole collection (seq + seq_base[p]).  An occurrence lies in exactly one sequence, hence in exactly one part: the
+ * located rows of all parts together are those of one index over the whole collection (as a multiset; hit limits per query would
+ * apply per part and are not offered here). */
+int fmb_search_and_locate_parts(const fmb_index* const* parts, uint32_t n_index_parts, const uint64_t* seq_base,
+                                const uint8_t* symbols, const uint64_t* offsets, uint64_t nq,
+                                int edit, uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l,
+                                const uint32_t* u, const uint32_t* partition,
+                                fmb_loc32* out, uint64_t part_capacity, uint64_t* n_out /* n_index_parts */, fmb_stats* stats);
 
 /* Exact-search kernel selection.  FMB_EXACT_AUTO (default): two-symbol steps on the 128-byte pair table when the
  * index has one (sigma <= 5), else one-symbol steps.  FMB_EXACT_ONE_SYMBOL: the one-symbol kernel, which also fills

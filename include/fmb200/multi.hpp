@@ -108,4 +108,76 @@ public:
     }
 };
 
+// A collection too large for one index (n >= 2^32 - 64 rows: the reference switches to 64-bit suffix arrays, utils.h:243-247; the
+// device image keeps 32-bit rows): the sequences are split, in order, into parts of at most `max_part_symbols` symbols (delimiters
+// included), one BiFMIndex per part, parts placed round-robin on `n_devices` devices (several parts on one device need an image budget
+// that lets them fit: fmb_set_image_budget).  search_and_locate searches the whole batch in every part (fmb_search_and_locate_parts)
+// and returns the located rows with the sequence numbers of the whole collection -- the rows one index over everything would return,
+// as a multiset, grouped by part.
+template <size_t Sigma>
+struct PartitionedBiFMIndex {
+    std::vector<BiFMIndex<Sigma>> parts;
+    std::vector<uint64_t> seq_base;             // number of the first sequence of every part
+
+    static constexpr uint64_t kMaxPartSymbols = 0xFFFFFFFFull - 64;
+
+    template <Sequences sequences_t>
+    PartitionedBiFMIndex(sequences_t const& sequences, size_t samplingRate, uint64_t max_part_symbols = kMaxPartSymbols - 1,
+                         int n_devices = fmb_device_count()) {
+        if (n_devices < 1) throw std::runtime_error("fmb200: no CUDA device (libfmb200 has no CPU fallback)");
+        if (max_part_symbols >= kMaxPartSymbols) max_part_symbols = kMaxPartSymbols - 1;
+        auto first = std::ranges::begin(sequences);
+        auto const end = std::ranges::end(sequences);
+        uint64_t seq_no = 0;
+        while (first != end) {
+            auto last = first;
+            uint64_t symbols = 0, count = 0;
+            while (last != end && (count == 0 || symbols + std::ranges::size(*last) + 1 <= max_part_symbols)) {
+                symbols += std::ranges::size(*last) + 1;
+                ++last;
+                ++count;
+            }
+            if (symbols > kMaxPartSymbols - 1) throw std::runtime_error("fmb200: one sequence alone exceeds 2^32 - 64 symbols");
+            std::vector<std::vector<uint8_t>> group;
+            for (auto it = first; it != last; ++it) group.emplace_back(std::ranges::begin(*it), std::ranges::end(*it));
+            seq_base.push_back(seq_no);
+            parts.emplace_back(group, samplingRate, 1, static_cast<int>(parts.size() % static_cast<size_t>(n_devices)));
+            seq_no += count;
+            first = last;
+        }
+    }
+    size_t size() const {
+        size_t n = 0;
+        for (auto const& p : parts) n += p.size();
+        return n;
+    }
+
+    template <Sequences queries_t, detail::SchemeLike scheme_t = search_scheme::Scheme>
+    std::vector<fmb_loc32> search_and_locate(queries_t const& queries, bool edit = false, scheme_t const* scheme = nullptr,
+                                             std::vector<size_t> const* partition = nullptr, fmb_stats* stats = nullptr) const {
+        auto flat = flatten(queries);
+        detail::FlatScheme fs;
+        if (scheme) fs = detail::flatten(*scheme, *partition);
+        size_t const P = parts.size();
+        std::vector<fmb_index const*> handles;
+        for (auto const& p : parts) handles.push_back(p.handle());
+        size_t cap = std::max<size_t>(flat.size() * 2, 1024);
+        std::vector<uint64_t> n_out(P);
+        for (;;) {
+            std::vector<fmb_loc32> out(cap * P);
+            int rc = fmb_search_and_locate_parts(handles.data(), static_cast<uint32_t>(P), seq_base.data(), flat.symbols.data(), flat.offsets.data(), flat.size(),
+                                                 edit ? 1 : 0, fs.n_searches, fs.n_parts, fs.pi.data(), fs.l.data(), fs.u.data(), fs.partition.data(), out.data(), cap,
+                                                 n_out.data(), stats);
+            if (rc == FMB_EOVERFLOW) {
+                size_t const need = *std::max_element(n_out.begin(), n_out.end());
+                if (need > cap) { cap = need; continue; }
+            }
+            check(rc);
+            std::vector<fmb_loc32> all;
+            for (size_t g = 0; g < P; ++g) all.insert(all.end(), out.begin() + g * cap, out.begin() + g * cap + n_out[g]);
+            return all;
+        }
+    }
+};
+
 }  // namespace fmb200

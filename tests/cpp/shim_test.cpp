@@ -332,6 +332,21 @@ int main() {
         CHECK(rows.size() == ref.size() && !rows.empty());
         for (size_t i = 0; i < rows.size() && i < ref.size(); ++i) CHECK(rows[i].qidx == ref[i].qidx && rows[i].seq == ref[i].seq && rows[i].pos == ref[i].pos && rows[i].e == ref[i].e);
     }
+    // ---- a collection split into parts (the capacity path for n >= 2^32 rows): here at most 61000 symbols per part -> {seq 0}, {seq 1, 2}
+    {
+        fmb200::PartitionedBiFMIndex<5> pidx{seqs, 8, /*max_part_symbols*/ 61000, /*n_devices*/ 1};
+        CHECK(pidx.parts.size() == 2 && pidx.seq_base == (std::vector<uint64_t>{0, 1}) && pidx.size() == index.size());
+        auto [scheme, partition] = fmb200::search_scheme::facadeScheme<true>(1, 40);
+        auto rows = pidx.search_and_locate(queries, true, &scheme, &partition);
+        auto ref = fmb200::search_and_locate_bulk(index, queries, true, &scheme, &partition);
+        auto key = [](fmb_loc32 const& a, fmb_loc32 const& b) { return std::tie(a.qidx, a.seq, a.pos, a.e) < std::tie(b.qidx, b.seq, b.pos, b.e); };
+        std::sort(rows.begin(), rows.end(), key);
+        std::sort(ref.begin(), ref.end(), key);
+        CHECK(rows.size() == ref.size() && !rows.empty());
+        bool same = rows.size() == ref.size();
+        for (size_t i = 0; same && i < rows.size(); ++i) same = rows[i].qidx == ref[i].qidx && rows[i].seq == ref[i].seq && rows[i].pos == ref[i].pos && rows[i].e == ref[i].e;
+        CHECK(same);
+    }
     fmo_index_free(o);
     std::printf("shim_test: %d checks, %d failed\n", g_checks, g_fail);
     return g_fail ? 1 : 0;

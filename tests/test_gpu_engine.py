@@ -144,3 +144,36 @@ def test_replicated_index_and_sharded_call_on_two_gpus(gpu, dna):
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
     assert hits_equal(r.search_exact(r.upload(sym, off)).hits(), o.search_exact(sym, off))
     _check_multi(gpu, [g, r], o, sym, off)
+
+
+def test_collection_split_into_parts_returns_the_rows_of_one_index(gpu):
+    """fmb_search_and_locate_parts (the capacity path for n >= 2^32 rows): sequences split into three indices, the whole batch searched in
+    every part, sequence numbers of the whole collection -- the located rows equal those of one index over everything"""
+    from fmb200 import capi, schemes, synth
+    lens = [9000, 400, 7000, 30, 5000, 6000, 1200]
+    text = synth.multi_text(lens, 5, 77)
+    o, whole = make_index_pair(gpu, text, 5, 8)
+    ends = np.flatnonzero(text == 0) + 1
+    cuts = [0, int(ends[1]), int(ends[4]), int(ends[6])]          # parts of 2, 3 and 2 sequences
+    seq_base = [0, 2, 5]
+    parts = [gpu.Index.build(5, text[a:b], sampling_rate=8, device=0) for a, b in zip(cuts[:-1], cuts[1:])]
+    reads, _ = synth.reads_from_text(text, 1500, 40, 9)
+    reads = [r for r in reads if 0 not in r][:1200]
+    reads[600:] = synth.plant_errors(np.array(reads[600:], dtype=np.uint8), 5, 1, True, 4)
+    sym, off = synth.flatten(reads)
+    sch, part = schemes.optimum(0, 1), schemes.uniform_partition(2, 40)
+    for scheme, edit in ((None, False), (sch, True), (sch, False)):
+        rows, st = capi.search_and_locate_parts(parts, seq_base, sym, off, scheme=scheme, partition=part, edit=edit)
+        assert len(rows) == 3 and all(r.size for r in rows)
+        for p, r in enumerate(rows):                    # part p only reports its own sequences
+            hi = seq_base[p + 1] if p + 1 < 3 else len(lens)
+            assert r["seq"].min() >= seq_base[p] and r["seq"].max() < hi
+        exp = o.locate(o.search_exact(sym, off) if scheme is None else o.search_ng26(sym, off, scheme, part, edit))
+        assert locs_equal(np.concatenate(rows), exp)
+        one, _ = whole.search_and_locate(sym, off, scheme=scheme, partition=part, edit=edit)
+        assert locs_equal(np.concatenate(rows), one)
+    with pytest.raises(gpu.FmbError) as e:
+        capi.search_and_locate_parts(parts, seq_base, sym, off, part_capacity=5)
+    assert e.value.code == -6
+    with pytest.raises(gpu.FmbError):
+        capi.search_and_locate_parts([parts[0], parts[0]], [0, 2], sym, off)

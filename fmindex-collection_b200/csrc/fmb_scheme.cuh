@@ -137,12 +137,34 @@ struct SchemeOut {
     unsigned long long* hit_keys;
     unsigned long long* overflow_keys;
     const unsigned long long* in_keys;
-    // hit limit n = 1: best_keys[q] = smallest discovery-order key of a hit of query q found so far (all ones: none); subtrees whose
-    // smallest possible key is larger cannot hold the first hit and are dropped.  n_queries > 0 additionally orders the roots search
-    // by search (all queries' search 0, then search 1, ...), so that the later searches of a query start after its earlier hits exist.
+    // hit limit n <= kMaxPruneN: best_keys[q * prune_n + i] = the (i + 1)-th smallest discovery-order key among the rows of query q found
+    // so far (all ones: none; a hit of len rows counts min(len, n) times); subtrees whose smallest possible key is larger than the n-th
+    // cannot hold one of the first n rows and are dropped.  n_queries > 0 additionally orders the roots search by search (all queries'
+    // search 0, then search 1, ...), so that the later searches of a query start after its earlier hits exist.
     unsigned long long* best_keys;
     uint64_t n_queries;
+    uint32_t prune_n;
 };
+constexpr uint32_t kMaxPruneN = 8;
+
+// the key no later row of query q can exceed and still be among its first n rows
+__device__ __forceinline__ unsigned long long prune_bound(const SchemeOut& out, uint32_t qidx) {
+    return __ldcg(out.best_keys + (size_t)qidx * out.prune_n + (out.prune_n - 1));
+}
+// A row with key `key` was found: bubble it into the query's n smallest.  Every step is one atomicMin whose displaced (larger) value is
+// carried to the next slot, so the slots only ever decrease and the multiset {slots, values in flight} is preserved: whenever slot n-1
+// holds x, slots 0 .. n-2 hold -- now and later -- other rows with keys <= x, i.e. x is a valid bound at any moment, not only at rest.
+__device__ __forceinline__ void prune_insert(const SchemeOut& out, uint32_t qidx, unsigned long long key, uint32_t copies) {
+    unsigned long long* slots = out.best_keys + (size_t)qidx * out.prune_n;
+    copies = copies < out.prune_n ? copies : out.prune_n;
+    for (uint32_t c = 0; c < copies; ++c) {
+        unsigned long long k = key;
+        for (uint32_t i = c; i < out.prune_n && k != ~0ull; ++i) {
+            const unsigned long long old = atomicMin(slots + i, k);
+            k = old > k ? old : k;
+        }
+    }
+}
 
 // smallest discovery-order key a descendant of a node (e errors so far, depth = steps + e) can end with: the slots of errors still to
 // come hold at least the code of an insertion at the node itself (the only codes below "no further error"; edit distance only)
@@ -486,8 +508,8 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         }
                         if constexpr (ORDERED) {
                             rkey = order_key_root(sp, s);
-                            // a hit of an earlier search of this query exists: this search cannot hold the first hit
-                            if (out.best_keys != nullptr && (rkey & (0xFFull << 56)) > __ldcg(out.best_keys + st.qidx)) st.len = 0;
+                            // n rows of earlier searches of this query exist: this search cannot hold one of the first n
+                            if (out.best_keys != nullptr && (rkey & (0xFFull << 56)) > prune_bound(out, st.qidx)) st.len = 0;
                         }
                         it = pack_item(st);
                     }
@@ -525,7 +547,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
             st = unpack_item(stack[top - 1 - lane]);
             if constexpr (ORDERED) {
                 st.key = kstack[top - 1 - lane];
-                if (out.best_keys != nullptr && order_key_lower_bound<EDIT>(sp, st.key, st.steps, st.e) > __ldcg(out.best_keys + st.qidx))
+                if (out.best_keys != nullptr && order_key_lower_bound<EDIT>(sp, st.key, st.steps, st.e) > prune_bound(out, st.qidx))
                     st.len = 0;                                  // every hit below this node comes after one already found: drop the subtree
             }
         }
@@ -917,7 +939,7 @@ __global__ void __launch_bounds__(256, FMB_SCHEME_MINB) scheme_search_kernel(con
                         out.hits[idx] = h;
                         if constexpr (ORDERED) {
                             out.hit_keys[idx] = st.key;
-                            if (out.best_keys != nullptr) atomicMin(out.best_keys + st.qidx, st.key);
+                            if (out.best_keys != nullptr) prune_insert(out, st.qidx, st.key, st.len);
                         }
                     }
                 }

@@ -306,10 +306,11 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
         FMB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tsort_bytes, tkeys[0].p, tkeys[1].p, tidx[0].p, tidx[1].p, (int64_t)ovf_cap, 0, 10, active_stream(ix)));
         FMB_TRY(tsort_tmp.alloc(tsort_bytes));
     }
-    // hit limit 1 (first hit per query): the kernel keeps the smallest key found per query and drops what cannot beat it
+    // small hit limits (n <= 8 rows per query): the kernel keeps the n smallest keys found per query and drops what cannot beat the n-th
     DevBuf<unsigned long long> best_keys;
-    const bool prune_first = ordered && n_limit == 1 && getenv("FMB_NO_FIRST_HIT_PRUNING") == nullptr;
-    if (prune_first) FMB_TRY(best_keys.alloc(std::max<uint64_t>(nq, 1)));
+    const bool prune_first = ordered && n_limit >= 1 && n_limit <= kMaxPruneN && getenv("FMB_NO_FIRST_HIT_PRUNING") == nullptr;
+    const uint64_t n_best = std::max<uint64_t>(nq, 1) * (prune_first ? n_limit : 1);
+    if (prune_first) FMB_TRY(best_keys.alloc(n_best));
     if (ordered) {
         FMB_TRY(ovf_keys[0].alloc(ovf_cap));
         FMB_TRY(ovf_keys[1].alloc(ovf_cap));
@@ -335,9 +336,10 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
         so.root_counter = ctr.p + 6;
         so.qidx_base = (uint32_t)q->qidx_base;
         if (prune_first) {
-            FMB_CUDA(cudaMemsetAsync(best_keys.p, 0xFF, std::max<uint64_t>(nq, 1) * sizeof(unsigned long long), st));
+            FMB_CUDA(cudaMemsetAsync(best_keys.p, 0xFF, n_best * sizeof(unsigned long long), st));
             so.best_keys = best_keys.p;
             so.n_queries = nq;
+            so.prune_n = (uint32_t)n_limit;
         }
         if (text_mode) {
             so.text = text_list.p;

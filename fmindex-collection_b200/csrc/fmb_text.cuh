@@ -26,7 +26,7 @@ namespace fmb {
 
 constexpr int kTextWords = 9;        // window words per lane: 144 symbols (2-bit codes) / 36 symbols (bytes)
 constexpr int kTextQWords = 10;      // query words per lane, walking order: 160 / 40 symbols
-constexpr int kTextStage = 64;       // staged items per warp before they are flushed to the global list
+constexpr int kTextStage = 64;       // staged items (and hits) per warp before they are flushed to the global lists (flushed at 32)
 constexpr int kTextStack = 16;       // private depth-first stack (packed nodes)
 #ifndef FMB_TEXT_BULK2
 #define FMB_TEXT_BULK2 1
@@ -39,6 +39,10 @@ constexpr bool kPrefetch = FMB_TEXT_PREFETCH != 0;
 #ifndef FMB_TEXT_MINB
 #define FMB_TEXT_MINB 4
 #endif
+#ifndef FMB_TEXT_REPORTS
+#define FMB_TEXT_REPORTS 1         // leaves are reported by the text kernel instead of going back to the frontier kernel as items
+#endif
+constexpr bool kTextReports = FMB_TEXT_REPORTS != 0;
 
 struct TNode {             // one pending node, "ready to expand" (the position advance already applied)
     uint32_t m;            // text symbols consumed since the item started: the node looks at window symbol m
@@ -75,6 +79,19 @@ static_assert(kTextWords * 16 <= 255 && kTextQWords * 16 <= 255, "window / query
 __device__ __forceinline__ uint32_t rev2(uint32_t w) {
     w = __brev(w);
     return ((w & 0xAAAAAAAAu) >> 1) | ((w & 0x55555555u) << 1);
+}
+
+// a hit in the slot of an item (the warp stage of scheme_text_kernel holds both): meta = kHitMark cannot be an item (mode 3 does not exist)
+constexpr uint32_t kHitMark = 0xFFFFFFFFu;
+__device__ __forceinline__ Item item_of_hit(const HitRec& h) {
+    Item it;
+    it.lb = h.lb; it.lb_rev = h.lb_rev; it.len = h.len; it.qidx = h.qidx; it.qpos = h.steps; it.pev_steps = h.e; it.meta = kHitMark; it.side = 0;
+    return it;
+}
+__device__ __forceinline__ HitRec hit_of_item(const Item& it) {
+    HitRec h;
+    h.qidx = it.qidx; h.lb = it.lb; h.lb_rev = it.lb_rev; h.len = it.len; h.steps = it.qpos; h.e = it.pev_steps;
+    return h;
 }
 
 // Edit distance, TWO errors left, inside the part, after a match (2-bit symbols).  At a matching position c (text position m) the
@@ -174,7 +191,7 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
 
     __shared__ uint32_t sw[(kTextWords + 1) * 256];      // [word][thread]: window symbols in walking order, one zero word behind
     __shared__ uint32_t sq[(kTextQWords + 1) * 256];     // [word][thread]: query symbols in walking order
-    __shared__ Item stage[8][kTextStage];
+    __shared__ Item stage[8][kTextStage];                // hand-overs AND hits (a hit travels as an item with meta = kHitMark) of a warp
     __shared__ uint32_t stage_cnt[8];
 
     const uint32_t tid = threadIdx.x;
@@ -202,8 +219,14 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
             stage[warp][slot] = it;
         } else {
             atomicSub(&stage_cnt[warp], 1u);
-            const unsigned long long g = atomicAdd(out.overflow_count, 1ull);
-            if (g < out.overflow_capacity) out.overflow[g] = it;
+            if (it.meta == kHitMark) {
+                const unsigned long long g = atomicAdd(out.hit_count, 1ull);
+                atomicAdd(out.row_count, 1ull);
+                if (g < out.hit_capacity) out.hits[g] = hit_of_item(it);
+            } else {
+                const unsigned long long g = atomicAdd(out.overflow_count, 1ull);
+                if (g < out.overflow_capacity) out.overflow[g] = it;
+            }
         }
     };
     // one LF step of a single row in direction R
@@ -334,11 +357,33 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
             const uint32_t n = stage_cnt[warp];
             const bool all_done = !__any_sync(0xFFFFFFFFu, busy || wants);
             if (n >= 32 || (all_done && n > 0)) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(out.overflow_count, (unsigned long long)n);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                for (uint32_t i = lane; i < n; i += 32)
-                    if (base + i < out.overflow_capacity) out.overflow[base + i] = stage[warp][i];
+                // hand-overs go to the overflow list, hits to the hit list: one counter update per kind and 32 entries
+                for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    Item it{};
+                    if (i < n) it = stage[warp][i];
+                    const bool is_hit = i < n && it.meta == kHitMark, is_item = i < n && it.meta != kHitMark;
+                    const uint32_t hb = __ballot_sync(0xFFFFFFFFu, is_hit), ib = __ballot_sync(0xFFFFFFFFu, is_item);
+                    unsigned long long hbase = 0, ibase = 0;
+                    if (lane == 0) {
+                        if (ib) ibase = atomicAdd(out.overflow_count, (unsigned long long)__popc(ib));
+                        if (hb) {
+                            hbase = atomicAdd(out.hit_count, (unsigned long long)__popc(hb));
+                            atomicAdd(out.row_count, (unsigned long long)__popc(hb));
+                        }
+                    }
+                    hbase = __shfl_sync(0xFFFFFFFFu, hbase, 0);
+                    ibase = __shfl_sync(0xFFFFFFFFu, ibase, 0);
+                    const uint32_t below = (1u << lane) - 1u;
+                    if (is_item) {
+                        const unsigned long long g = ibase + __popc(ib & below);
+                        if (g < out.overflow_capacity) out.overflow[g] = it;
+                    }
+                    if (is_hit) {
+                        const unsigned long long g = hbase + __popc(hb & below);
+                        if (g < out.hit_capacity) out.hits[g] = hit_of_item(it);
+                    }
+                }
                 __syncwarp();
                 if (lane == 0) stage_cnt[warp] = 0;
                 __syncwarp();
@@ -359,14 +404,28 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                     const uint32_t row = row_at(s.m);
                     if (R) ch.lb_rev = row; else ch.lb = row;
                     ch.steps += s.m;
-                    if (R) ch.qposR = (ch.qposR + s.c) & 0xFFFF; else ch.qposL = (ch.qposL - s.c) & 0xFFFF;
-                    ch.part = s.part; ch.pev = s.pev; ch.e = s.e;
                     if (R) ch.RInfo = s.T; else ch.LInfo = s.T;
-                    ch.side = side_set(side_set(ch.side, R, 0, s.lastRank), R, 1, s.lastQRank);
-                    ch.mode = s.kind == TN_TURN ? MODE_POS : (s.kind == TN_NEXT ? MODE_NEXT : (s.noerr ? MODE_NOERR : MODE_POS));
-                    ch.NextPos = s.kind == TN_TURN ? 1u : 0u;
-                    ch.Right = R; ch.notext = 0;
-                    stage_emit(pack_item(ch));
+                    // a hand-over that ends the search (the last part is over: search_next, :98-117) is a leaf: reported here (staged per
+                    // warp) instead of travelling to the frontier kernel as an item.  (Measured and dropped: letting the lane continue
+                    // with one of its own hand-overs -- a new direction run in the same lane -- instead of the next pass: the warps then
+                    // mix the classes the host sorted them by, k = 1 / 2 edit 18.8 -> 21.9 / 67.0 -> 82.5 ms.)
+                    const bool leaf = kTextReports && (s.kind == TN_TURN ? s.part + 1 == np : (s.kind == TN_NEXT && s.part == np));
+                    if (leaf) {
+                        const bool ok = !EDIT || PSEUDO || ((ch.LInfo == INFO_M || ch.LInfo == INFO_I) && (ch.RInfo == INFO_M || ch.RInfo == INFO_I));
+                        if (ok && sp.l[search][np - 1] <= s.e && s.e <= sp.u[search][np - 1]) {
+                            HitRec h;
+                            h.qidx = ch.qidx + out.qidx_base; h.lb = ch.lb; h.lb_rev = sp.zero_lb_rev ? 0 : ch.lb_rev; h.len = 1; h.steps = ch.steps; h.e = s.e;
+                            stage_emit(item_of_hit(h));
+                        }
+                    } else {
+                        if (R) ch.qposR = (ch.qposR + s.c) & 0xFFFF; else ch.qposL = (ch.qposL - s.c) & 0xFFFF;
+                        ch.part = s.part; ch.pev = s.pev; ch.e = s.e;
+                        ch.side = side_set(side_set(ch.side, R, 0, s.lastRank), R, 1, s.lastQRank);
+                        ch.mode = s.kind == TN_TURN ? MODE_POS : (s.kind == TN_NEXT ? MODE_NEXT : (s.noerr ? MODE_NOERR : MODE_POS));
+                        ch.NextPos = s.kind == TN_TURN ? 1u : 0u;
+                        ch.Right = R; ch.notext = 0;
+                        stage_emit(pack_item(ch));
+                    }
                 }
             }
             nreq = 0;

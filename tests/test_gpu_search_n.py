@@ -191,3 +191,34 @@ def test_first_hit_limit_bounds_the_work(gpu, edit):
     assert _same_list(first.hits(), exp)
     everything = g.search_scheme(q, sch, part, edit, n=10**9)
     assert first.stats.extensions < 0.9 * everything.stats.extensions, (first.stats.extensions, everything.stats.extensions)
+    # small limits n <= 8: the n smallest keys per query are kept, the n-th is the bound; n = 9 bounds the output only
+    few = g.search_scheme(q, sch, part, edit, n=3)
+    assert _same_list(few.hits(), o.search_ng26(sym, off, sch, part, edit, max_hits=3))
+    assert few.stats.extensions <= everything.stats.extensions          # (most reads have fewer than three rows: little to cut)
+    nine = g.search_scheme(q, sch, part, edit, n=9)
+    assert _same_list(nine.hits(), o.search_ng26(sym, off, sch, part, edit, max_hits=9))
+    assert nine.stats.extensions == everything.stats.extensions
+
+
+def test_small_hit_limits_on_repeats_count_rows_not_hits(gpu):
+    """a repetitive text: single hits cover many rows, so one hit can fill the limit (a hit of len rows counts min(len, n) times in the
+    per-query bound) -- the clipped lists still equal the oracle's for every small n, Hamming and edit distance"""
+    from fmb200 import schemes, synth
+    unit = synth.text(600, 5, 3)[:-1]
+    rng = np.random.default_rng(12)
+    copies = []
+    for _ in range(40):
+        c = unit.copy()
+        for p in rng.integers(0, c.size, 6):
+            c[p] = 1 + (c[p] + int(rng.integers(0, 3))) % 4
+        copies.append(c)
+    text = np.concatenate(copies + [np.zeros(1, dtype=np.uint8)]).astype(np.uint8)
+    o, g = make_index_pair(gpu, text, 5, 8)
+    reads, _ = synth.reads_from_text(text, 3000, 36, 5)
+    sym, off = synth.flatten(reads)
+    q = g.upload(sym, off)
+    sch, part = schemes.optimum(0, 2), schemes.uniform_partition(4, 36)
+    for edit in (False, True):
+        for n in (1, 2, 4, 8):
+            got = g.search_scheme(q, sch, part, edit, n=n)
+            assert _same_list(got.hits(), o.search_ng26(sym, off, sch, part, edit, max_hits=n)), (edit, n)

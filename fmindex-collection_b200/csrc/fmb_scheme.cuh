@@ -133,6 +133,10 @@ struct SchemeOut {
     Item* text;
     unsigned long long* text_count;
     uint64_t text_capacity;
+    // text kernel only: the text list of the NEXT pass -- its text-class hand-overs (a new direction run, a new window) go there
+    // directly instead of through the overflow list and a routing launch of the frontier kernel (null: everything to the overflow list)
+    Item* text_next;
+    unsigned long long* text_next_count;
     // ordered mode: keys of the hits / the spilled items / the items fed in
     unsigned long long* hit_keys;
     unsigned long long* overflow_keys;

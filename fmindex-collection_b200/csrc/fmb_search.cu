@@ -295,10 +295,14 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     size_t tsort_bytes = 0;
     static const bool sort_text = getenv("FMB_NO_TEXT_SORT") == nullptr;
     DevBuf<unsigned long long> ovf_keys[2], hit_keys;
-    DevBuf<unsigned long long> ctr;          // [0..3] counters, [4] hit_count, [5] overflow_count, [6] root_counter, [7] text_count, [8] row_count
+    DevBuf<unsigned long long> ctr;          // [0..3] counters, [4] hit_count, [5] overflow_count, [6] root_counter, [7] / [9] text_count of the two text lists, [8] row_count
     FMB_TRY(ovf[0].alloc(ovf_cap));
     FMB_TRY(ovf[1].alloc(ovf_cap));
     if (text_mode) FMB_TRY(text_list.alloc(ovf_cap));
+    // the text kernel appends its text-class hand-overs to the list of the next pass (two lists, swapped after every text launch)
+    DevBuf<Item> text_list2;
+    static const bool direct_text = getenv("FMB_NO_DIRECT_TEXT") == nullptr;
+    if (text_mode && direct_text) FMB_TRY(text_list2.alloc(ovf_cap));
     if (text_mode && sort_text && (sp.edit || getenv("FMB_TEXT_SORT_HAMMING"))) {
         // (edit distance only: the Hamming walk has one shape whatever the class)
         FMB_TRY(text_sorted.alloc(ovf_cap));
@@ -341,17 +345,24 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
             so.n_queries = nq;
             so.prune_n = (uint32_t)n_limit;
         }
+        Item* tlist[2] = {text_list.p, text_list2.p};
+        unsigned long long* tcount[2] = {ctr.p + 7, ctr.p + 9};
+        int tcur = 0;                               // the list the frontier kernel fills and the text kernel reads
         if (text_mode) {
-            so.text = text_list.p;
-            so.text_count = ctr.p + 7;
+            so.text = tlist[0];
+            so.text_count = tcount[0];
             so.text_capacity = ovf_cap;
+            if (text_list2.p) { so.text_next = tlist[1]; so.text_next_count = tcount[1]; }
         }
         cudaEventRecord(ev0, st);
         for (uint64_t root_base = 0; root_base < std::max<uint64_t>(n_roots, 1); root_base += slab) {
             uint64_t roots = n_roots ? std::min<uint64_t>(slab, n_roots - root_base) : 0, n_in = 0;
             int cur = 0;
             so.root_base = root_base;
-            if (root_base) FMB_CUDA(cudaMemsetAsync(ctr.p + 5, 0, 3 * sizeof(unsigned long long), st));   // overflow_count, root_counter, text_count
+            if (root_base) {
+                FMB_CUDA(cudaMemsetAsync(ctr.p + 5, 0, 3 * sizeof(unsigned long long), st));   // overflow_count, root_counter, text_count
+                FMB_CUDA(cudaMemsetAsync(ctr.p + 9, 0, sizeof(unsigned long long), st));
+            }
             for (int pass = 0;; ++pass) {
                 so.overflow = ovf[cur].p;
                 so.overflow_keys = ovf_keys[cur].p;
@@ -375,49 +386,59 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
                     float ms = 0;
                     cudaEventElapsedTime(&ms, tr.a, tr.b);
                     fprintf(stderr, "[fmb scheme] slab %llu pass %d frontier kernel: %.3f ms, %llu roots + %llu items in -> %llu text, %llu back, %llu hits so far\n",
-                            (unsigned long long)root_base, pass, ms, (unsigned long long)roots, (unsigned long long)n_in, h_ctr[7], h_ctr[5], h_ctr[4]);
+                            (unsigned long long)root_base, pass, ms, (unsigned long long)roots, (unsigned long long)n_in, h_ctr[tcur ? 9 : 7], h_ctr[5], h_ctr[4]);
                 }
-                if (h_ctr[5] > ovf_cap || h_ctr[7] > ovf_cap) {
+                const int ti = tcur ? 9 : 7, tn = tcur ? 7 : 9;      // counters of the current / the next text list
+                if (h_ctr[5] > ovf_cap || h_ctr[ti] > ovf_cap) {
                     set_error("scheme search: frontier lists exceeded %llu items; split the query batch", (unsigned long long)ovf_cap);
                     return FMB_EOVERFLOW;
                 }
-                if (h_ctr[7]) {
-                    // the single-row items of this pass are decided on the text; what survives joins the overflow list
-                    const unsigned long long n_text = h_ctr[7], back0 = h_ctr[5];
+                unsigned long long n_text_next = 0;
+                if (h_ctr[ti]) {
+                    // the single-row items of this pass are decided on the text; what survives joins the next text list (a new direction
+                    // run, a new window) or the overflow list (what must be expanded on the index)
+                    const unsigned long long n_text = h_ctr[ti], back0 = h_ctr[5];
                     if (trace) cudaEventRecord(tr.a, st);
-                    const Item* text_in = text_list.p;
+                    const Item* text_in = tlist[tcur];
                     if (text_sorted.p && n_text > 65536) {
                         const unsigned grid = (unsigned)((n_text + 255) / 256);
-                        text_class_keys_kernel<<<grid, 256, 0, st>>>(text_list.p, n_text, tkeys[0].p, tidx[0].p);
+                        text_class_keys_kernel<<<grid, 256, 0, st>>>(tlist[tcur], n_text, tkeys[0].p, tidx[0].p);
                         FMB_CUDA(cub::DeviceRadixSort::SortPairs(tsort_tmp.p, tsort_bytes, tkeys[0].p, tkeys[1].p, tidx[0].p, tidx[1].p, (int64_t)n_text, 0, 10, st));
-                        gather_items_kernel<<<grid, 256, 0, st>>>(text_list.p, tidx[1].p, n_text, text_sorted.p);
+                        gather_items_kernel<<<grid, 256, 0, st>>>(tlist[tcur], tidx[1].p, n_text, text_sorted.p);
                         FMB_CUDA(cudaGetLastError());
                         note_launches(3);
                         text_in = text_sorted.p;
                     }
                     FMB_TRY(launch_text(ix, sp, q, text_in, n_text, so, pseudo, st));
                     if (trace) cudaEventRecord(tr.b, st);
-                    FMB_CUDA(cudaMemsetAsync(ctr.p + 7, 0, sizeof(unsigned long long), st));
+                    FMB_CUDA(cudaMemsetAsync(ctr.p + ti, 0, sizeof(unsigned long long), st));
                     FMB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
                     FMB_CUDA(cudaStreamSynchronize(st));
-                    h_ctr[7] = 0;
+                    h_ctr[ti] = 0;
+                    n_text_next = text_list2.p ? h_ctr[tn] : 0;
                     if (trace) {
                         float ms = 0;
                         cudaEventElapsedTime(&ms, tr.a, tr.b);
-                        fprintf(stderr, "[fmb scheme] slab %llu pass %d text kernel: %.3f ms, %llu items -> %llu back\n", (unsigned long long)root_base, pass, ms,
-                                n_text, h_ctr[5] - back0);
+                        fprintf(stderr, "[fmb scheme] slab %llu pass %d text kernel: %.3f ms, %llu items -> %llu to the next text list, %llu back\n",
+                                (unsigned long long)root_base, pass, ms, n_text, n_text_next, h_ctr[5] - back0);
                     }
-                    if (h_ctr[5] > ovf_cap) {
+                    if (text_list2.p) {                     // the lists swap roles: the frontier kernel of the next pass appends to what the text kernel began
+                        tcur ^= 1;
+                        so.text = tlist[tcur]; so.text_count = tcount[tcur];
+                        so.text_next = tlist[tcur ^ 1]; so.text_next_count = tcount[tcur ^ 1];
+                    }
+                    if (h_ctr[5] > ovf_cap || n_text_next > ovf_cap) {
                         set_error("scheme search: frontier lists exceeded %llu items; split the query batch", (unsigned long long)ovf_cap);
                         return FMB_EOVERFLOW;
                     }
                 }
-                if (h_ctr[5] == 0) break;
+                if (h_ctr[5] == 0 && n_text_next == 0) break;
                 // feed the spilled / returned items to the next pass
                 n_in = h_ctr[5];
                 roots = 0;
                 cur ^= 1;
-                FMB_CUDA(cudaMemsetAsync(ctr.p + 5, 0, 3 * sizeof(unsigned long long), st));   // overflow_count, root_counter, text_count
+                FMB_CUDA(cudaMemsetAsync(ctr.p + 5, 0, 2 * sizeof(unsigned long long), st));   // overflow_count, root_counter
+                if (!text_list2.p) FMB_CUDA(cudaMemsetAsync(ctr.p + 7, 0, sizeof(unsigned long long), st));
                 if (pass > 100000) { set_error("scheme search did not terminate"); return FMB_ECUDA; }
             }
         }

@@ -362,10 +362,15 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                     const uint32_t i = i0 + lane;
                     Item it{};
                     if (i < n) it = stage[warp][i];
-                    const bool is_hit = i < n && it.meta == kHitMark, is_item = i < n && it.meta != kHitMark;
-                    const uint32_t hb = __ballot_sync(0xFFFFFFFFu, is_hit), ib = __ballot_sync(0xFFFFFFFFu, is_item);
-                    unsigned long long hbase = 0, ibase = 0;
+                    const bool is_hit = i < n && it.meta == kHitMark;
+                    // text class again (every hand-over is a single row of an unflagged query and not a leaf): not flagged `notext`, and
+                    // not an error-free stretch of the generic layout (those stay in the frontier kernel, text_class())
+                    const bool is_text = i < n && !is_hit && out.text_next != nullptr && !(it.meta & 0x80u) && !(BYTES && ((it.meta >> 24) & 3u) == MODE_NOERR);
+                    const bool is_item = i < n && !is_hit && !is_text;
+                    const uint32_t hb = __ballot_sync(0xFFFFFFFFu, is_hit), ib = __ballot_sync(0xFFFFFFFFu, is_item), tb = __ballot_sync(0xFFFFFFFFu, is_text);
+                    unsigned long long hbase = 0, ibase = 0, tbase = 0;
                     if (lane == 0) {
+                        if (tb) tbase = atomicAdd(out.text_next_count, (unsigned long long)__popc(tb));
                         if (ib) ibase = atomicAdd(out.overflow_count, (unsigned long long)__popc(ib));
                         if (hb) {
                             hbase = atomicAdd(out.hit_count, (unsigned long long)__popc(hb));
@@ -374,7 +379,12 @@ __global__ void __launch_bounds__(256, FMB_TEXT_MINB) scheme_text_kernel(const _
                     }
                     hbase = __shfl_sync(0xFFFFFFFFu, hbase, 0);
                     ibase = __shfl_sync(0xFFFFFFFFu, ibase, 0);
+                    tbase = __shfl_sync(0xFFFFFFFFu, tbase, 0);
                     const uint32_t below = (1u << lane) - 1u;
+                    if (is_text) {
+                        const unsigned long long g = tbase + __popc(tb & below);
+                        if (g < out.text_capacity) out.text_next[g] = it;
+                    }
                     if (is_item) {
                         const unsigned long long g = ibase + __popc(ib & below);
                         if (g < out.overflow_capacity) out.overflow[g] = it;

@@ -324,7 +324,9 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
     const cudaEvent_t ev0 = evs.a, ev1 = evs.b;
     double total_ms = 0;
     unsigned long long h_ctr[16];
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    // (a second attempt runs with the exact size the first one counted; with work-bounding hit limits the count depends on the timing of
+    // the pruning, so those retries reserve twice what was counted and may repeat)
+    for (int attempt = 0; attempt < (prune_first ? 5 : 2); ++attempt) {
         FMB_TRY(res->hits.alloc(hit_cap));
         if (ordered) FMB_TRY(hit_keys.alloc(hit_cap));
         FMB_CUDA(cudaMemsetAsync(ctr.p, 0, 16 * sizeof(unsigned long long), st));
@@ -448,10 +450,10 @@ int run_scheme(const fmb_index* ix, const fmb_queries* q, const SchemeParams& sp
         cudaEventElapsedTime(&ms, ev0, ev1);
         total_ms += ms;
         if (h_ctr[4] <= hit_cap) break;
-        hit_cap = h_ctr[4];                  // second attempt with the exact size
+        hit_cap = prune_first ? 2 * h_ctr[4] : h_ctr[4];
     }
     if (h_ctr[4] > hit_cap) {
-        // the second attempt ran with the exact size of the first: only a non-deterministic hit count could get here
+        // (the retries ran with the size counted before: only a hit count that keeps growing between attempts could get here)
         set_error("scheme search: %llu hits do not fit the %llu reserved", h_ctr[4], (unsigned long long)hit_cap);
         return FMB_EOVERFLOW;
     }

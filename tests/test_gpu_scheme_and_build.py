@@ -221,3 +221,28 @@ def test_scheme_work_counters_match_oracle(gpu, edit):
     assert st.extensions == ctr.extensions
     assert abs(int(st.occ_lookups) - int(ctr.occ_lookups)) <= 0.05 * ctr.occ_lookups
     assert 0 < st.line_requests < st.occ_lookups          # the jumps save physical fetches
+
+
+@pytest.mark.parametrize("L", [170, 400, 700])
+def test_long_reads_cross_the_text_window(gpu, L):
+    """reads longer than the text kernel's window (144 symbols) and query words (160 symbols): a direction run is then cut into several
+    items (hand-overs of kind "continue", straight to the next text list); hits and extension counters still equal the oracle's"""
+    from fmb200 import schemes, synth
+    from oracle.pyoracle import Counters
+    text = synth.multi_text([200000, 3000], 5, 14)
+    o, g = make_index_pair(gpu, text, 5, 16)
+    reads, _ = synth.reads_from_text(text[:200001], 400, L, 8)
+    reads[100:250] = synth.plant_errors(reads[100:250], 5, 1, True, 3)
+    reads[250:] = synth.plant_errors(reads[250:], 5, 2, True, 4)
+    sym, off = synth.flatten(reads)
+    q = g.upload(sym, off)
+    for k in (1, 2):
+        sch = schemes.optimum(0, k)
+        part = schemes.uniform_partition(sch[0].shape[1], L)
+        for edit in (False, True):
+            ctr = Counters()
+            exp = o.search_ng26(sym, off, sch, part, edit, counters=ctr)
+            res = g.search_scheme(q, sch, part, edit)
+            assert hits_equal(res.hits(), exp), (L, k, edit)
+            assert res.stats.extensions == ctr.extensions, (L, k, edit)
+            assert len(exp) >= 100

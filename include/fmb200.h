@@ -213,9 +213,9 @@ int fmb_search_scheme(const fmb_index* ix, const fmb_queries* q, int edit,
  * them (searches of the scheme in order, SearchNg26.h:385-390) until n ROWS are reached; the cursor that crosses the
  * limit is clipped to the rows still missing (:414-417).  n = UINT64_MAX: no limit (= fmb_search_scheme); n = 0: no
  * result.  The device enumerates alignments in its own order and orders / cuts afterwards (hits come back sorted by qidx,
- * then discovery order).  n = 1 (first hit per query) also bounds the WORK: the kernel keeps the smallest discovery-order key found
- * per query and drops every subtree that cannot beat it, and it starts the searches of the scheme one after the other; larger n bound
- * the output only.  FMB_EUNSUPPORTED when errors x key width exceed the 56-bit ordering key (e.g. more than 4 errors on
+ * then discovery order).  Small limits (n <= 8) also bound the WORK: the kernel keeps the n smallest discovery-order keys found per
+ * query (a cursor of len rows counts min(len, n) times) and drops every subtree that cannot beat the n-th, and it starts the searches
+ * of the scheme one after the other; larger n bound the output only.  FMB_EUNSUPPORTED when errors x key width exceed the 56-bit ordering key (e.g. more than 4 errors on
  * 150-symbol DNA queries). */
 int fmb_search_scheme_n(const fmb_index* ix, const fmb_queries* q, int edit,
                         uint32_t n_searches, uint32_t n_parts, const uint32_t* pi, const uint32_t* l, const uint32_t* u,

@@ -6,15 +6,17 @@
 // function of (text window, query, scheme): the node state machine of search_ng26 (search_next_pos / search_next_dir_single /
 // search_next_dir_no_errors, search/SearchNg26.h:119-141, 225-365) is run here on the window symbols held in shared memory, with a
 // private depth-first stack per lane, and the index is touched only to fetch the window (one lookup per 16 symbols) and to compute
-// the rows of the few paths that survive.  What leaves the walk goes back to the frontier kernel (scheme_search_kernel) as an item:
+// the rows of the few paths that survive.  What leaves the walk of an item is a hand-over (an item again):
 //   * a child whose position advance ends the last part of the direction run (the search turns around or ends): the child exactly
 //     as search_next_dir_single creates it, advance pending                                                    ("turn" items)
 //   * an error-free stretch that ends a part the same way: the state search_next_dir_no_errors leaves (:241-249)
 //   * a node at the end of the window (144 symbols, a delimiter ahead, or the private stack full): the node as it is ("continue")
 //   * an item whose row has no usable window at all (delimiter within the next 16 symbols): the item itself, flagged `notext`
-// The frontier kernel reports the leaves and routes text-class items back here.  Results are identical by construction: this is the
-// same state machine on the same symbols; fmb_stats.extensions still equals the oracle's count (one per node visit, one per symbol
-// of an error-free stretch).
+// A hand-over that ends the search is a leaf and is reported here; the others are single rows again -- text class -- and go straight
+// to the text list of the next pass (SchemeOut::text_next); only `notext` items (and error-free stretches of the generic layout) go
+// to the overflow list, i.e. to the frontier kernel (scheme_search_kernel), which expands them on the index.  Results are identical
+// by construction: this is the same state machine on the same symbols; fmb_stats.extensions still equals the oracle's count (one per
+// node visit, one per symbol of an error-free stretch).
 //
 // Work distribution: one item per LANE, in a flat loop -- every iteration each lane pops one node of its private stack (or takes its
 // next item when the stack is empty) -- so that the lanes of a warp always execute the same loop body although their items need
